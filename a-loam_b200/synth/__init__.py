@@ -1,0 +1,58 @@
+"""Seeded synthetic lidar scans (VLP-16 / HDL-32 / HDL-64 shaped) -- ctypes binding of synth.cc."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SENSORS = {  # name -> (n_scans, azimuth steps, minimum_range [launch/*.launch], line_res, plane_res)
+    "VLP-16": (16, 1800, 0.3, 0.2, 0.4),
+    "HDL-32": (32, 2200, 0.3, 0.2, 0.4),
+    "HDL-64": (64, 2000, 5.0, 0.4, 0.8),
+}
+BASE_SEED = 20240901
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libaloam_synth.so")
+    src = os.path.join(_HERE, "synth.cc")
+    if force or not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+        subprocess.check_call(["g++", "-std=c++17", "-O3", "-fPIC", "-shared", "-o", so, src, "-lpthread"])
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libaloam_synth.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.synth_scan.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                 C.POINTER(C.c_float), C.c_int]
+        L.synth_pose.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _LIB = L
+    return _LIB
+
+
+def scan(sensor, index, seed=BASE_SEED, n_az=None, noise=0.02, max_range=120.0):
+    """Raw scan `index` of the trajectory: (n, 4) float32 x,y,z,0 in the sensor frame, firing order."""
+    n_scans, az = SENSORS[sensor][0], SENSORS[sensor][1]
+    if n_az is not None:
+        az = n_az
+    out = np.zeros((n_scans * az, 4), np.float32)
+    n = _lib().synth_scan(seed, n_scans, az, index, noise, max_range, out.ctypes.data_as(C.POINTER(C.c_float)), out.shape[0])
+    if n < 0:
+        raise RuntimeError("synth_scan failed: %d" % n)
+    return out[:n].copy()
+
+
+def pose(index):
+    """Ground-truth world pose of scan `index`: (q xyzw, t)."""
+    q = np.zeros(4)
+    t = np.zeros(3)
+    _lib().synth_pose(index, q.ctypes.data_as(C.POINTER(C.c_double)), t.ctypes.data_as(C.POINTER(C.c_double)))
+    return q, t
