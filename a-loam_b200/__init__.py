@@ -1,1 +1,263 @@
-"""aloam-b200: B200-native A-LOAM per-scan registration hot path."""
+"""aloam-b200: B200-native (sm_100a) A-LOAM per-scan registration hot path.
+
+Python here is only a ctypes mirror of the C ABI in include/aloam_b200.h (the reference is C++; its host side is
+C++ inside libaloam_b200.so).  There is no CPU fallback: importing works anywhere (so the symbol table can be
+checked on a CPU box) but creating a context needs a CUDA device and fails loudly without one.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libaloam_b200.so")
+_LIB = None
+
+OK = 0
+FLAG_FEW_CORRESPONDENCES, FLAG_MAP_TOO_THIN, FLAG_INITIALISED_ONLY = 1, 2, 4
+BLOCK_DOUBLES = 11
+
+EXPORTED_SYMBOLS = [
+    "aloam_default_config", "aloam_create", "aloam_destroy", "aloam_strerror", "aloam_extract_features",
+    "aloam_odometry_set_last", "aloam_odometry_register", "aloam_map_upload", "aloam_mapping_register",
+    "aloam_voxel_filter", "aloam_scan_to_pose", "aloam_scan_to_pose_device", "aloam_reset_odometry", "aloam_knn",
+    "aloam_odometry_associate", "aloam_normal_equations", "aloam_solve", "aloam_debug_features",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("n_scans", C.c_int), ("minimum_range", C.c_float), ("line_res", C.c_float), ("plane_res", C.c_float),
+                ("outer_iters", C.c_int), ("inner_iters", C.c_int), ("huber", C.c_double), ("dist_sq_thresh", C.c_double),
+                ("nearby_scan", C.c_double), ("device", C.c_int), ("max_points", C.c_int), ("max_map_points", C.c_int)]
+
+
+class CloudView(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_float)), ("n", C.c_int), ("stride_floats", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_corner_corr", C.c_int), ("n_plane_corr", C.c_int), ("lm_iters", C.c_int), ("accepted_steps", C.c_int),
+                ("flags", C.c_int), ("termination", C.c_int * 4), ("init_cost", C.c_double), ("final_cost", C.c_double),
+                ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {"n_corner_corr": self.n_corner_corr, "n_plane_corr": self.n_plane_corr, "lm_iters": self.lm_iters,
+                "accepted_steps": self.accepted_steps, "flags": self.flags, "termination": list(self.termination),
+                "init_cost": self.init_cost, "final_cost": self.final_cost, "ms_total": self.ms_total}
+
+
+class AloamError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("aloam_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def build(force=False, verbose=False):
+    from . import build as _b  # noqa
+    return _b.build(force=force, verbose=verbose)
+
+
+def lib():
+    """Loads libaloam_b200.so (raises if it has not been built -- there is no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError("libaloam_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(SO_PATH)
+        dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int)
+        L.aloam_default_config.argtypes = [C.POINTER(Config), C.c_int]
+        L.aloam_default_config.restype = None
+        L.aloam_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        L.aloam_destroy.argtypes = [C.c_void_p]
+        L.aloam_strerror.argtypes = [C.c_int]
+        L.aloam_strerror.restype = C.c_char_p
+        cv = CloudView
+        L.aloam_extract_features.argtypes = [C.c_void_p, cv] + [C.POINTER(cv)] * 5
+        L.aloam_odometry_set_last.argtypes = [C.c_void_p, cv, cv]
+        L.aloam_odometry_register.argtypes = [C.c_void_p, cv, cv, dp, dp, C.POINTER(Stats)]
+        L.aloam_map_upload.argtypes = [C.c_void_p, cv, cv]
+        L.aloam_mapping_register.argtypes = [C.c_void_p, cv, cv, dp, C.POINTER(Stats)]
+        L.aloam_voxel_filter.argtypes = [C.c_void_p, cv, C.c_float, C.POINTER(cv)]
+        L.aloam_scan_to_pose.argtypes = [C.c_void_p, cv, dp, dp, C.POINTER(Stats)]
+        L.aloam_scan_to_pose_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp, dp, C.POINTER(Stats)]
+        L.aloam_reset_odometry.argtypes = [C.c_void_p]
+        L.aloam_knn.argtypes = [C.c_void_p, C.c_int, cv, C.c_int, ip, fp]
+        L.aloam_odometry_associate.argtypes = [C.c_void_p, cv, cv, dp, dp, ip, ip]
+        L.aloam_normal_equations.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp, dp]
+        L.aloam_solve.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp, C.c_int, ip]
+        L.aloam_debug_features.argtypes = [C.c_void_p, fp, ip, ip, ip]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise AloamError(rc, lib().aloam_strerror(rc).decode())
+
+
+def _view(a):
+    """numpy (n, 4|8) float32 -> CloudView (keeps `a` alive through the returned tuple)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (4, 8):
+        raise ValueError("clouds are (n, 4) or (n, 8) float32")
+    return CloudView(a.ctypes.data_as(C.POINTER(C.c_float)), a.shape[0], a.shape[1]), a
+
+
+def _out(v):
+    if v.n == 0:
+        return np.zeros((0, 4), np.float32)
+    return np.ctypeslib.as_array(v.data, shape=(v.n, 4)).copy()
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def default_config(n_scans):
+    cfg = Config()
+    lib().aloam_default_config(C.byref(cfg), n_scans)
+    return cfg
+
+
+class Aloam:
+    """One context = one caller thread = one CUDA stream on one B200 (mirrors `aloam_ctx`)."""
+
+    def __init__(self, n_scans=64, device=0, max_points=None, **overrides):
+        cfg = default_config(n_scans)
+        cfg.device = device
+        if max_points is not None:
+            cfg.max_points = max_points
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        _check(lib().aloam_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            lib().aloam_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- scanRegistration.cpp:129-408
+    def extract_features(self, raw):
+        v, keep = _view(raw)
+        outs = [CloudView() for _ in range(5)]
+        _check(lib().aloam_extract_features(self._h, v, *[C.byref(o) for o in outs]))
+        names = ["full", "sharp", "less_sharp", "flat", "less_flat"]
+        return {n: _out(o) for n, o in zip(names, outs)}
+
+    def debug_features(self, n_full):
+        curv = np.zeros(n_full, np.float32)
+        label = np.zeros(n_full, np.int32)
+        s = np.zeros(64, np.int32)
+        e = np.zeros(64, np.int32)
+        ip = C.POINTER(C.c_int)
+        _check(lib().aloam_debug_features(self._h, curv.ctypes.data_as(C.POINTER(C.c_float)), label.ctypes.data_as(ip),
+                                          s.ctypes.data_as(ip), e.ctypes.data_as(ip)))
+        return curv, label, s[:self.cfg.n_scans], e[:self.cfg.n_scans]
+
+    # --- laserOdometry.cpp:554-568 / :274-502
+    def odometry_set_last(self, corner_last, surf_last):
+        a, ka = _view(corner_last)
+        b, kb = _view(surf_last)
+        _check(lib().aloam_odometry_set_last(self._h, a, b))
+
+    def odometry_register(self, sharp, flat, q, t):
+        a, ka = _view(sharp)
+        b, kb = _view(flat)
+        q = np.array(q, np.float64)
+        t = np.array(t, np.float64)
+        st = Stats()
+        _check(lib().aloam_odometry_register(self._h, a, b, _dp(q), _dp(t), C.byref(st)))
+        return q, t, st.as_dict()
+
+    def odometry_associate(self, sharp, flat, q, t):
+        a, ka = _view(sharp)
+        b, kb = _view(flat)
+        cc = np.zeros((max(a.n, 1), 3), np.int32)
+        pc = np.zeros((max(b.n, 1), 4), np.int32)
+        ip = C.POINTER(C.c_int)
+        _check(lib().aloam_odometry_associate(self._h, a, b, _dp(np.ascontiguousarray(q, np.float64)),
+                                              _dp(np.ascontiguousarray(t, np.float64)), cc.ctypes.data_as(ip), pc.ctypes.data_as(ip)))
+        return cc[:a.n], pc[:b.n]
+
+    # --- laserMapping.cpp:531-559 / :554-729
+    def map_upload(self, corner_map, surf_map):
+        a, ka = _view(corner_map)
+        b, kb = _view(surf_map)
+        _check(lib().aloam_map_upload(self._h, a, b))
+
+    def mapping_register(self, corner_stack, surf_stack, x):
+        a, ka = _view(corner_stack)
+        b, kb = _view(surf_stack)
+        x = np.array(x, np.float64)
+        st = Stats()
+        _check(lib().aloam_mapping_register(self._h, a, b, _dp(x), C.byref(st)))
+        return x, st.as_dict()
+
+    def voxel_filter(self, cloud, leaf):
+        a, ka = _view(cloud)
+        o = CloudView()
+        _check(lib().aloam_voxel_filter(self._h, a, float(leaf), C.byref(o)))
+        return _out(o)
+
+    # --- fused device-resident pipeline
+    def scan_to_pose(self, raw):
+        v, keep = _view(raw)
+        q = np.zeros(4)
+        t = np.zeros(3)
+        st = Stats()
+        _check(lib().aloam_scan_to_pose(self._h, v, _dp(q), _dp(t), C.byref(st)))
+        return q, t, st.as_dict()
+
+    def scan_to_pose_ptr(self, host_ptr, n, stride=4):
+        """raw scan given as a host address (e.g. pinned memory owned by the caller)."""
+        v = CloudView(C.cast(host_ptr, C.POINTER(C.c_float)), n, stride)
+        q = np.zeros(4)
+        t = np.zeros(3)
+        st = Stats()
+        _check(lib().aloam_scan_to_pose(self._h, v, _dp(q), _dp(t), C.byref(st)))
+        return q, t, st
+
+    def scan_to_pose_device(self, dev_ptr, n):
+        q = np.zeros(4)
+        t = np.zeros(3)
+        st = Stats()
+        _check(lib().aloam_scan_to_pose_device(self._h, C.c_void_p(dev_ptr), n, _dp(q), _dp(t), C.byref(st)))
+        return q, t, st
+
+    def reset_odometry(self):
+        _check(lib().aloam_reset_odometry(self._h))
+
+    # --- fine-grained
+    def knn(self, which, queries, k):
+        v, keep = _view(queries)
+        idx = np.zeros((v.n, k), np.int32)
+        sqd = np.zeros((v.n, k), np.float32)
+        _check(lib().aloam_knn(self._h, which, v, k, idx.ctypes.data_as(C.POINTER(C.c_int)), sqd.ctypes.data_as(C.POINTER(C.c_float))))
+        return idx, sqd
+
+    def normal_equations(self, blocks, x):
+        blocks = np.ascontiguousarray(blocks, np.float64).reshape(-1, BLOCK_DOUBLES)
+        JtJ = np.zeros((6, 6))
+        Jtr = np.zeros(6)
+        cost = C.c_double(0)
+        _check(lib().aloam_normal_equations(self._h, _dp(blocks), blocks.shape[0], _dp(np.ascontiguousarray(x, np.float64)),
+                                            _dp(JtJ), _dp(Jtr), C.byref(cost)))
+        return JtJ, Jtr, cost.value
+
+    def solve(self, blocks, x):
+        blocks = np.ascontiguousarray(blocks, np.float64).reshape(-1, BLOCK_DOUBLES)
+        x = np.array(x, np.float64)
+        s = np.zeros(7)
+        trace = np.zeros((8, 8))
+        rows = C.c_int(0)
+        _check(lib().aloam_solve(self._h, _dp(blocks), blocks.shape[0], _dp(x), _dp(s), _dp(trace), 8, C.byref(rows)))
+        keys = ["termination", "num_iterations", "num_successful", "num_jac_evals", "num_cost_evals", "initial_cost", "final_cost"]
+        return x, dict(zip(keys, s)), trace[:rows.value]

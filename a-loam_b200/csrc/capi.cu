@@ -1,0 +1,567 @@
+// Host side of the C ABI (include/aloam_b200.h): context, device buffers, kernel sequencing.
+// The reference's host code around the hot path is C++ (the ROS node bodies), so this layer is C++ too.
+// No CPU fallback: every entry point runs the sm_100a kernels or returns an error.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "../../include/aloam_b200.h"
+#include "kernels.h"
+
+using namespace aloam;
+
+namespace {
+
+constexpr int kMaxSharpPerRing = 12, kMaxLessSharpPerRing = 120, kMaxFlatPerRing = 24;
+constexpr int kFusedSharpSlots = 64 * kMaxSharpPerRing;  // 768
+constexpr int kFusedFlatSlots = 64 * kMaxFlatPerRing;    // 1536
+constexpr int kMaxQueries = 16384;                       // API-path capacity for sharp / flat query clouds
+
+struct FeatBuf {
+  Pt4 *sharp = nullptr, *less_sharp = nullptr, *flat = nullptr, *less_flat = nullptr;
+  int* counts = nullptr;           // [4] n_sharp, n_less_sharp, n_flat, n_less_flat (device)
+  int *rs_ls = nullptr, *rs_lf = nullptr;  // ring_start tables [65+]
+  float *tlo_ls = nullptr, *thi_ls = nullptr, *tlo_lf = nullptr, *thi_lf = nullptr;
+};
+
+}  // namespace
+
+struct aloam_ctx {
+  aloam_config cfg;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int max_points = 0, nblocks_max = 0, tile_cap = 0;
+  // raw scan + ring binning
+  float* d_raw = nullptr;
+  int8_t* d_ring = nullptr;
+  int *d_hist = nullptr, *d_offsets = nullptr, *d_ring_start = nullptr, *d_scan_start = nullptr, *d_scan_end = nullptr;
+  ScanScalars* d_sc = nullptr;  // [2]
+  Pt4* d_full = nullptr;
+  float* d_curv = nullptr;
+  int8_t* d_label = nullptr;
+  Pt4 *st_sharp = nullptr, *st_less_sharp = nullptr, *st_flat = nullptr, *st_less_flat = nullptr;
+  int* st_counts = nullptr;
+  FeatBuf feat[2];
+  // odometry
+  BlockRec* d_blocks = nullptr;
+  int* d_corr = nullptr;
+  double *d_pose = nullptr, *d_world = nullptr, *d_out28 = nullptr, *d_packed = nullptr;
+  LmSummary* d_summary = nullptr;  // [4]
+  int* d_err = nullptr;
+  Pt4* d_query = nullptr;
+  int* d_knn_idx = nullptr;
+  float* d_knn_d = nullptr;
+  // pinned host mirrors
+  Pt4* h_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int* h_ints = nullptr;        // scratch ints (counts etc.)
+  double* h_dbl = nullptr;      // scratch doubles
+  LmSummary* h_summary = nullptr;
+  ScanScalars* h_sc = nullptr;
+  // state
+  int parity = 0;         // ScanScalars slot of the next scan
+  int frame = 0;          // fused pipeline: scans seen
+  int cur = 0;            // fused pipeline: feat[] slot of the most recent scan
+  bool have_last = false; // API path: set_last called
+  int last_n_full = 0;
+};
+
+namespace {
+
+LmParams lm_params(const aloam_config& c) {
+  LmParams p;
+  p.max_iters = c.inner_iters; p.huber_a = c.huber;
+  p.initial_radius = 1e4; p.max_radius = 1e16; p.min_radius = 1e-32;
+  p.min_relative_decrease = 1e-3; p.min_lm_diagonal = 1e-6; p.max_lm_diagonal = 1e32;
+  p.function_tolerance = 1e-6; p.gradient_tolerance = 1e-10; p.parameter_tolerance = 1e-8;
+  p.max_invalid = 5;
+  return p;
+}
+
+template <typename T> cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+template <typename T> cudaError_t halloc(T** p, size_t n) { return cudaMallocHost((void**)p, n * sizeof(T)); }
+
+int upload_cloud(aloam_ctx* c, aloam_cloud_view v, Pt4* dst, int capacity) {
+  if (v.n < 0 || (v.n > 0 && !v.data) || (v.stride_floats != 4 && v.stride_floats != 8 && v.n > 0)) return ALOAM_ERR_INVALID_ARG;
+  if (v.n > capacity) return ALOAM_ERR_CAPACITY;
+  if (v.n == 0) return ALOAM_OK;
+  if (v.stride_floats == 4) {
+    CUDA_CHECK_RET(cudaMemcpyAsync(dst, v.data, (size_t)v.n * 16, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CUDA_CHECK_RET(cudaMemcpy2DAsync(dst, 16, v.data, (size_t)v.stride_floats * 4, 16, v.n, cudaMemcpyHostToDevice, c->stream));
+  }
+  return ALOAM_OK;
+}
+
+LastCloud last_corner(const FeatBuf& f) { return LastCloud{f.less_sharp, f.counts + 1, f.rs_ls, f.tlo_ls, f.thi_ls}; }
+LastCloud last_surf(const FeatBuf& f) { return LastCloud{f.less_flat, f.counts + 3, f.rs_lf, f.tlo_lf, f.thi_lf}; }
+
+// feature extraction kernels on a raw scan already in device memory
+int run_features(aloam_ctx* c, const float* d_raw, int n, int stride, FeatBuf& out) {
+  const int nb = (n + 1023) / 1024;
+  const float thres = c->cfg.minimum_range;
+  ScanScalars* sc = c->d_sc + c->parity;
+  ScanScalars* sc_next = c->d_sc + (c->parity ^ 1);
+  k_classify<<<nb, 256, 0, c->stream>>>(d_raw, n, stride, c->cfg.n_scans, thres * thres, c->d_ring, c->d_hist, sc);
+  k_ring_scan<<<1, 1024, 0, c->stream>>>(d_raw, stride, nb, c->cfg.n_scans, c->d_hist, c->d_offsets, c->d_ring_start,
+                                         c->d_scan_start, c->d_scan_end, sc, sc_next);
+  k_scatter<<<nb, 256, 0, c->stream>>>(d_raw, n, stride, c->d_ring, c->d_offsets, sc, c->d_full);
+  k_ring_features<<<c->cfg.n_scans, 256, ring_features_smem_bytes(), c->stream>>>(
+      c->d_full, c->d_ring_start, c->cfg.n_scans, 0.2f, c->st_sharp, c->st_less_sharp, c->st_flat, c->st_less_flat,
+      c->st_counts, c->d_curv, c->d_label, sc);
+  k_compact<<<c->cfg.n_scans, 128, 0, c->stream>>>(c->cfg.n_scans, c->st_sharp, c->st_less_sharp, c->st_flat,
+                                                   c->st_less_flat, c->st_counts, out.sharp, out.less_sharp, out.flat,
+                                                   out.less_flat, out.counts, out.rs_ls, out.rs_lf);
+  c->parity ^= 1;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return ALOAM_OK;
+}
+
+void run_tile_bounds(aloam_ctx* c, FeatBuf& f) {
+  const int blocks = (c->tile_cap + 7) / 8;
+  k_tile_bounds<<<blocks, 256, 0, c->stream>>>(f.less_sharp, f.counts + 1, f.tlo_ls, f.thi_ls);
+  k_tile_bounds<<<blocks, 256, 0, c->stream>>>(f.less_flat, f.counts + 3, f.tlo_lf, f.thi_lf);
+}
+
+// outer_iters x (association + LM) ; `cur` supplies sharp/flat, `last` the targets ; pose in c->d_pose
+void run_register(aloam_ctx* c, const FeatBuf& cur, const FeatBuf& last, int sharp_slots, int flat_slots, bool integrate,
+                  int* d_corr) {
+  OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan};
+  const LmParams lp = lm_params(c->cfg);
+  const int slots = sharp_slots + flat_slots;
+  for (int it = 0; it < c->cfg.outer_iters; ++it) {
+    k_odom_assoc<<<(slots + 7) / 8, 256, 0, c->stream>>>(cur.sharp, cur.flat, cur.counts, last_corner(last), last_surf(last),
+                                                         c->d_pose, op, c->d_blocks, d_corr, sharp_slots);
+    const bool last_it = it == c->cfg.outer_iters - 1;
+    k_lm_solve<<<1, ALOAM_LM_THREADS, 0, c->stream>>>(c->d_blocks, nullptr, slots, c->d_pose, lp, c->d_summary + (it & 3), 0,
+                                                      nullptr, c->d_world, (integrate && last_it) ? 1 : 0);
+  }
+}
+
+void fill_stats(aloam_ctx* c, aloam_stats* st, int outer, int flags, float ms) {
+  if (!st) return;
+  std::memset(st, 0, sizeof(*st));
+  st->flags = flags;
+  st->ms_total = ms;
+  for (int it = 0; it < outer && it < 4; ++it) {
+    const LmSummary& s = c->h_summary[it];
+    st->lm_iters += s.num_iterations;
+    st->accepted_steps += s.num_successful;
+    st->termination[it] = s.termination;
+    if (it == outer - 1) {
+      st->n_corner_corr = s.n_edge; st->n_plane_corr = s.n_plane;
+      st->init_cost = s.initial_cost; st->final_cost = s.final_cost;
+      if (s.n_edge + s.n_plane < 10) st->flags |= ALOAM_FLAG_FEW_CORRESPONDENCES;
+    }
+  }
+}
+
+int check_view(const aloam_cloud_view& v) {
+  if (v.n < 0) return ALOAM_ERR_INVALID_ARG;
+  if (v.n > 0 && (!v.data || (v.stride_floats != 4 && v.stride_floats != 8))) return ALOAM_ERR_INVALID_ARG;
+  return ALOAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void aloam_default_config(aloam_config* cfg, int n_scans) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->n_scans = n_scans;
+  // launch/aloam_velodyne_VLP_16.launch:3-13, ..._HDL_32.launch:3-13, ..._HDL_64.launch:3-13
+  if (n_scans == 64) { cfg->minimum_range = 5.0f; cfg->line_res = 0.4f; cfg->plane_res = 0.8f; }
+  else { cfg->minimum_range = 0.3f; cfg->line_res = 0.2f; cfg->plane_res = 0.4f; }
+  cfg->outer_iters = 2; cfg->inner_iters = 4; cfg->huber = 0.1;
+  cfg->dist_sq_thresh = 25.0; cfg->nearby_scan = 2.5;
+  cfg->device = 0; cfg->max_points = 400000; cfg->max_map_points = 0;
+}
+
+const char* aloam_strerror(int code) {
+  switch (code) {
+    case ALOAM_OK: return "ok";
+    case ALOAM_ERR_INVALID_ARG: return "invalid argument";
+    case ALOAM_ERR_UNSUPPORTED_SCANS: return "only 16, 32 or 64 scan lines are supported";
+    case ALOAM_ERR_EMPTY_CLOUD: return "no point survives the NaN / minimum-range filter";
+    case ALOAM_ERR_CAPACITY: return "cloud larger than the context capacity";
+    case ALOAM_ERR_CUDA: return "CUDA error";
+    case ALOAM_ERR_NO_DEVICE: return "no CUDA device";
+    case ALOAM_ERR_RING_TOO_LARGE: return "a ring holds more than ALOAM_MAX_RING_POINTS returns";
+    case ALOAM_ERR_NOT_RING_MAJOR: return "cloud is not in ascending ring order";
+    case ALOAM_ERR_STATE: return "call sequence error";
+    case ALOAM_ERR_COMM: return "communicator error";
+    default: return "unknown error";
+  }
+}
+
+int aloam_destroy(aloam_ctx* c) {
+  if (!c) return ALOAM_OK;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  void* dev[] = {c->d_raw, c->d_ring, c->d_hist, c->d_offsets, c->d_ring_start, c->d_scan_start, c->d_scan_end, c->d_sc,
+                 c->d_full, c->d_curv, c->d_label, c->st_sharp, c->st_less_sharp, c->st_flat, c->st_less_flat, c->st_counts,
+                 c->d_blocks, c->d_corr, c->d_pose, c->d_world, c->d_out28, c->d_packed, c->d_summary, c->d_err, c->d_query,
+                 c->d_knn_idx, c->d_knn_d};
+  for (void* p : dev) if (p) cudaFree(p);
+  for (FeatBuf& f : c->feat) {
+    void* fp[] = {f.sharp, f.less_sharp, f.flat, f.less_flat, f.counts, f.rs_ls, f.rs_lf, f.tlo_ls, f.thi_ls, f.tlo_lf, f.thi_lf};
+    for (void* p : fp) if (p) cudaFree(p);
+  }
+  for (Pt4* p : c->h_out) if (p) cudaFreeHost(p);
+  if (c->h_ints) cudaFreeHost(c->h_ints);
+  if (c->h_dbl) cudaFreeHost(c->h_dbl);
+  if (c->h_summary) cudaFreeHost(c->h_summary);
+  if (c->h_sc) cudaFreeHost(c->h_sc);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return ALOAM_OK;
+}
+
+int aloam_reset_odometry(aloam_ctx* c) {
+  if (!c) return ALOAM_ERR_INVALID_ARG;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  const double ident[7] = {0, 0, 0, 1, 0, 0, 0};
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->d_pose, ident, sizeof(ident), cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->d_world, ident, sizeof(ident), cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  c->frame = 0; c->cur = 0; c->have_last = false;
+  return ALOAM_OK;
+}
+
+int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
+  if (!cfg || !out) return ALOAM_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (cfg->n_scans != 16 && cfg->n_scans != 32 && cfg->n_scans != 64) return ALOAM_ERR_UNSUPPORTED_SCANS;
+  if (cfg->max_points <= 0 || cfg->outer_iters < 1 || cfg->outer_iters > 4 || cfg->inner_iters < 0) return ALOAM_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return ALOAM_ERR_NO_DEVICE;
+  if (cfg->device < 0 || cfg->device >= ndev) return ALOAM_ERR_INVALID_ARG;
+  CUDA_CHECK_RET(cudaSetDevice(cfg->device));
+  aloam_ctx* c = new (std::nothrow) aloam_ctx();
+  if (!c) return ALOAM_ERR_INVALID_ARG;
+  c->cfg = *cfg;
+  c->max_points = cfg->max_points;
+  c->nblocks_max = (c->max_points + 1023) / 1024;
+  c->tile_cap = ((c->max_points + ALOAM_TILE - 1) / ALOAM_TILE + 7) / 8 * 8;
+  const size_t mp = (size_t)c->max_points;
+#define TRY(e) do { if ((e) != cudaSuccess) { fprintf(stderr, "[aloam_b200] %s failed: %s\n", #e, cudaGetErrorString(cudaGetLastError())); aloam_destroy(c); return ALOAM_ERR_CUDA; } } while (0)
+  TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  TRY(cudaEventCreate(&c->ev0)); TRY(cudaEventCreate(&c->ev1));
+  TRY(dalloc(&c->d_raw, mp * 8));
+  TRY(dalloc(&c->d_ring, mp));
+  TRY(dalloc(&c->d_hist, (size_t)c->nblocks_max * 64)); TRY(dalloc(&c->d_offsets, (size_t)c->nblocks_max * 64));
+  TRY(dalloc(&c->d_ring_start, 72)); TRY(dalloc(&c->d_scan_start, 64)); TRY(dalloc(&c->d_scan_end, 64));
+  TRY(dalloc(&c->d_sc, 2));
+  TRY(dalloc(&c->d_full, mp)); TRY(dalloc(&c->d_curv, mp)); TRY(dalloc(&c->d_label, mp));
+  TRY(dalloc(&c->st_sharp, 64 * kMaxSharpPerRing)); TRY(dalloc(&c->st_less_sharp, 64 * kMaxLessSharpPerRing));
+  TRY(dalloc(&c->st_flat, 64 * kMaxFlatPerRing)); TRY(dalloc(&c->st_less_flat, (size_t)64 * ALOAM_MAX_RING));
+  TRY(dalloc(&c->st_counts, 64 * 4));
+  for (FeatBuf& f : c->feat) {
+    TRY(dalloc(&f.sharp, kMaxQueries)); TRY(dalloc(&f.flat, kMaxQueries));
+    TRY(dalloc(&f.less_sharp, mp)); TRY(dalloc(&f.less_flat, mp));
+    TRY(dalloc(&f.counts, 4)); TRY(dalloc(&f.rs_ls, 72)); TRY(dalloc(&f.rs_lf, 72));
+    TRY(dalloc(&f.tlo_ls, (size_t)c->tile_cap * 4)); TRY(dalloc(&f.thi_ls, (size_t)c->tile_cap * 4));
+    TRY(dalloc(&f.tlo_lf, (size_t)c->tile_cap * 4)); TRY(dalloc(&f.thi_lf, (size_t)c->tile_cap * 4));
+    TRY(cudaMemset(f.counts, 0, 16)); TRY(cudaMemset(f.rs_ls, 0, 72 * 4)); TRY(cudaMemset(f.rs_lf, 0, 72 * 4));
+  }
+  TRY(dalloc(&c->d_blocks, (size_t)2 * kMaxQueries)); TRY(dalloc(&c->d_corr, (size_t)2 * kMaxQueries * 4));
+  TRY(dalloc(&c->d_pose, 8)); TRY(dalloc(&c->d_world, 8)); TRY(dalloc(&c->d_out28, 32));
+  TRY(dalloc(&c->d_packed, (size_t)2 * kMaxQueries * 11));
+  TRY(dalloc(&c->d_summary, 4)); TRY(dalloc(&c->d_err, 4));
+  TRY(dalloc(&c->d_query, mp)); TRY(dalloc(&c->d_knn_idx, mp)); TRY(dalloc(&c->d_knn_d, mp));
+  for (int k = 0; k < 5; ++k) TRY(halloc(&c->h_out[k], k == 0 || k == 4 ? mp : (size_t)kMaxQueries));
+  TRY(halloc(&c->h_ints, 4096)); TRY(halloc(&c->h_dbl, 4096)); TRY(halloc(&c->h_summary, 4)); TRY(halloc(&c->h_sc, 2));
+  ScanScalars init[2];
+  for (ScanScalars& s : init) { s.first_valid = INT32_MAX; s.last_valid = -1; s.half_idx = INT32_MAX; s.n_full = 0; s.start_ori = 0; s.end_ori = 0; s.error = 0; s.pad = 0; }
+  TRY(cudaMemcpy(c->d_sc, init, sizeof(init), cudaMemcpyHostToDevice));
+  TRY(cudaMemset(c->d_err, 0, 16));
+  TRY(cudaFuncSetAttribute(k_ring_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_features_smem_bytes()));
+#undef TRY
+  int rc = aloam_reset_odometry(c);
+  if (rc != ALOAM_OK) { aloam_destroy(c); return rc; }
+  *out = c;
+  return ALOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ feature extraction
+int aloam_extract_features(aloam_ctx* c, aloam_cloud_view raw, aloam_cloud_view* full, aloam_cloud_view* sharp,
+                           aloam_cloud_view* less_sharp, aloam_cloud_view* flat, aloam_cloud_view* less_flat) {
+  if (!c || !full || !sharp || !less_sharp || !flat || !less_flat) return ALOAM_ERR_INVALID_ARG;
+  int rc = check_view(raw);
+  if (rc) return rc;
+  if (raw.n == 0) return ALOAM_ERR_EMPTY_CLOUD;
+  if (raw.n > c->max_points) return ALOAM_ERR_CAPACITY;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->d_raw, raw.data, (size_t)raw.n * raw.stride_floats * 4, cudaMemcpyHostToDevice, c->stream));
+  FeatBuf& f = c->feat[1];
+  const int slot = c->parity;
+  rc = run_features(c, c->d_raw, raw.n, raw.stride_floats, f);
+  if (rc) return rc;
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints, f.counts, 16, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_sc, c->d_sc + slot, sizeof(ScanScalars), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  if (c->h_sc->error) {
+    int e = c->h_sc->error;
+    CUDA_CHECK_RET(cudaMemset(&(c->d_sc + slot)->error, 0, 4));
+    return e;
+  }
+  const int n_full = c->h_sc->n_full;
+  c->last_n_full = n_full;
+  if (c->h_sc->first_valid == INT32_MAX) return ALOAM_ERR_EMPTY_CLOUD;
+  const int n[5] = {n_full, c->h_ints[0], c->h_ints[1], c->h_ints[2], c->h_ints[3]};
+  const Pt4* src[5] = {c->d_full, f.sharp, f.less_sharp, f.flat, f.less_flat};
+  for (int k = 0; k < 5; ++k)
+    if (n[k] > 0) CUDA_CHECK_RET(cudaMemcpyAsync(c->h_out[k], src[k], (size_t)n[k] * 16, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  aloam_cloud_view* outs[5] = {full, sharp, less_sharp, flat, less_flat};
+  for (int k = 0; k < 5; ++k) { outs[k]->data = reinterpret_cast<const float*>(c->h_out[k]); outs[k]->n = n[k]; outs[k]->stride_floats = 4; }
+  return ALOAM_OK;
+}
+
+int aloam_debug_features(aloam_ctx* c, float* curvature, int* label, int* scan_start, int* scan_end) {
+  if (!c) return ALOAM_ERR_INVALID_ARG;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  const int n = c->last_n_full;
+  if (curvature && n > 0) CUDA_CHECK_RET(cudaMemcpy(curvature, c->d_curv, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (label && n > 0) {
+    std::vector<int8_t> tmp(n);
+    CUDA_CHECK_RET(cudaMemcpy(tmp.data(), c->d_label, (size_t)n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) label[i] = tmp[i];
+  }
+  if (scan_start) CUDA_CHECK_RET(cudaMemcpy(scan_start, c->d_scan_start, (size_t)c->cfg.n_scans * 4, cudaMemcpyDeviceToHost));
+  if (scan_end) CUDA_CHECK_RET(cudaMemcpy(scan_end, c->d_scan_end, (size_t)c->cfg.n_scans * 4, cudaMemcpyDeviceToHost));
+  return ALOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ odometry (API path)
+int aloam_odometry_set_last(aloam_ctx* c, aloam_cloud_view corner_last, aloam_cloud_view surf_last) {
+  if (!c) return ALOAM_ERR_INVALID_ARG;
+  int rc = check_view(corner_last); if (rc) return rc;
+  rc = check_view(surf_last); if (rc) return rc;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  FeatBuf& f = c->feat[0];
+  rc = upload_cloud(c, corner_last, f.less_sharp, c->max_points); if (rc) return rc;
+  rc = upload_cloud(c, surf_last, f.less_flat, c->max_points); if (rc) return rc;
+  c->h_ints[0] = 0; c->h_ints[1] = corner_last.n; c->h_ints[2] = 0; c->h_ints[3] = surf_last.n;
+  CUDA_CHECK_RET(cudaMemcpyAsync(f.counts, c->h_ints, 16, cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK_RET(cudaMemsetAsync(f.rs_ls, 0, 72 * 4, c->stream));
+  CUDA_CHECK_RET(cudaMemsetAsync(f.rs_lf, 0, 72 * 4, c->stream));
+  CUDA_CHECK_RET(cudaMemsetAsync(c->d_err, 0, 4, c->stream));
+  if (corner_last.n > 0) k_ring_offsets<<<(corner_last.n + 255) / 256, 256, 0, c->stream>>>(f.less_sharp, corner_last.n, f.rs_ls, c->d_err);
+  if (surf_last.n > 0) k_ring_offsets<<<(surf_last.n + 255) / 256, 256, 0, c->stream>>>(f.less_flat, surf_last.n, f.rs_lf, c->d_err);
+  run_tile_bounds(c, f);
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints + 8, c->d_err, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK_RET(cudaGetLastError());
+  if (c->h_ints[8]) return ALOAM_ERR_NOT_RING_MAJOR;
+  c->have_last = true;
+  return ALOAM_OK;
+}
+
+static int upload_queries(aloam_ctx* c, aloam_cloud_view sharp, aloam_cloud_view flat, FeatBuf& f) {
+  int rc = check_view(sharp); if (rc) return rc;
+  rc = check_view(flat); if (rc) return rc;
+  rc = upload_cloud(c, sharp, f.sharp, kMaxQueries); if (rc) return rc;
+  rc = upload_cloud(c, flat, f.flat, kMaxQueries); if (rc) return rc;
+  c->h_ints[16] = sharp.n; c->h_ints[17] = 0; c->h_ints[18] = flat.n; c->h_ints[19] = 0;
+  CUDA_CHECK_RET(cudaMemcpyAsync(f.counts, c->h_ints + 16, 16, cudaMemcpyHostToDevice, c->stream));
+  return ALOAM_OK;
+}
+
+int aloam_odometry_register(aloam_ctx* c, aloam_cloud_view sharp, aloam_cloud_view flat, double q[4], double t[3],
+                            aloam_stats* stats) {
+  if (!c || !q || !t) return ALOAM_ERR_INVALID_ARG;
+  if (!c->have_last) return ALOAM_ERR_STATE;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  FeatBuf& cur = c->feat[1];
+  int rc = upload_queries(c, sharp, flat, cur); if (rc) return rc;
+  for (int k = 0; k < 4; ++k) c->h_dbl[k] = q[k];
+  for (int k = 0; k < 3; ++k) c->h_dbl[4 + k] = t[k];
+  CUDA_CHECK_RET(cudaEventRecord(c->ev0, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->d_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
+  run_register(c, cur, c->feat[0], sharp.n, flat.n, false, nullptr);
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 8, c->d_pose, 56, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaEventRecord(c->ev1, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK_RET(cudaGetLastError());
+  for (int k = 0; k < 4; ++k) q[k] = c->h_dbl[8 + k];
+  for (int k = 0; k < 3; ++k) t[k] = c->h_dbl[12 + k];
+  float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  fill_stats(c, stats, c->cfg.outer_iters, 0, ms);
+  return ALOAM_OK;
+}
+
+int aloam_odometry_associate(aloam_ctx* c, aloam_cloud_view sharp, aloam_cloud_view flat, const double q[4], const double t[3],
+                             int* corner_corr, int* plane_corr) {
+  if (!c || !q || !t) return ALOAM_ERR_INVALID_ARG;
+  if (!c->have_last) return ALOAM_ERR_STATE;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  FeatBuf& cur = c->feat[1];
+  int rc = upload_queries(c, sharp, flat, cur); if (rc) return rc;
+  for (int k = 0; k < 4; ++k) c->h_dbl[k] = q[k];
+  for (int k = 0; k < 3; ++k) c->h_dbl[4 + k] = t[k];
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->d_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
+  OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan};
+  const int slots = sharp.n + flat.n;
+  if (slots > 0)
+    k_odom_assoc<<<(slots + 7) / 8, 256, 0, c->stream>>>(cur.sharp, cur.flat, cur.counts, last_corner(c->feat[0]),
+                                                         last_surf(c->feat[0]), c->d_pose, op, c->d_blocks, c->d_corr, sharp.n);
+  std::vector<int> h((size_t)slots * 4 + 4);
+  if (slots > 0) CUDA_CHECK_RET(cudaMemcpyAsync(h.data(), c->d_corr, (size_t)slots * 16, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK_RET(cudaGetLastError());
+  for (int i = 0; i < sharp.n && corner_corr; ++i) { corner_corr[3 * i] = h[4 * i]; corner_corr[3 * i + 1] = h[4 * i + 1]; corner_corr[3 * i + 2] = h[4 * i + 3]; }
+  for (int i = 0; i < flat.n && plane_corr; ++i) {
+    const int* s = &h[4 * (size_t)(sharp.n + i)];
+    plane_corr[4 * i] = s[0]; plane_corr[4 * i + 1] = s[1]; plane_corr[4 * i + 2] = s[2]; plane_corr[4 * i + 3] = s[3];
+  }
+  return ALOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fused pipeline
+static int scan_to_pose_impl(aloam_ctx* c, const float* d_raw, int n, int stride, double q_w[4], double t_w[3], aloam_stats* stats) {
+  FeatBuf& cur = c->feat[c->frame & 1];
+  FeatBuf& last = c->feat[(c->frame & 1) ^ 1];
+  const int slot = c->parity;
+  int rc = run_features(c, d_raw, n, stride, cur);
+  if (rc) return rc;
+  int flags = 0;
+  if (c->frame == 0) {
+    flags |= ALOAM_FLAG_INITIALISED_ONLY;  // laserOdometry.cpp:267-271
+  } else {
+    run_register(c, cur, last, kFusedSharpSlots, kFusedFlatSlots, true, nullptr);
+  }
+  run_tile_bounds(c, cur);  // index for the next scan (replaces the kd-tree rebuild, laserOdometry.cpp:567-568)
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 16, c->d_world, 56, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_sc, c->d_sc + slot, sizeof(ScanScalars), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaEventRecord(c->ev1, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK_RET(cudaGetLastError());
+  if (c->h_sc->error) {
+    int e = c->h_sc->error;
+    CUDA_CHECK_RET(cudaMemset(&(c->d_sc + slot)->error, 0, 4));
+    return e;
+  }
+  if (c->h_sc->first_valid == INT32_MAX) return ALOAM_ERR_EMPTY_CLOUD;
+  c->last_n_full = c->h_sc->n_full;
+  for (int k = 0; k < 4; ++k) q_w[k] = c->h_dbl[16 + k];
+  for (int k = 0; k < 3; ++k) t_w[k] = c->h_dbl[20 + k];
+  float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  if (c->frame == 0) { if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->flags = flags; stats->ms_total = ms; } }
+  else fill_stats(c, stats, c->cfg.outer_iters, flags, ms);
+  c->cur = c->frame & 1;
+  c->frame++;
+  return ALOAM_OK;
+}
+
+int aloam_scan_to_pose(aloam_ctx* c, aloam_cloud_view raw, double q_w[4], double t_w[3], aloam_stats* stats) {
+  if (!c || !q_w || !t_w) return ALOAM_ERR_INVALID_ARG;
+  int rc = check_view(raw); if (rc) return rc;
+  if (raw.n == 0) return ALOAM_ERR_EMPTY_CLOUD;
+  if (raw.n > c->max_points) return ALOAM_ERR_CAPACITY;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  CUDA_CHECK_RET(cudaEventRecord(c->ev0, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->d_raw, raw.data, (size_t)raw.n * raw.stride_floats * 4, cudaMemcpyHostToDevice, c->stream));
+  return scan_to_pose_impl(c, c->d_raw, raw.n, raw.stride_floats, q_w, t_w, stats);
+}
+
+int aloam_scan_to_pose_device(aloam_ctx* c, const float* d_raw, int n, double q_w[4], double t_w[3], aloam_stats* stats) {
+  if (!c || !q_w || !t_w || !d_raw) return ALOAM_ERR_INVALID_ARG;
+  if (n <= 0) return ALOAM_ERR_EMPTY_CLOUD;
+  if (n > c->max_points) return ALOAM_ERR_CAPACITY;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  CUDA_CHECK_RET(cudaEventRecord(c->ev0, c->stream));
+  return scan_to_pose_impl(c, d_raw, n, 4, q_w, t_w, stats);
+}
+
+// ------------------------------------------------------------------------------------------------ fine-grained
+int aloam_knn(aloam_ctx* c, int which, aloam_cloud_view queries, int k, int* idx, float* sqdist) {
+  if (!c || !idx || !sqdist || k < 1) return ALOAM_ERR_INVALID_ARG;
+  int rc = check_view(queries); if (rc) return rc;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  if (which == 0 || which == 1) {
+    if (!c->have_last) return ALOAM_ERR_STATE;
+    if (k != 1) return ALOAM_ERR_INVALID_ARG;  // the reference only asks for k = 1 on these trees (laserOdometry.cpp:302,390)
+    rc = upload_cloud(c, queries, c->d_query, c->max_points); if (rc) return rc;
+    if (queries.n > 0) {
+      LastCloud L = which == 0 ? last_corner(c->feat[0]) : last_surf(c->feat[0]);
+      k_knn_last<<<(queries.n + 7) / 8, 256, 0, c->stream>>>(L, c->d_query, queries.n, c->d_knn_idx, c->d_knn_d);
+      CUDA_CHECK_RET(cudaMemcpyAsync(idx, c->d_knn_idx, (size_t)queries.n * 4, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK_RET(cudaMemcpyAsync(sqdist, c->d_knn_d, (size_t)queries.n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK_RET(cudaGetLastError());
+    return ALOAM_OK;
+  }
+  return ALOAM_ERR_STATE;  // map trees: see aloam_map_upload
+}
+
+static int run_lm_api(aloam_ctx* c, const double* blocks, int n_blocks, const double x[7], int mode) {
+  if (n_blocks < 0 || n_blocks > 2 * kMaxQueries) return ALOAM_ERR_CAPACITY;
+  if (n_blocks > 0) {
+    CUDA_CHECK_RET(cudaMemcpyAsync(c->d_packed, blocks, (size_t)n_blocks * 11 * 8, cudaMemcpyHostToDevice, c->stream));
+    k_pack_blocks<<<(n_blocks + 255) / 256, 256, 0, c->stream>>>(c->d_packed, n_blocks, c->d_blocks);
+  }
+  for (int k = 0; k < 7; ++k) c->h_dbl[k] = x[k];
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->d_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
+  k_lm_solve<<<1, ALOAM_LM_THREADS, 0, c->stream>>>(c->d_blocks, nullptr, n_blocks, c->d_pose, lm_params(c->cfg), c->d_summary, mode,
+                                                    c->d_out28, nullptr, 0);
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 8, c->d_pose, 56, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 32, c->d_out28, 28 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(LmSummary), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK_RET(cudaGetLastError());
+  return ALOAM_OK;
+}
+
+int aloam_normal_equations(aloam_ctx* c, const double* blocks, int n_blocks, const double x[7], double JtJ[36], double Jtr[6],
+                           double* cost) {
+  if (!c || !x || !JtJ || !Jtr || (n_blocks > 0 && !blocks)) return ALOAM_ERR_INVALID_ARG;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  int rc = run_lm_api(c, blocks, n_blocks, x, 1);
+  if (rc) return rc;
+  const double* o = c->h_dbl + 32;
+  int k = 0;
+  for (int a = 0; a < 6; ++a)
+    for (int b = a; b < 6; ++b) { JtJ[6 * a + b] = o[k]; JtJ[6 * b + a] = o[k]; ++k; }
+  for (int a = 0; a < 6; ++a) Jtr[a] = o[21 + a];
+  if (cost) *cost = o[27];
+  return ALOAM_OK;
+}
+
+int aloam_solve(aloam_ctx* c, const double* blocks, int n_blocks, double x[7], double summary7[7], double* trace, int max_trace,
+                int* trace_rows) {
+  if (!c || !x || (n_blocks > 0 && !blocks)) return ALOAM_ERR_INVALID_ARG;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  int rc = run_lm_api(c, blocks, n_blocks, x, 0);
+  if (rc) return rc;
+  for (int k = 0; k < 7; ++k) x[k] = c->h_dbl[8 + k];
+  const LmSummary& s = c->h_summary[0];
+  if (summary7) {
+    summary7[0] = s.termination; summary7[1] = s.num_iterations; summary7[2] = s.num_successful; summary7[3] = s.num_jac_evals;
+    summary7[4] = 0; summary7[5] = s.initial_cost; summary7[6] = s.final_cost;
+  }
+  int rows = 0;
+  if (trace)
+    for (; rows < s.trace_rows && rows < max_trace; ++rows) std::memcpy(trace + (size_t)rows * 8, s.trace[rows], 64);
+  if (trace_rows) *trace_rows = rows;
+  return ALOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ mapping (mapping.cu)
+int aloam_map_upload_impl(aloam_ctx* c, aloam_cloud_view corner_map, aloam_cloud_view surf_map);
+int aloam_mapping_register_impl(aloam_ctx* c, aloam_cloud_view corner_stack, aloam_cloud_view surf_stack, double x[7], aloam_stats* stats);
+int aloam_voxel_filter_impl(aloam_ctx* c, aloam_cloud_view in, float leaf, aloam_cloud_view* out);
+
+int aloam_map_upload(aloam_ctx* c, aloam_cloud_view corner_map, aloam_cloud_view surf_map) { return aloam_map_upload_impl(c, corner_map, surf_map); }
+int aloam_mapping_register(aloam_ctx* c, aloam_cloud_view corner_stack, aloam_cloud_view surf_stack, double x[7], aloam_stats* stats) {
+  return aloam_mapping_register_impl(c, corner_stack, surf_stack, x, stats);
+}
+int aloam_voxel_filter(aloam_ctx* c, aloam_cloud_view in, float leaf, aloam_cloud_view* out) { return aloam_voxel_filter_impl(c, in, leaf, out); }
+
+}  // extern "C"

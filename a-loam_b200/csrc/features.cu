@@ -1,0 +1,567 @@
+// Feature extraction on the GPU -- replaces scanRegistration.cpp:85-112,129-408.
+//
+//   k_classify   (thread / return)   NaN + minimum-range removal (:85-112,136-137), elevation -> ring id (:166-205),
+//                                    sweep-start azimuth (:141), the return that flips `halfPassed` (:209-224, found
+//                                    with a parallel min instead of the sequential state machine), per-block ring
+//                                    histograms for the stable counting sort that replaces laserCloudScans[] (:240)
+//   k_ring_scan  (one CTA)           histogram -> global offsets, scanStartInd/scanEndInd (:249-251), endOri (:142-153)
+//   k_scatter    (thread / return)   relTime + intensity (:226-239), stable scatter into the ring-major cloud (:247-252)
+//   k_ring_features (CTA / ring)     curvature (:256-266), per-sixth sort by (curvature, index) (:282-289), greedy
+//                                    sharp / less-sharp / flat picks with neighbour suppression (:291-390), less-flat
+//                                    gather (:392-398), pcl::VoxelGrid(0.2) (:401-407) -- all in shared memory
+//   k_compact    (CTA / ring)        ring-ordered concatenation of the four feature clouds (:304-310,356,407)
+//
+// Everything here is float32 with the reference's evaluation order (compiled -fmad=false); ties in the two
+// reference-internal unstable sorts are resolved by original index (SURVEY.md 8a note 4).
+#include <climits>
+#include <cfloat>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace aloam {
+
+namespace {
+
+constexpr int CT = 256;        // threads per CTA in classify / scatter
+constexpr int CHUNK = 1024;    // returns per CTA (CT x 4)
+constexpr int ITERS = CHUNK / CT;
+constexpr double kPi = 3.14159265358979323846;  // M_PI
+
+__device__ __forceinline__ bool point_ok(float x, float y, float z, float thres2) {
+  if (!(isfinite(x) && isfinite(y) && isfinite(z))) return false;  // pcl::removeNaNFromPointCloud (:136)
+  return !(x * x + y * y + z * z < thres2);                        // removeClosedPointCloud (:99)
+}
+
+// scanRegistration.cpp:166-205 ; returns -1 when the reference drops the return
+__device__ __forceinline__ int ring_of(float x, float y, float z, int n_scans) {
+  // :166 double atan / sqrt over float products, *180/M_PI in double, stored to float
+  float angle = (float)(atan((double)z / sqrt((double)(x * x + y * y))) * 180.0 / kPi);
+  int id;
+  if (n_scans == 16) {
+    id = (int)((double)((angle + 15.0f) / 2.0f) + 0.5);
+    if (id > n_scans - 1 || id < 0) return -1;
+  } else if (n_scans == 32) {
+    id = (int)(((double)angle + 92.0 / 3.0) * 3.0 / 4.0);
+    if (id > n_scans - 1 || id < 0) return -1;
+  } else {
+    if ((double)angle >= -8.83) id = (int)((double)(2.0f - angle) * 3.0 + 0.5);
+    else id = n_scans / 2 + (int)((-8.83 - (double)angle) * 2.0 + 0.5);
+    if (angle > 2.0f || (double)angle < -24.33 || id > 50 || id < 0) return -1;
+  }
+  return id;
+}
+
+__device__ __forceinline__ void load_xyz(const float* __restrict__ raw, int i, int stride, float& x, float& y, float& z) {
+  if (stride == 4) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(raw) + i);
+    x = v.x; y = v.y; z = v.z;
+  } else {
+    const float* p = raw + (size_t)i * stride;
+    x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+  }
+}
+
+// azimuth of a return before the halfPassed flip (:208-218)
+__device__ __forceinline__ float ori_first_half(float x, float y, float start_ori) {
+  float ori = -atan2f(y, x);
+  if ((double)ori < (double)start_ori - kPi / 2) ori = (float)((double)ori + 2 * kPi);
+  else if ((double)ori > (double)start_ori + kPi * 3 / 2) ori = (float)((double)ori - 2 * kPi);
+  return ori;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CT) k_classify(const float* __restrict__ raw, int n, int stride, int n_scans,
+                                                 float thres2, int8_t* __restrict__ ring_out,
+                                                 int* __restrict__ hist, ScanScalars* __restrict__ sc) {
+  __shared__ int s_hist[64];
+  __shared__ int s_first, s_last, s_half;
+  const int tid = threadIdx.x;
+  if (tid < 64) s_hist[tid] = 0;
+  if (tid == 0) { s_first = INT_MAX; s_last = -1; s_half = INT_MAX; }
+  __syncthreads();
+  // every CTA finds the first surviving return itself (normally raw[0]) so start_ori needs no grid-wide step
+  for (int base = 0; base < n; base += CT) {
+    int i = base + tid;
+    if (i < n) {
+      float x, y, z; load_xyz(raw, i, stride, x, y, z);
+      if (point_ok(x, y, z, thres2)) atomicMin(&s_first, i);
+    }
+    __syncthreads();
+    int f = s_first;
+    __syncthreads();
+    if (f != INT_MAX) break;
+  }
+  const int first = s_first;
+  float start_ori = 0.f;
+  if (first != INT_MAX) {
+    float x, y, z; load_xyz(raw, first, stride, x, y, z);
+    start_ori = -atan2f(y, x);  // :141
+  }
+  int my_last = -1, my_half = INT_MAX;
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    int i = blockIdx.x * CHUNK + it * CT + tid;
+    if (i >= n) continue;
+    float x, y, z; load_xyz(raw, i, stride, x, y, z);
+    int ring = -2;
+    if (point_ok(x, y, z, thres2)) {
+      my_last = max(my_last, i);
+      ring = ring_of(x, y, z, n_scans);
+      if (ring >= 0) {
+        atomicAdd(&s_hist[ring], 1);
+        float ori = ori_first_half(x, y, start_ori);
+        if ((double)(ori - start_ori) > kPi) my_half = min(my_half, i);  // :220
+      }
+    }
+    ring_out[i] = (int8_t)ring;
+  }
+  if (my_last >= 0) atomicMax(&s_last, my_last);
+  if (my_half != INT_MAX) atomicMin(&s_half, my_half);
+  __syncthreads();
+  if (tid < 64) hist[blockIdx.x * 64 + tid] = s_hist[tid];
+  if (tid == 0) {
+    if (s_last >= 0) atomicMax(&sc->last_valid, s_last);
+    if (s_half != INT_MAX) atomicMin(&sc->half_idx, s_half);
+    if (blockIdx.x == 0) { sc->first_valid = first; sc->start_ori = start_ori; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one CTA of 1024 threads: thread (r = t>>4, s = t&15) owns slice s of ring r's per-block histogram column
+__global__ void __launch_bounds__(1024) k_ring_scan(const float* __restrict__ raw, int stride, int nblocks,
+                                                    int n_scans, const int* __restrict__ hist,
+                                                    int* __restrict__ offsets, int* __restrict__ ring_start,
+                                                    int* __restrict__ scan_start, int* __restrict__ scan_end,
+                                                    ScanScalars* __restrict__ sc, ScanScalars* __restrict__ sc_next) {
+  __shared__ int s_tot[64];
+  __shared__ int s_start[65];
+  const int t = threadIdx.x, r = t >> 4, s = t & 15;
+  const int bps = (nblocks + 15) / 16;
+  const int b0 = min(nblocks, s * bps), b1 = min(nblocks, b0 + bps);
+  int local = 0;
+  for (int b = b0; b < b1; ++b) local += hist[b * 64 + r];
+  // inclusive scan across the 16 slices (half-warp)
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, d, 16);
+    if (s >= d) incl += v;
+  }
+  if (s == 15) s_tot[r] = incl;
+  __syncthreads();
+  if (t < 32) {  // exclusive scan of 64 ring totals, two per lane
+    int a = s_tot[2 * t], b = s_tot[2 * t + 1];
+    int pair = a + b, inc = pair;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, inc, d);
+      if (t >= d) inc += v;
+    }
+    int ex = inc - pair;
+    s_start[2 * t] = ex;
+    s_start[2 * t + 1] = ex + a;
+    if (t == 31) s_start[64] = inc;
+  }
+  __syncthreads();
+  int running = s_start[r] + (incl - local);
+  for (int b = b0; b < b1; ++b) {
+    offsets[b * 64 + r] = running;
+    running += hist[b * 64 + r];
+  }
+  if (t <= 64) ring_start[t] = s_start[t];
+  if (t < 64) {  // :249-251
+    scan_start[t] = s_start[t] + 5;
+    scan_end[t] = s_start[t + 1] - 6;
+  }
+  if (t == 0) {
+    sc->n_full = s_start[64];
+    float end_ori = 0.f;
+    if (sc->last_valid >= 0) {
+      float x, y, z; load_xyz(raw, sc->last_valid, stride, x, y, z);
+      const float start_ori = sc->start_ori;
+      end_ori = (float)((double)(-atan2f(y, x)) + 2 * kPi);  // :142-144
+      if ((double)(end_ori - start_ori) > 3 * kPi) end_ori = (float)((double)end_ori - 2 * kPi);
+      else if ((double)(end_ori - start_ori) < kPi) end_ori = (float)((double)end_ori + 2 * kPi);
+    }
+    sc->end_ori = end_ori;
+    // arm the other parity slot for the next scan
+    sc_next->first_valid = INT_MAX; sc_next->last_valid = -1; sc_next->half_idx = INT_MAX; sc_next->n_full = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CT) k_scatter(const float* __restrict__ raw, int n, int stride,
+                                                const int8_t* __restrict__ ring_in, const int* __restrict__ offsets,
+                                                const ScanScalars* __restrict__ sc, Pt4* __restrict__ full) {
+  __shared__ int s_cnt[ITERS * (CT / 32)][64];  // [slot = it*8 + warp][ring], then exclusive prefix over slots
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  for (int k = tid; k < ITERS * (CT / 32) * 64; k += CT) (&s_cnt[0][0])[k] = 0;
+  __syncthreads();
+  int ring[ITERS], rank[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    int i = blockIdx.x * CHUNK + it * CT + tid;
+    int r = (i < n) ? (int)ring_in[i] : -2;
+    ring[it] = r;
+    unsigned grp = __match_any_sync(0xffffffffu, r);
+    rank[it] = __popc(grp & ((1u << lane) - 1u));
+    if (r >= 0 && rank[it] == 0) s_cnt[it * (CT / 32) + w][r] = __popc(grp);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    int run = offsets[blockIdx.x * 64 + tid];
+#pragma unroll
+    for (int k = 0; k < ITERS * (CT / 32); ++k) { int c = s_cnt[k][tid]; s_cnt[k][tid] = run; run += c; }
+  }
+  __syncthreads();
+  const float start_ori = sc->start_ori, end_ori = sc->end_ori;
+  const int half_idx = sc->half_idx;
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int r = ring[it];
+    if (r < 0) continue;
+    int i = blockIdx.x * CHUNK + it * CT + tid;
+    float x, y, z; load_xyz(raw, i, stride, x, y, z);
+    float ori;
+    if (i <= half_idx) {           // the flipping return itself still takes the first branch (:209-224)
+      ori = ori_first_half(x, y, start_ori);
+    } else {                       // :226-236
+      ori = (float)((double)(-atan2f(y, x)) + 2 * kPi);
+      if ((double)ori < (double)end_ori - kPi * 3 / 2) ori = (float)((double)ori + 2 * kPi);
+      else if ((double)ori > (double)end_ori + kPi / 2) ori = (float)((double)ori - 2 * kPi);
+    }
+    float rel = (ori - start_ori) / (end_ori - start_ori);  // :238
+    Pt4 p; p.x = x; p.y = y; p.z = z;
+    p.i = (float)((double)r + 0.1 * (double)rel);           // :239 scanID + scanPeriod * relTime
+    full[s_cnt[it * (CT / 32) + w][r] + rank[it]] = p;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* a, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        int hi = lo + j;
+        unsigned long long x = a[lo], y = a[hi];
+        bool asc = (lo & k) == 0;
+        if ((x > y) == asc) { a[lo] = y; a[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// gap bit i = |p[i+1]-p[i]|^2 > 0.05 (float expression compared with the double literal, :324)
+__device__ __forceinline__ unsigned bits5(const unsigned* m, int from) {  // 5 bits starting at bit `from`
+  unsigned long long two = (unsigned long long)m[from >> 5] | ((unsigned long long)m[(from >> 5) + 1] << 32);
+  return (unsigned)(two >> (from & 31)) & 31u;
+}
+__device__ __forceinline__ void suppress_range(const unsigned* gap, int ind, int& lo, int& hi) {
+  unsigned fw = bits5(gap, ind);           // gaps (ind,ind+1) .. (ind+4,ind+5)
+  int f = fw ? (__ffs(fw) - 1) : 5;
+  unsigned bw = bits5(gap, ind - 5);       // gaps (ind-5,ind-4) .. (ind-1,ind) ; walk down from bit 4
+  int b = bw ? (4 - (31 - __clz(bw))) : 5;
+  lo = ind - b; hi = ind + f;
+}
+__device__ __forceinline__ void set_bits(unsigned* m, int lo, int hi) {  // single warp, called by one lane
+  for (int w = lo >> 5; w <= (hi >> 5); ++w) {
+    int a = max(lo, w << 5) & 31, b = min(hi, (w << 5) + 31) & 31;
+    unsigned mask = (b == 31 ? 0xffffffffu : ((1u << (b + 1)) - 1u)) & ~((1u << a) - 1u);
+    m[w] |= mask;
+  }
+}
+
+}  // namespace
+
+// dynamic shared memory layout (bytes): pts 16*MAXR | keys 8*MAXR | curv 4*MAXR | label MAXR | gap 4*(MAXR/32+2) | picked same
+constexpr int MAXR = ALOAM_MAX_RING;
+size_t ring_features_smem_bytes() { return (size_t)MAXR * (16 + 8 + 4 + 1) + 2 * 4 * (MAXR / 32 + 2) + 64; }
+
+__global__ void __launch_bounds__(256) k_ring_features(const Pt4* __restrict__ full, const int* __restrict__ ring_start,
+                                                       int n_scans, float leaf, Pt4* __restrict__ st_sharp,
+                                                       Pt4* __restrict__ st_less_sharp, Pt4* __restrict__ st_flat,
+                                                       Pt4* __restrict__ st_less_flat, int* __restrict__ st_counts,
+                                                       float* __restrict__ dbg_curv, int8_t* __restrict__ dbg_label,
+                                                       ScanScalars* __restrict__ sc) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Pt4* pts = reinterpret_cast<Pt4*>(smem);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + (size_t)MAXR * 16);
+  float* curv = reinterpret_cast<float*>(smem + (size_t)MAXR * 24);
+  signed char* label = reinterpret_cast<signed char*>(smem + (size_t)MAXR * 28);
+  unsigned* gap = reinterpret_cast<unsigned*>(smem + (size_t)MAXR * 29);
+  unsigned* picked = gap + (MAXR / 32 + 2);
+  __shared__ int s_i[16];
+  __shared__ float s_red[6][8];
+
+  const int ring = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g0 = ring_start[ring], nr = ring_start[ring + 1] - g0;
+  int* counts = st_counts + ring * 4;
+  if (nr > MAXR) {
+    if (tid == 0) { sc->error = ALOAM_ERR_RING_TOO_LARGE_DEV; counts[0] = counts[1] = counts[2] = counts[3] = 0; }
+    return;
+  }
+  // scanStartInd = g0+5, scanEndInd = g0+nr-6 ; skip ring if end - start < 6 (:279)
+  const int s_loc = 5, e_loc = nr - 6;
+  for (int i = tid; i < nr; i += blockDim.x) { label[i] = 0; if (dbg_label) dbg_label[g0 + i] = 0; if (dbg_curv) dbg_curv[g0 + i] = 0.f; }
+  if (e_loc - s_loc < 6) {
+    if (tid == 0) counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    return;
+  }
+  int P = 32;
+  while (P < nr) P <<= 1;
+
+  for (int i = tid; i < nr; i += blockDim.x) pts[i] = full[g0 + i];
+  for (int i = tid; i < MAXR / 32 + 2; i += blockDim.x) { gap[i] = 0; picked[i] = 0; }
+  __syncthreads();
+
+  // curvature (:256-266) for local 5 .. nr-6, left-to-right float sums ; gap bits (whole warps iterate together)
+  for (int base = warp * 32; base < nr; base += blockDim.x) {
+    const int i = base + lane;
+    float c = 0.f;
+    bool g = false;
+    if (i < nr) {
+      if (i >= 5 && i < nr - 5) {
+        float dx = pts[i - 5].x + pts[i - 4].x + pts[i - 3].x + pts[i - 2].x + pts[i - 1].x - 10 * pts[i].x + pts[i + 1].x + pts[i + 2].x + pts[i + 3].x + pts[i + 4].x + pts[i + 5].x;
+        float dy = pts[i - 5].y + pts[i - 4].y + pts[i - 3].y + pts[i - 2].y + pts[i - 1].y - 10 * pts[i].y + pts[i + 1].y + pts[i + 2].y + pts[i + 3].y + pts[i + 4].y + pts[i + 5].y;
+        float dz = pts[i - 5].z + pts[i - 4].z + pts[i - 3].z + pts[i - 2].z + pts[i - 1].z - 10 * pts[i].z + pts[i + 1].z + pts[i + 2].z + pts[i + 3].z + pts[i + 4].z + pts[i + 5].z;
+        c = dx * dx + dy * dy + dz * dz;
+      }
+      curv[i] = c;
+      if (dbg_curv) dbg_curv[g0 + i] = c;
+      if (i + 1 < nr) {
+        float dx = pts[i + 1].x - pts[i].x, dy = pts[i + 1].y - pts[i].y, dz = pts[i + 1].z - pts[i].z;
+        g = (double)(dx * dx + dy * dy + dz * dz) > 0.05;
+      }
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, g);
+    if (lane == 0) gap[base >> 5] = bal;
+  }
+  // sort keys: [segment 3b | curvature bits 32b | local index 12b] ; positions outside [s_loc, e_loc-1] -> segment 7
+  const int span = e_loc - s_loc;
+  for (int i = tid; i < P; i += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i >= s_loc && i < e_loc) {
+      // segment j covers [s + span*j/6, s + span*(j+1)/6 - 1] (:284-285)
+      int j = 0;
+      while (j < 5 && i > s_loc + span * (j + 1) / 6 - 1) ++j;
+      key = ((unsigned long long)j << 44) | ((unsigned long long)__float_as_uint(curv[i]) << 12) | (unsigned)i;
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  bitonic_sort_u64(keys, P);
+
+  // greedy picks: one warp walks the six segments in order (marks spill into the next segment, :319-342)
+  if (warp == 0) {
+    int n_sharp = 0, n_less_sharp = 0, n_flat = 0;
+    Pt4* o_sharp = st_sharp + ring * 12;
+    Pt4* o_less = st_less_sharp + ring * 120;
+    Pt4* o_flat = st_flat + ring * 24;
+    for (int j = 0; j < 6; ++j) {
+      const int sp = s_loc + span * j / 6, ep = s_loc + span * (j + 1) / 6 - 1;
+      const int lo_s = sp - s_loc, hi_s = ep - s_loc;  // range in the sorted array
+      // ---- largest curvature first (:291-344)
+      int n_large = 0;
+      bool done = false;
+      for (int top = hi_s; top >= lo_s && !done; top -= 32) {
+        int pos = top - lane;
+        bool in = pos >= lo_s;
+        unsigned long long key = in ? keys[pos] : 0ull;
+        int ind = (int)(key & 0xfffu);
+        float c = __uint_as_float((unsigned)(key >> 12));
+        bool elig = in && !((picked[ind >> 5] >> (ind & 31)) & 1u) && ((double)c > 0.1);
+        for (;;) {
+          unsigned m = __ballot_sync(0xffffffffu, elig);
+          if (!m) break;
+          int leader = __ffs(m) - 1;
+          int lind = __shfl_sync(0xffffffffu, ind, leader);
+          ++n_large;
+          if (n_large > 20) { done = true; break; }
+          int lo, hi; suppress_range(gap, lind, lo, hi);
+          if (lane == 0) {
+            Pt4 p = pts[lind];
+            if (n_large <= 2) { label[lind] = 2; o_sharp[n_sharp] = p; o_less[n_less_sharp] = p; }
+            else { label[lind] = 1; o_less[n_less_sharp] = p; }
+            set_bits(picked, lo, hi);
+          }
+          if (n_large <= 2) ++n_sharp;
+          ++n_less_sharp;
+          elig = elig && !(ind >= lo && ind <= hi);
+        }
+        __syncwarp();
+      }
+      // ---- smallest curvature first (:346-390) ; the 4th pick is emitted but not marked
+      int n_small = 0;
+      done = false;
+      for (int bot = lo_s; bot <= hi_s && !done; bot += 32) {
+        int pos = bot + lane;
+        bool in = pos <= hi_s;
+        unsigned long long key = in ? keys[pos] : 0ull;
+        int ind = (int)(key & 0xfffu);
+        float c = __uint_as_float((unsigned)(key >> 12));
+        bool elig = in && !((picked[ind >> 5] >> (ind & 31)) & 1u) && ((double)c < 0.1);
+        for (;;) {
+          unsigned m = __ballot_sync(0xffffffffu, elig);
+          if (!m) break;
+          int leader = __ffs(m) - 1;
+          int lind = __shfl_sync(0xffffffffu, ind, leader);
+          ++n_small;
+          int lo = lind, hi = lind;
+          if (n_small < 4) suppress_range(gap, lind, lo, hi);
+          if (lane == 0) {
+            label[lind] = -1;
+            o_flat[n_flat] = pts[lind];
+            if (n_small < 4) set_bits(picked, lo, hi);
+          }
+          ++n_flat;
+          if (n_small >= 4) { done = true; break; }
+          elig = elig && !(ind >= lo && ind <= hi);
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) { counts[0] = n_sharp; counts[1] = n_less_sharp; counts[2] = n_flat; }
+  }
+  __syncthreads();
+  if (dbg_label) for (int i = tid; i < nr; i += blockDim.x) dbg_label[g0 + i] = label[i];
+
+  // ---- less-flat candidates = positions [s_loc, e_loc-1] with label <= 0 (:392-398), voxel-filtered per ring (:401-407)
+  // pcl::VoxelGrid::applyFilter: bounding box, voxel index, sort by (index, position), float centroid per voxel
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int my_cnt = 0;
+  for (int i = s_loc + tid; i < e_loc; i += blockDim.x) {
+    if (label[i] <= 0) {
+      ++my_cnt;
+      mn[0] = fminf(mn[0], pts[i].x); mn[1] = fminf(mn[1], pts[i].y); mn[2] = fminf(mn[2], pts[i].z);
+      mx[0] = fmaxf(mx[0], pts[i].x); mx[1] = fmaxf(mx[1], pts[i].y); mx[2] = fmaxf(mx[2], pts[i].z);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], d));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], d));
+    }
+    if (lane == 0) { s_red[a][warp] = mn[a]; s_red[3 + a][warp] = mx[a]; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float lo = s_red[a][0], hi = s_red[3 + a][0];
+    for (int w2 = 1; w2 < (int)(blockDim.x >> 5); ++w2) { lo = fminf(lo, s_red[a][w2]); hi = fmaxf(hi, s_red[3 + a][w2]); }
+    mn[a] = lo; mx[a] = hi;
+  }
+  const float inv = 1.0f / leaf;  // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
+  long long dxyz[3];
+  int min_b[3], div_b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    dxyz[a] = (long long)((mx[a] - mn[a]) * inv) + 1;
+    min_b[a] = (int)floorf(mn[a] * inv);
+    div_b[a] = (int)floorf(mx[a] * inv) - min_b[a] + 1;
+  }
+  const bool any_cand = mn[0] <= mx[0];
+  const bool overflow = any_cand && (dxyz[0] * dxyz[1] * dxyz[2] > (long long)INT_MAX);
+  // keys: [voxel idx 32b | local position 12b], non-candidates last
+  for (int i = tid; i < P; i += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i >= s_loc && i < e_loc && label[i] <= 0) {
+      unsigned idx = 0;
+      if (!overflow) {
+        int i0 = (int)(floorf(pts[i].x * inv) - (float)min_b[0]);
+        int i1 = (int)(floorf(pts[i].y * inv) - (float)min_b[1]);
+        int i2 = (int)(floorf(pts[i].z * inv) - (float)min_b[2]);
+        idx = (unsigned)(i0 + i1 * div_b[0] + i2 * div_b[0] * div_b[1]);
+      }
+      key = ((unsigned long long)idx << 12) | (unsigned)i;
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  bitonic_sort_u64(keys, P);  // overflow case: idx = 0 everywhere => position order (output = input, PCL's early return)
+
+  // head flags -> output slots ; each thread owns E consecutive sorted slots
+  const int E = P / (int)blockDim.x > 0 ? P / (int)blockDim.x : 1;
+  const int k0 = tid * E;
+  int heads = 0;
+  for (int k = k0; k < k0 + E && k < P; ++k) {
+    unsigned long long key = keys[k];
+    if (key == ~0ull) break;
+    bool head = overflow || k == 0 || (unsigned)(keys[k - 1] >> 12) != (unsigned)(key >> 12);
+    heads += head ? 1 : 0;
+  }
+  // block exclusive scan of `heads`
+  int incl = heads;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) s_i[warp] = incl;
+  __syncthreads();
+  int wbase = 0, total = 0;
+  for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) { if (w2 < warp) wbase += s_i[w2]; total += s_i[w2]; }
+  int slot = wbase + incl - heads;
+  Pt4* o_lf = st_less_flat + (size_t)ring * MAXR;
+  for (int k = k0; k < k0 + E && k < P; ++k) {
+    unsigned long long key = keys[k];
+    if (key == ~0ull) break;
+    unsigned idx = (unsigned)(key >> 12);
+    bool head = overflow || k == 0 || (unsigned)(keys[k - 1] >> 12) != idx;
+    if (!head) continue;
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int cnt = 0;
+    for (int k2 = k; k2 < P; ++k2) {  // float accumulation in sorted order, then divide (pcl::CentroidPoint)
+      unsigned long long key2 = keys[k2];
+      if (key2 == ~0ull || (!overflow && (unsigned)(key2 >> 12) != idx) || (overflow && k2 > k)) break;
+      const Pt4 p = pts[(int)(key2 & 0xfffu)];
+      sx += p.x; sy += p.y; sz += p.z; si += p.i;
+      ++cnt;
+    }
+    const float nf = (float)cnt;
+    Pt4 o; o.x = sx / nf; o.y = sy / nf; o.z = sz / nf; o.i = si / nf;
+    o_lf[slot++] = o;
+  }
+  if (tid == 0) counts[3] = total;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ring-ordered concatenation of the staged per-ring outputs ; also ring_start tables of the two "less" clouds
+__global__ void __launch_bounds__(128) k_compact(int n_scans, const Pt4* __restrict__ st_sharp,
+                                                 const Pt4* __restrict__ st_less_sharp, const Pt4* __restrict__ st_flat,
+                                                 const Pt4* __restrict__ st_less_flat, const int* __restrict__ st_counts,
+                                                 Pt4* __restrict__ sharp, Pt4* __restrict__ less_sharp,
+                                                 Pt4* __restrict__ flat, Pt4* __restrict__ less_flat,
+                                                 int* __restrict__ counts, int* __restrict__ rs_less_sharp,
+                                                 int* __restrict__ rs_less_flat) {
+  __shared__ int s_off[4];
+  const int ring = blockIdx.x, tid = threadIdx.x;
+  if (tid < 4) {
+    int off = 0;
+    for (int r = 0; r < ring; ++r) off += st_counts[r * 4 + tid];
+    s_off[tid] = off;
+    if (tid == 1) rs_less_sharp[ring] = off;
+    if (tid == 3) rs_less_flat[ring] = off;
+    if (ring == n_scans - 1) {
+      int tot = off + st_counts[ring * 4 + tid];
+      counts[tid] = tot;
+      if (tid == 1) for (int r = n_scans; r <= 64; ++r) rs_less_sharp[r] = tot;
+      if (tid == 3) for (int r = n_scans; r <= 64; ++r) rs_less_flat[r] = tot;
+    }
+  }
+  __syncthreads();
+  const int c0 = st_counts[ring * 4], c1 = st_counts[ring * 4 + 1], c2 = st_counts[ring * 4 + 2], c3 = st_counts[ring * 4 + 3];
+  for (int i = tid; i < c0; i += blockDim.x) sharp[s_off[0] + i] = st_sharp[ring * 12 + i];
+  for (int i = tid; i < c1; i += blockDim.x) less_sharp[s_off[1] + i] = st_less_sharp[ring * 120 + i];
+  for (int i = tid; i < c2; i += blockDim.x) flat[s_off[2] + i] = st_flat[ring * 24 + i];
+  for (int i = tid; i < c3; i += blockDim.x) less_flat[s_off[3] + i] = st_less_flat[(size_t)ring * MAXR + i];
+}
+
+}  // namespace aloam

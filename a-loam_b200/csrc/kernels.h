@@ -1,0 +1,80 @@
+// Kernel declarations shared between the .cu translation units and the host-side context (capi.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include "common.cuh"
+
+#define ALOAM_MAX_RING 4096                  // == ALOAM_MAX_RING_POINTS of the public header
+#define ALOAM_ERR_RING_TOO_LARGE_DEV (-7)    // == ALOAM_ERR_RING_TOO_LARGE
+#define ALOAM_TILE 32                        // points per AABB tile of a "last" cloud
+#define ALOAM_LM_THREADS 512
+#define ALOAM_LM_MAX_TRACE 8
+
+namespace aloam {
+
+// ---- features.cu
+size_t ring_features_smem_bytes();
+__global__ void k_classify(const float* raw, int n, int stride, int n_scans, float thres2, int8_t* ring_out, int* hist,
+                           ScanScalars* sc);
+__global__ void k_ring_scan(const float* raw, int stride, int nblocks, int n_scans, const int* hist, int* offsets,
+                            int* ring_start, int* scan_start, int* scan_end, ScanScalars* sc, ScanScalars* sc_next);
+__global__ void k_scatter(const float* raw, int n, int stride, const int8_t* ring_in, const int* offsets,
+                          const ScanScalars* sc, Pt4* full);
+__global__ void k_ring_features(const Pt4* full, const int* ring_start, int n_scans, float leaf, Pt4* st_sharp,
+                                Pt4* st_less_sharp, Pt4* st_flat, Pt4* st_less_flat, int* st_counts, float* dbg_curv,
+                                int8_t* dbg_label, ScanScalars* sc);
+__global__ void k_compact(int n_scans, const Pt4* st_sharp, const Pt4* st_less_sharp, const Pt4* st_flat,
+                          const Pt4* st_less_flat, const int* st_counts, Pt4* sharp, Pt4* less_sharp, Pt4* flat,
+                          Pt4* less_flat, int* counts, int* rs_less_sharp, int* rs_less_flat);
+
+// ---- odometry.cu
+// "last" cloud index = what replaces the kd-tree build of laserOdometry.cpp:567-568: ring offsets + 32-point AABB tiles
+struct LastCloud {
+  const Pt4* pts;
+  const int* n;          // device scalar: number of points
+  const int* ring_start; // [65] first index of each ring (ring-major ascending cloud)
+  const float* tile_lo;  // [ntiles][4] AABB min (x,y,z,-)
+  const float* tile_hi;  // [ntiles][4] AABB max
+};
+__global__ void k_ring_offsets(const Pt4* pts, int n, int* ring_start, int* err);
+__global__ void k_tile_bounds(const Pt4* pts, const int* n_ptr, float* tile_lo, float* tile_hi);
+
+// one residual block, ready for the LM kernel (doubles; built once per association like the Ceres cost functions)
+struct __align__(8) BlockRec {
+  double cp[3];  // curr_point (untransformed)
+  double a[3];   // edge: last_point_a          plane: last_point_j      plane-norm: unit normal
+  double b[3];   // edge: last_point_b          plane: ljm_norm          plane-norm: unused
+  double s;      // edge: |a-b|  (de.norm())    plane: unused            plane-norm: negative_OA_dot_norm
+  int type;      // 0 edge, 1 plane, 2 plane-norm, -1 = no residual (query without correspondence)
+  int pad;
+};
+struct OdomParams { double dist_sq_thresh; double nearby_scan; };
+__global__ void k_odom_assoc(const Pt4* sharp, const Pt4* flat, const int* feat_counts /*[4]*/, LastCloud corner,
+                             LastCloud surf, const double* pose7, OdomParams prm, BlockRec* blocks,
+                             int* corr /*[(n_sharp+n_flat)][4] a,b,c,valid*/, int max_sharp);
+__global__ void k_knn_last(LastCloud cloud, const Pt4* queries, int nq, int* idx, float* sqd);
+
+// ---- lm.cu
+struct LmParams {
+  int max_iters;
+  double huber_a;
+  double initial_radius, max_radius, min_radius;
+  double min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
+  double function_tolerance, gradient_tolerance, parameter_tolerance;
+  int max_invalid;
+};
+struct LmSummary {
+  int termination, num_iterations, num_successful, num_jac_evals;
+  int n_edge, n_plane;      // residual blocks by kind
+  double initial_cost, final_cost;
+  int trace_rows; int pad;
+  double trace[ALOAM_LM_MAX_TRACE][8];
+};
+// mode 0: full trust-region solve, x updated in place ; mode 1: one evaluation, out28 = [JtJ upper 21, g 6, cost]
+// integrate != 0 : after the solve compose the world pose (laserOdometry.cpp:504-505): world7 <- world7 (+) x
+__global__ void k_lm_solve(const BlockRec* blocks, const int* n_blocks_ptr, int n_blocks_host, double* x7,
+                           LmParams prm, LmSummary* summary, int mode, double* out28, double* world7, int integrate);
+// packs API-side residual blocks (11 doubles) into BlockRec
+__global__ void k_pack_blocks(const double* packed, int n, BlockRec* out);
+
+}  // namespace aloam

@@ -1,0 +1,122 @@
+"""GPU parity: scan-to-scan association + LM (laserOdometry.cpp:274-568, lidarFactor.hpp) vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import rot_angle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pair(orc, synth, scans):
+    """features of two consecutive HDL-64 scans (oracle, canonical)"""
+    ns, _, mr = synth.SENSORS["HDL-64"][:3]
+    f0 = orc.Features(scans("HDL-64", 0), ns, mr)
+    f1 = orc.Features(scans("HDL-64", 1), ns, mr)
+    return f0, f1
+
+
+@pytest.fixture(scope="module")
+def ctx(aloam):
+    c = aloam.Aloam(n_scans=64, max_points=200000)
+    yield c
+    c.close()
+
+
+def test_knn_exact(ctx, orc, pair):
+    f0, f1 = pair
+    ctx.odometry_set_last(f0.less_sharp, f0.less_flat)
+    for which, cloud, q in [(0, f0.less_sharp, f1.sharp), (1, f0.less_flat, f1.flat), (1, f0.less_flat, f1.less_sharp[:3000])]:
+        idx, sqd = ctx.knn(which, q, 1)
+        ridx, rsqd = orc.bruteforce_knn(cloud, q, 1)
+        assert np.array_equal(idx, ridx)
+        assert np.array_equal(sqd, rsqd)  # float-exact distances
+        kidx, ksqd = orc.KdTree(cloud).knn(q, 1)
+        assert np.array_equal(kidx, ridx) and np.array_equal(ksqd, rsqd)
+
+
+@pytest.mark.parametrize("pose", [([0, 0, 0, 1.0], [0, 0, 0.0]), ([0.001, -0.002, 0.008, 0.99996], [0.7, 0.02, -0.01])])
+def test_association_exact(ctx, orc, pair, pose):
+    f0, f1 = pair
+    q = np.array(pose[0]); q /= np.linalg.norm(q)
+    t = np.array(pose[1])
+    od = orc.Odometry()
+    od.set_last(f0.less_sharp, f0.less_flat)
+    cc, pc, blocks = od.associate(f1.sharp, f1.flat, q, t)
+    ctx.odometry_set_last(f0.less_sharp, f0.less_flat)
+    gcc, gpc = ctx.odometry_associate(f1.sharp, f1.flat, q, t)
+    got_c = [(i, a, b) for i, (a, b, v) in enumerate(gcc) if v]
+    got_p = [(i, a, b, c) for i, (a, b, c, v) in enumerate(gpc) if v]
+    assert got_c == [tuple(r) for r in cc]
+    assert got_p == [tuple(r) for r in pc]
+    assert len(got_c) > 500 and len(got_p) > 1000
+
+
+def test_normal_equations(ctx, orc, pair):
+    f0, f1 = pair
+    od = orc.Odometry()
+    od.set_last(f0.less_sharp, f0.less_flat)
+    q = np.array([0.002, 0.001, 0.004, 1.0]); q /= np.linalg.norm(q)
+    t = np.array([0.5, 0.05, 0.0])
+    _, _, blocks = od.associate(f1.sharp, f1.flat, q, t)
+    x = np.concatenate([q, t])
+    for autodiff in (True, False):
+        JtJ, Jtr, cost = orc.normal_equations(blocks, x, autodiff=autodiff)
+        g_JtJ, g_Jtr, g_cost = ctx.normal_equations(blocks, x)
+        assert abs(g_cost - cost) <= 1e-12 * cost
+        assert np.abs(g_JtJ - JtJ).max() <= 1e-10 * np.abs(JtJ).max()
+        assert np.abs(g_Jtr - Jtr).max() <= 1e-10 * np.abs(Jtr).max()
+
+
+def test_solve_matches_ceres_restatement(ctx, orc, pair):
+    f0, f1 = pair
+    od = orc.Odometry()
+    od.set_last(f0.less_sharp, f0.less_flat)
+    x0 = np.array([0, 0, 0, 1.0, 0, 0, 0])
+    _, _, blocks = od.associate(f1.sharp, f1.flat, x0[:4], x0[4:])
+    xr, sr, tr = orc.solve(blocks, x0, max_iters=4)
+    xg, sg, tg = ctx.solve(blocks, x0)
+    assert sg["termination"] == sr["termination"]
+    assert sg["num_iterations"] == sr["num_iterations"] and sg["num_successful"] == sr["num_successful"]
+    assert np.abs(xg - xr).max() < 1e-9
+    assert abs(sg["final_cost"] - sr["final_cost"]) < 1e-9 * sr["final_cost"]
+    n = min(len(tr), len(tg))
+    assert np.allclose(tg[:n, [0, 5]], tr[:n, [0, 5]], rtol=1e-8)  # cost and trust-region radius, step by step
+    # empty problem: parameters untouched
+    xe, se, _ = ctx.solve(np.zeros((0, 11)), x0)
+    assert np.array_equal(xe, x0) and se["termination"] == 4
+
+
+def test_register_pose(ctx, orc, pair):
+    f0, f1 = pair
+    od = orc.Odometry()
+    od.set_last(f0.less_sharp, f0.less_flat)
+    q, t, info = od.register(f1.sharp, f1.flat, [0, 0, 0, 1.0], [0, 0, 0.0])
+    ctx.odometry_set_last(f0.less_sharp, f0.less_flat)
+    gq, gt, st = ctx.odometry_register(f1.sharp, f1.flat, [0, 0, 0, 1.0], [0, 0, 0.0])
+    assert np.abs(gt - t).max() < 1e-4 and rot_angle(gq, q) < 1e-4     # the north-star tolerance
+    assert np.abs(gt - t).max() < 1e-8 and rot_angle(gq, q) < 1e-7     # what the design actually delivers
+    assert st["n_corner_corr"] == info["corner_corr"] and st["n_plane_corr"] == info["plane_corr"]
+
+
+@pytest.mark.parametrize("sensor,frames", [("HDL-64", 6), ("VLP-16", 5), ("HDL-32", 4)])
+def test_fused_pipeline_poses(aloam, orc, synth, scans, sensor, frames):
+    """raw scans -> world poses, fused device pipeline vs oracle pipeline (extract -> register -> integrate -> set_last)"""
+    ns, _, mr = synth.SENSORS[sensor][:3]
+    c = aloam.Aloam(n_scans=ns, max_points=200000)
+    od = orc.Odometry()
+    q = np.array([0, 0, 0, 1.0]); t = np.zeros(3)
+    qw = np.array([0, 0, 0, 1.0]); tw = np.zeros(3)
+    for k in range(frames):
+        raw = scans(sensor, k)
+        f = orc.Features(raw, ns, mr)
+        if k > 0:
+            q, t, _ = od.register(f.sharp, f.flat, q, t)
+            qw, tw = orc.integrate_pose(qw, tw, q, t)
+        od.set_last(f.less_sharp, f.less_flat)
+        gq, gt, st = c.scan_to_pose(raw)
+        if k == 0:
+            assert st["flags"] & aloam.FLAG_INITIALISED_ONLY
+        assert np.abs(gt - tw).max() < 1e-4 and rot_angle(gq, qw) < 1e-4, (k, gt, tw)
+        assert np.abs(gt - tw).max() < 1e-7, (k, gt - tw)
+    c.close()
