@@ -53,8 +53,8 @@ class AloamError(RuntimeError):
 
 
 def build(force=False, verbose=False):
-    from . import build as _b  # noqa
-    return _b.build(force=force, verbose=verbose)
+    from . import _build
+    return _build.build(force=force, verbose=verbose)
 
 
 def lib():
@@ -86,6 +86,10 @@ def lib():
         L.aloam_normal_equations.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp, dp]
         L.aloam_solve.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp, C.c_int, ip]
         L.aloam_debug_features.argtypes = [C.c_void_p, fp, ip, ip, ip]
+        L.aloam_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.aloam_profile_read.argtypes = [C.c_void_p, dp, C.POINTER(C.c_longlong), C.POINTER(C.c_char_p), C.c_int]
+        L.aloam_launch_count.argtypes = [C.c_void_p]
+        L.aloam_launch_count.restype = C.c_longlong
         _LIB = L
     return _LIB
 
@@ -234,6 +238,21 @@ class Aloam:
 
     def reset_odometry(self):
         _check(lib().aloam_reset_odometry(self._h))
+
+    # --- measurement hooks
+    def profile_enable(self, on=True):
+        _check(lib().aloam_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} measured with CUDA events on the ctx stream"""
+        ms = (C.c_double * 16)()
+        cnt = (C.c_longlong * 16)()
+        names = (C.c_char_p * 16)()
+        n = lib().aloam_profile_read(self._h, ms, cnt, names, 16)
+        return {names[k].decode(): (ms[k], cnt[k]) for k in range(n) if names[k] and cnt[k] > 0}
+
+    def launch_count(self):
+        return int(lib().aloam_launch_count(self._h))
 
     # --- fine-grained
     def knn(self, which, queries, k):

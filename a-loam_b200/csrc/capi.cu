@@ -58,6 +58,14 @@ struct aloam_ctx {
   double* h_dbl = nullptr;      // scratch doubles
   LmSummary* h_summary = nullptr;
   ScanScalars* h_sc = nullptr;
+  // per-kernel profiler (bench.py roofline leg) + cumulative launch counter
+  bool prof_on = false;
+  cudaEvent_t prof_ev[64] = {};
+  int prof_kid[32] = {};
+  int prof_n = 0;
+  double prof_ms[ALOAM_N_KERNEL_IDS] = {};
+  long long prof_cnt[ALOAM_N_KERNEL_IDS] = {};
+  long long launches = 0;
   // state
   int parity = 0;         // ScanScalars slot of the next scan
   int frame = 0;          // fused pipeline: scans seen
@@ -67,6 +75,30 @@ struct aloam_ctx {
 };
 
 namespace {
+
+enum { KID_CLASSIFY = 0, KID_RING_SCAN, KID_SCATTER, KID_RING_FEATURES, KID_COMPACT, KID_TILE_BOUNDS, KID_ODOM_ASSOC, KID_LM_SOLVE,
+       KID_RING_OFFSETS, KID_KNN_LAST, KID_PACK_BLOCKS, KID_MAP_GRID, KID_MAP_KNN_FIT, KID_VOXEL };
+const char* const kKernelNames[ALOAM_N_KERNEL_IDS] = {"k_classify", "k_ring_scan", "k_scatter", "k_ring_features", "k_compact",
+    "k_tile_bounds", "k_odom_assoc", "k_lm_solve", "k_ring_offsets", "k_knn_last", "k_pack_blocks", "k_map_grid", "k_map_knn_fit",
+    "k_voxel", "", ""};
+
+inline void prof_begin(aloam_ctx* c, int kid) {
+  ++c->launches;
+  if (c->prof_on && c->prof_n < 32) { cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream); c->prof_kid[c->prof_n] = kid; }
+}
+inline void prof_end(aloam_ctx* c) {
+  if (c->prof_on && c->prof_n < 32) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream); ++c->prof_n; }
+}
+// call after the stream has been synchronised
+inline void prof_collect(aloam_ctx* c) {
+  for (int i = 0; i < c->prof_n; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]) == cudaSuccess) { c->prof_ms[c->prof_kid[i]] += ms; ++c->prof_cnt[c->prof_kid[i]]; }
+  }
+  c->prof_n = 0;
+}
+#define LAUNCH(c, kid, kernel, grid, block, smem, ...) \
+  do { prof_begin(c, kid); kernel<<<grid, block, smem, (c)->stream>>>(__VA_ARGS__); prof_end(c); } while (0)
 
 LmParams lm_params(const aloam_config& c) {
   LmParams p;
@@ -102,16 +134,14 @@ int run_features(aloam_ctx* c, const float* d_raw, int n, int stride, FeatBuf& o
   const float thres = c->cfg.minimum_range;
   ScanScalars* sc = c->d_sc + c->parity;
   ScanScalars* sc_next = c->d_sc + (c->parity ^ 1);
-  k_classify<<<nb, 256, 0, c->stream>>>(d_raw, n, stride, c->cfg.n_scans, thres * thres, c->d_ring, c->d_hist, sc);
-  k_ring_scan<<<1, 1024, 0, c->stream>>>(d_raw, stride, nb, c->cfg.n_scans, c->d_hist, c->d_offsets, c->d_ring_start,
-                                         c->d_scan_start, c->d_scan_end, sc, sc_next);
-  k_scatter<<<nb, 256, 0, c->stream>>>(d_raw, n, stride, c->d_ring, c->d_offsets, sc, c->d_full);
-  k_ring_features<<<c->cfg.n_scans, 256, ring_features_smem_bytes(), c->stream>>>(
-      c->d_full, c->d_ring_start, c->cfg.n_scans, 0.2f, c->st_sharp, c->st_less_sharp, c->st_flat, c->st_less_flat,
-      c->st_counts, c->d_curv, c->d_label, sc);
-  k_compact<<<c->cfg.n_scans, 128, 0, c->stream>>>(c->cfg.n_scans, c->st_sharp, c->st_less_sharp, c->st_flat,
-                                                   c->st_less_flat, c->st_counts, out.sharp, out.less_sharp, out.flat,
-                                                   out.less_flat, out.counts, out.rs_ls, out.rs_lf);
+  LAUNCH(c, KID_CLASSIFY, k_classify, nb, 256, 0, d_raw, n, stride, c->cfg.n_scans, thres * thres, c->d_ring, c->d_hist, sc);
+  LAUNCH(c, KID_RING_SCAN, k_ring_scan, 1, 1024, 0, d_raw, stride, nb, c->cfg.n_scans, c->d_hist, c->d_offsets, c->d_ring_start,
+         c->d_scan_start, c->d_scan_end, sc, sc_next);
+  LAUNCH(c, KID_SCATTER, k_scatter, nb, 256, 0, d_raw, n, stride, c->d_ring, c->d_offsets, sc, c->d_full);
+  LAUNCH(c, KID_RING_FEATURES, k_ring_features, c->cfg.n_scans, 256, ring_features_smem_bytes(), c->d_full, c->d_ring_start,
+         c->cfg.n_scans, 0.2f, c->st_sharp, c->st_less_sharp, c->st_flat, c->st_less_flat, c->st_counts, c->d_curv, c->d_label, sc);
+  LAUNCH(c, KID_COMPACT, k_compact, c->cfg.n_scans, 128, 0, c->cfg.n_scans, c->st_sharp, c->st_less_sharp, c->st_flat,
+         c->st_less_flat, c->st_counts, out.sharp, out.less_sharp, out.flat, out.less_flat, out.counts, out.rs_ls, out.rs_lf);
   c->parity ^= 1;
   CUDA_CHECK_RET(cudaGetLastError());
   return ALOAM_OK;
@@ -119,8 +149,8 @@ int run_features(aloam_ctx* c, const float* d_raw, int n, int stride, FeatBuf& o
 
 void run_tile_bounds(aloam_ctx* c, FeatBuf& f) {
   const int blocks = (c->tile_cap + 7) / 8;
-  k_tile_bounds<<<blocks, 256, 0, c->stream>>>(f.less_sharp, f.counts + 1, f.tlo_ls, f.thi_ls);
-  k_tile_bounds<<<blocks, 256, 0, c->stream>>>(f.less_flat, f.counts + 3, f.tlo_lf, f.thi_lf);
+  LAUNCH(c, KID_TILE_BOUNDS, k_tile_bounds, blocks, 256, 0, f.less_sharp, f.counts + 1, f.tlo_ls, f.thi_ls);
+  LAUNCH(c, KID_TILE_BOUNDS, k_tile_bounds, blocks, 256, 0, f.less_flat, f.counts + 3, f.tlo_lf, f.thi_lf);
 }
 
 // outer_iters x (association + LM) ; `cur` supplies sharp/flat, `last` the targets ; pose in c->d_pose
@@ -130,11 +160,12 @@ void run_register(aloam_ctx* c, const FeatBuf& cur, const FeatBuf& last, int sha
   const LmParams lp = lm_params(c->cfg);
   const int slots = sharp_slots + flat_slots;
   for (int it = 0; it < c->cfg.outer_iters; ++it) {
-    k_odom_assoc<<<(slots + 7) / 8, 256, 0, c->stream>>>(cur.sharp, cur.flat, cur.counts, last_corner(last), last_surf(last),
-                                                         c->d_pose, op, c->d_blocks, d_corr, sharp_slots);
+    if (slots > 0)
+      LAUNCH(c, KID_ODOM_ASSOC, k_odom_assoc, (slots + 7) / 8, 256, 0, cur.sharp, cur.flat, cur.counts, last_corner(last),
+             last_surf(last), c->d_pose, op, c->d_blocks, d_corr, sharp_slots);
     const bool last_it = it == c->cfg.outer_iters - 1;
-    k_lm_solve<<<1, ALOAM_LM_THREADS, 0, c->stream>>>(c->d_blocks, nullptr, slots, c->d_pose, lp, c->d_summary + (it & 3), 0,
-                                                      nullptr, c->d_world, (integrate && last_it) ? 1 : 0);
+    LAUNCH(c, KID_LM_SOLVE, k_lm_solve, 1, ALOAM_LM_THREADS, 0, c->d_blocks, nullptr, slots, c->d_pose, lp, c->d_summary + (it & 3), 0,
+           nullptr, c->d_world, (integrate && last_it) ? 1 : 0);
   }
 }
 
@@ -213,6 +244,7 @@ int aloam_destroy(aloam_ctx* c) {
   if (c->h_dbl) cudaFreeHost(c->h_dbl);
   if (c->h_summary) cudaFreeHost(c->h_summary);
   if (c->h_sc) cudaFreeHost(c->h_sc);
+  for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -250,6 +282,7 @@ int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
 #define TRY(e) do { if ((e) != cudaSuccess) { fprintf(stderr, "[aloam_b200] %s failed: %s\n", #e, cudaGetErrorString(cudaGetLastError())); aloam_destroy(c); return ALOAM_ERR_CUDA; } } while (0)
   TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   TRY(cudaEventCreate(&c->ev0)); TRY(cudaEventCreate(&c->ev1));
+  for (cudaEvent_t& e : c->prof_ev) TRY(cudaEventCreate(&e));
   TRY(dalloc(&c->d_raw, mp * 8));
   TRY(dalloc(&c->d_ring, mp));
   TRY(dalloc(&c->d_hist, (size_t)c->nblocks_max * 64)); TRY(dalloc(&c->d_offsets, (size_t)c->nblocks_max * 64));
@@ -350,8 +383,8 @@ int aloam_odometry_set_last(aloam_ctx* c, aloam_cloud_view corner_last, aloam_cl
   CUDA_CHECK_RET(cudaMemsetAsync(f.rs_ls, 0, 72 * 4, c->stream));
   CUDA_CHECK_RET(cudaMemsetAsync(f.rs_lf, 0, 72 * 4, c->stream));
   CUDA_CHECK_RET(cudaMemsetAsync(c->d_err, 0, 4, c->stream));
-  if (corner_last.n > 0) k_ring_offsets<<<(corner_last.n + 255) / 256, 256, 0, c->stream>>>(f.less_sharp, corner_last.n, f.rs_ls, c->d_err);
-  if (surf_last.n > 0) k_ring_offsets<<<(surf_last.n + 255) / 256, 256, 0, c->stream>>>(f.less_flat, surf_last.n, f.rs_lf, c->d_err);
+  if (corner_last.n > 0) LAUNCH(c, KID_RING_OFFSETS, k_ring_offsets, (corner_last.n + 255) / 256, 256, 0, f.less_sharp, corner_last.n, f.rs_ls, c->d_err);
+  if (surf_last.n > 0) LAUNCH(c, KID_RING_OFFSETS, k_ring_offsets, (surf_last.n + 255) / 256, 256, 0, f.less_flat, surf_last.n, f.rs_lf, c->d_err);
   run_tile_bounds(c, f);
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints + 8, c->d_err, 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
@@ -408,8 +441,8 @@ int aloam_odometry_associate(aloam_ctx* c, aloam_cloud_view sharp, aloam_cloud_v
   OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan};
   const int slots = sharp.n + flat.n;
   if (slots > 0)
-    k_odom_assoc<<<(slots + 7) / 8, 256, 0, c->stream>>>(cur.sharp, cur.flat, cur.counts, last_corner(c->feat[0]),
-                                                         last_surf(c->feat[0]), c->d_pose, op, c->d_blocks, c->d_corr, sharp.n);
+    LAUNCH(c, KID_ODOM_ASSOC, k_odom_assoc, (slots + 7) / 8, 256, 0, cur.sharp, cur.flat, cur.counts, last_corner(c->feat[0]),
+           last_surf(c->feat[0]), c->d_pose, op, c->d_blocks, c->d_corr, sharp.n);
   std::vector<int> h((size_t)slots * 4 + 4);
   if (slots > 0) CUDA_CHECK_RET(cudaMemcpyAsync(h.data(), c->d_corr, (size_t)slots * 16, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
@@ -442,6 +475,7 @@ static int scan_to_pose_impl(aloam_ctx* c, const float* d_raw, int n, int stride
   CUDA_CHECK_RET(cudaEventRecord(c->ev1, c->stream));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
   CUDA_CHECK_RET(cudaGetLastError());
+  prof_collect(c);
   if (c->h_sc->error) {
     int e = c->h_sc->error;
     CUDA_CHECK_RET(cudaMemset(&(c->d_sc + slot)->error, 0, 4));
@@ -490,7 +524,7 @@ int aloam_knn(aloam_ctx* c, int which, aloam_cloud_view queries, int k, int* idx
     rc = upload_cloud(c, queries, c->d_query, c->max_points); if (rc) return rc;
     if (queries.n > 0) {
       LastCloud L = which == 0 ? last_corner(c->feat[0]) : last_surf(c->feat[0]);
-      k_knn_last<<<(queries.n + 7) / 8, 256, 0, c->stream>>>(L, c->d_query, queries.n, c->d_knn_idx, c->d_knn_d);
+      LAUNCH(c, KID_KNN_LAST, k_knn_last, (queries.n + 7) / 8, 256, 0, L, c->d_query, queries.n, c->d_knn_idx, c->d_knn_d);
       CUDA_CHECK_RET(cudaMemcpyAsync(idx, c->d_knn_idx, (size_t)queries.n * 4, cudaMemcpyDeviceToHost, c->stream));
       CUDA_CHECK_RET(cudaMemcpyAsync(sqdist, c->d_knn_d, (size_t)queries.n * 4, cudaMemcpyDeviceToHost, c->stream));
     }
@@ -505,12 +539,12 @@ static int run_lm_api(aloam_ctx* c, const double* blocks, int n_blocks, const do
   if (n_blocks < 0 || n_blocks > 2 * kMaxQueries) return ALOAM_ERR_CAPACITY;
   if (n_blocks > 0) {
     CUDA_CHECK_RET(cudaMemcpyAsync(c->d_packed, blocks, (size_t)n_blocks * 11 * 8, cudaMemcpyHostToDevice, c->stream));
-    k_pack_blocks<<<(n_blocks + 255) / 256, 256, 0, c->stream>>>(c->d_packed, n_blocks, c->d_blocks);
+    LAUNCH(c, KID_PACK_BLOCKS, k_pack_blocks, (n_blocks + 255) / 256, 256, 0, c->d_packed, n_blocks, c->d_blocks);
   }
   for (int k = 0; k < 7; ++k) c->h_dbl[k] = x[k];
   CUDA_CHECK_RET(cudaMemcpyAsync(c->d_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
-  k_lm_solve<<<1, ALOAM_LM_THREADS, 0, c->stream>>>(c->d_blocks, nullptr, n_blocks, c->d_pose, lm_params(c->cfg), c->d_summary, mode,
-                                                    c->d_out28, nullptr, 0);
+  LAUNCH(c, KID_LM_SOLVE, k_lm_solve, 1, ALOAM_LM_THREADS, 0, c->d_blocks, nullptr, n_blocks, c->d_pose, lm_params(c->cfg), c->d_summary, mode,
+         c->d_out28, nullptr, 0);
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 8, c->d_pose, 56, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 32, c->d_out28, 28 * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(LmSummary), cudaMemcpyDeviceToHost, c->stream));
@@ -552,6 +586,22 @@ int aloam_solve(aloam_ctx* c, const double* blocks, int n_blocks, double x[7], d
   if (trace_rows) *trace_rows = rows;
   return ALOAM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ profiling hooks
+int aloam_profile_enable(aloam_ctx* c, int on) {
+  if (!c) return ALOAM_ERR_INVALID_ARG;
+  c->prof_on = on != 0;
+  c->prof_n = 0;
+  for (int k = 0; k < ALOAM_N_KERNEL_IDS; ++k) { c->prof_ms[k] = 0; c->prof_cnt[k] = 0; }
+  return ALOAM_OK;
+}
+int aloam_profile_read(aloam_ctx* c, double* ms_sum, long long* count, const char** names, int capacity) {
+  if (!c) return ALOAM_ERR_INVALID_ARG;
+  int n = capacity < ALOAM_N_KERNEL_IDS ? capacity : ALOAM_N_KERNEL_IDS;
+  for (int k = 0; k < n; ++k) { if (ms_sum) ms_sum[k] = c->prof_ms[k]; if (count) count[k] = c->prof_cnt[k]; if (names) names[k] = kKernelNames[k]; }
+  return n;
+}
+long long aloam_launch_count(aloam_ctx* c) { return c ? c->launches : 0; }
 
 // ------------------------------------------------------------------------------------------------ mapping (mapping.cu)
 int aloam_map_upload_impl(aloam_ctx* c, aloam_cloud_view corner_map, aloam_cloud_view surf_map);

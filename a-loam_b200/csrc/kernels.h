@@ -9,6 +9,7 @@
 #define ALOAM_TILE 32                        // points per AABB tile of a "last" cloud
 #define ALOAM_LM_THREADS 512
 #define ALOAM_LM_MAX_TRACE 8
+#define ALOAM_N_KERNEL_IDS 16
 
 namespace aloam {
 

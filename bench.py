@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- scans/sec of the A-LOAM per-scan registration hot path on B200 (BASELINE.json metric).
+
+A "step" = one HDL-64-shaped synthetic scan (64x2000 firing pattern, ~128k returns, ~102k kept) through the
+whole hot path: feature extraction -> 2 x (correspondence search + LM solve) -> pose integration -> index build
+for the next scan, i.e. configs[1] of BASELINE.json.  Scans are consecutive poses of one seeded trajectory; the
+odometry of scan k depends on scan k-1 exactly as in the reference (warm start + "last" clouds).
+
+  value : scans/s with the raw scans already resident in HBM (aloam_scan_to_pose_device)
+  e2e   : scans/s through the public C ABI with HOST buffers: per step the raw scan is copied host->device from
+          pinned memory and the pose is read back (aloam_scan_to_pose)
+  --impl reference : the CPU oracle (a C++ restatement of the reference's Ceres+PCL path -- the reference itself
+          cannot be built in this image) run as the reference runs it: extraction and odometry as two pipelined
+          single-threaded stages (ascanRegistration | alaserOdometry)
+
+L2 hygiene: every step reads a raw scan that has never been touched before (1 + warmup + steps distinct scans of
+~2 MB each; with the defaults 141 MB > the 126 MB L2), so inputs always come from HBM.
+Timing: each C-ABI call is synchronous (returns after its stream is drained), so the K-step loop is bracketed by
+barrier + synchronize and timed on the host; the per-call device time (CUDA events on the context's stream) is
+reported next to it.  Multi-GPU: one process per GPU, independent scan streams (replicas, weak scaling, no
+data-path collective), time = max over ranks.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SENSOR = "HDL-64"
+
+
+def gen_scans(synth, count, seed):
+    scans = [synth.scan(SENSOR, k, seed=seed) for k in range(count)]
+    return scans
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_pipeline_sequential(orc, synth, scans):
+    """single-threaded oracle: extract -> register -> integrate -> set_last per scan; returns seconds per stage"""
+    ns, _, mr = synth.SENSORS[SENSOR][:3]
+    od = orc.Odometry()
+    q = np.array([0, 0, 0, 1.0]); t = np.zeros(3)
+    qw = np.array([0, 0, 0, 1.0]); tw = np.zeros(3)
+    t_ext = t_odo = 0.0
+    t0 = time.perf_counter()
+    for k, raw in enumerate(scans):
+        a = time.perf_counter()
+        f = orc.Features(raw, ns, mr, orc.SORT_LITERAL)
+        b = time.perf_counter()
+        if k > 0:
+            q, t, _ = od.register(f.sharp, f.flat, q, t)
+            qw, tw = orc.integrate_pose(qw, tw, q, t)
+        od.set_last(f.less_sharp, f.less_flat)
+        c = time.perf_counter()
+        t_ext += b - a
+        t_odo += c - b
+    return time.perf_counter() - t0, t_ext, t_odo
+
+
+def cpu_pipeline_two_stage(orc, synth, scans, warmup):
+    """the reference's process structure for this path: ascanRegistration | alaserOdometry, one thread each.
+    Returns seconds for the scans after `warmup` (steady state, measured at the odometry stage output)."""
+    import queue
+    ns, _, mr = synth.SENSORS[SENSOR][:3]
+    qu = queue.Queue(maxsize=4)
+
+    def extractor():
+        for raw in scans:
+            qu.put(orc.Features(raw, ns, mr, orc.SORT_LITERAL))
+        qu.put(None)
+
+    th = threading.Thread(target=extractor, daemon=True)
+    od = orc.Odometry()
+    q = np.array([0, 0, 0, 1.0]); t = np.zeros(3)
+    qw = np.array([0, 0, 0, 1.0]); tw = np.zeros(3)
+    th.start()
+    k = 0
+    t_start = None
+    while True:
+        f = qu.get()
+        if f is None:
+            break
+        if k == warmup + 1:
+            t_start = time.perf_counter()
+        if k > 0:
+            q, t, _ = od.register(f.sharp, f.flat, q, t)
+            qw, tw = orc.integrate_pose(qw, tw, q, t)
+        od.set_last(f.less_sharp, f.less_flat)
+        k += 1
+    return time.perf_counter() - t_start
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    K, W = args.steps, max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_scans_needed = 1 + W + K
+
+    synth = importlib.import_module("a-loam_b200.synth")
+    config = {"workload": "HDL-64 synthetic 64x2000 scan-to-scan odometry (BASELINE.json configs[1]): feature extraction + "
+                          "2 x (k-NN association + <=4-iter LM) + index build, consecutive scans of one trajectory",
+              "sensor": SENSOR, "azimuth_steps": 2000, "beams": 64, "outer_iters": 2, "inner_iters": 4,
+              "parallelism": "replicas x%d (independent scan streams, no collective)" % max(world, 1)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import pyoracle as orc
+        scans = gen_scans(synth, n_scans_needed, synth.BASE_SEED + 1)
+        secs = cpu_pipeline_two_stage(orc, synth, scans, W)
+        val = K / secs
+        line = {"impl": "reference", "metric": "scans/sec", "value": val, "unit": "scans/s", "n_gpus": args.gpus, "steps": K,
+                "warmup": W, "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32/f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "scans/s", "cores": 2, "kind": "port",
+                                 "sample": "%d consecutive HDL-64 scans after %d warm-up; CPU oracle (C++ restatement of the "
+                                           "Ceres+PCL path, g++ -O3 no -march), extraction and odometry as two pipelined "
+                                           "single-threaded stages like the reference's two ROS nodes" % (K, W)},
+                "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("a-loam_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    scans = gen_scans(synth, n_scans_needed, synth.BASE_SEED + 1 + rank)
+    counts = [s.shape[0] for s in scans]
+    maxn = max(counts)
+    host = torch.zeros((n_scans_needed, maxn, 4), dtype=torch.float32).pin_memory()
+    for i, s in enumerate(scans):
+        host[i, :s.shape[0]] = torch.from_numpy(s)
+    dev = host.to("cuda", non_blocking=False)
+    torch.cuda.synchronize()
+    ctx = pkg.Aloam(n_scans=64, device=local_rank, max_points=maxn + 1024)
+
+    def run(mode, timed_steps, profile=False):
+        """returns (wall seconds for the timed steps, sum of per-call device ms, launches, last pose)"""
+        ctx.reset_odometry()
+        ctx.profile_enable(profile)
+
+        def step(i):
+            if mode == "device":
+                return ctx.scan_to_pose_device(dev[i].data_ptr(), counts[i])
+            return ctx.scan_to_pose_ptr(host[i].data_ptr(), counts[i])
+        for i in range(1 + W):       # frame 0 only initialises; then W untimed warm-up steps
+            step(i)
+        barrier()
+        l0 = ctx.launch_count()
+        dev_ms = 0.0
+        t0 = time.perf_counter()
+        for i in range(1 + W, 1 + W + timed_steps):
+            q, t, st = step(i)
+            dev_ms += st.ms_total
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        return t1 - t0, dev_ms, ctx.launch_count() - l0, (q, t)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    secs_dev, devms_dev, launches, pose_dev = run("device", K)
+    secs_e2e, devms_e2e, _, pose_e2e = run("host", K)
+    clocks = sampler.stop()
+    _, _, _, _ = run("device", K, profile=True)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([secs_dev, secs_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        secs_dev, secs_e2e = float(tt[0]), float(tt[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+
+    if rank == 0:
+        # sizes of one representative scan for the algorithmic-bytes model
+        feats = ctx.extract_features(scans[1 + W])
+        n_raw = counts[1 + W]
+        n_full = feats["full"].shape[0]
+        n_q = feats["sharp"].shape[0] + feats["flat"].shape[0]
+        n_m = feats["less_sharp"].shape[0] + feats["less_flat"].shape[0]
+        n_out = n_q + n_m
+        alg_bytes = {
+            "k_classify": 16 * n_raw + n_raw,
+            "k_ring_scan": 2 * 4 * 64 * ((n_raw + 1023) // 1024),
+            "k_scatter": 16 * n_raw + n_raw + 16 * n_full,
+            "k_ring_features": 16 * n_full + 16 * n_out + 5 * n_full,
+            "k_compact": 2 * 16 * n_out,
+            "k_tile_bounds": 16 * n_m / 2 + 32 * (n_m / 32) / 2,   # per launch (two launches, one per cloud)
+            "k_odom_assoc": 16 * n_m + 16 * n_q + 8 * 3 * n_q + 88 * n_q,
+            "k_lm_solve": 88 * (768 + 1536) * 5,
+        }
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
+        per_kernel = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / K, "ms_per_step": v[0] / K} for k, v in prof.items()}
+        dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
+        dom_ms = per_kernel[dom]["ms_per_launch"]
+        achieved = alg_bytes.get(dom, 0) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes.get(dom, 0),
+                    "ms_per_launch": dom_ms, "per_kernel": per_kernel,
+                    "note": "single ~2 MB scans are latency/occupancy bound, not HBM bound (SURVEY.md 8d): frac is expected << 1"}
+
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            import pyoracle as orc
+            sample = scans[:min(len(scans), 1 + 60)]
+            tot, t_ext, t_odo = cpu_pipeline_sequential(orc, synth, sample)
+            cpu_baseline = {"value": (len(sample) - 1) / tot, "unit": "scans/s", "cores": 1, "kind": "port",
+                            "sample": "%d consecutive HDL-64 scans of the same stream, single thread; extraction %.1f ms/scan, "
+                                      "odometry (kd-tree builds + 2 x (association + LM)) %.1f ms/scan" %
+                                      (len(sample), 1e3 * t_ext / len(sample), 1e3 * t_odo / len(sample))}
+        total_scans = K * world
+        config["points_per_scan_raw"] = n_raw
+        config["points_per_scan_kept"] = n_full
+        config["queries_per_scan"] = n_q
+        config["targets_per_scan"] = n_m
+        config["l2"] = ("inputs larger than L2: %d distinct raw scans of %.2f MB = %.0f MB > 126 MB, each read once"
+                        % (n_scans_needed, 16 * n_raw / 1e6, 16 * n_raw * n_scans_needed / 1e6))
+        line = {"metric": "scans/sec", "value": total_scans / secs_dev, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": 1e3 * secs_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32/f64", "data": "synthetic", "config": config, "clocks": clocks,
+                "device_ms_per_step": devms_dev / K,
+                "e2e": {"value": total_scans / secs_e2e, "unit": "scans/s", "h2d_bytes_per_step": 16 * n_raw,
+                        "d2h_bytes_per_step": 56 + 4 * 560 + 32, "ms_per_step": 1e3 * secs_e2e / K,
+                        "api": "aloam_scan_to_pose (host pinned raw scan in, world pose + solver summaries out)"},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "pose_check": {"t_w_device_vs_host_path_maxabs": float(np.abs(pose_dev[1] - pose_e2e[1]).max())}}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

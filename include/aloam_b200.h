@@ -140,6 +140,11 @@ int aloam_solve(aloam_ctx* ctx, const double* blocks, int n_blocks, double x[7],
 /* last extract_features call: per-point curvature (scanRegistration.cpp:262), label (:303,309,355), ring start/end */
 int aloam_debug_features(aloam_ctx* ctx, float* curvature, int* label, int* scan_start, int* scan_end);
 
+/* ---- measurement hooks (bench.py): per-kernel CUDA-event timing on the ctx stream, and a launch counter */
+int aloam_profile_enable(aloam_ctx* ctx, int on);
+int aloam_profile_read(aloam_ctx* ctx, double* ms_sum, long long* count, const char** names, int capacity);
+long long aloam_launch_count(aloam_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif
