@@ -10,8 +10,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libaloam_b200.so")
 SOURCES = ["features.cu", "odometry.cu", "lm.cu", "mapping.cu", "capi.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# float32 decision kernels must not contract a*b+c (bit parity with an x86-64 no-FMA build of the reference);
+# lm.cu is double precision, compared at 1e-9, and keeps FMA.
+FMAD = {"lm.cu": "-fmad=true"}
 
 
 def build(force=False, verbose=False):
@@ -24,7 +27,7 @@ def build(force=False, verbose=False):
     objs = []
     for s in srcs:
         o = s[:-3] + ".o"
-        cmd = [nvcc] + NVCC_FLAGS + ["-dc" if False else "-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + [FMAD.get(os.path.basename(s), "-fmad=false"), "-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -1,6 +1,7 @@
 // Host side of the C ABI (include/aloam_b200.h): context, device buffers, kernel sequencing.
 // The reference's host code around the hot path is C++ (the ROS node bodies), so this layer is C++ too.
 // No CPU fallback: every entry point runs the sm_100a kernels or returns an error.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -22,7 +23,7 @@ struct FeatBuf {
   Pt4 *sharp = nullptr, *less_sharp = nullptr, *flat = nullptr, *less_flat = nullptr;
   int* counts = nullptr;           // [4] n_sharp, n_less_sharp, n_flat, n_less_flat (device)
   int *rs_ls = nullptr, *rs_lf = nullptr;  // ring_start tables [65+]
-  float *tlo_ls = nullptr, *thi_ls = nullptr, *tlo_lf = nullptr, *thi_lf = nullptr;
+  RabIndex g_ls = {}, g_lf = {};           // (azimuth bucket x ring) indices over less_sharp / less_flat
 };
 
 }  // namespace
@@ -31,7 +32,7 @@ struct aloam_ctx {
   aloam_config cfg;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int max_points = 0, nblocks_max = 0, tile_cap = 0;
+  int max_points = 0, nblocks_max = 0;
   // raw scan + ring binning
   float* d_raw = nullptr;
   int8_t* d_ring = nullptr;
@@ -76,10 +77,10 @@ struct aloam_ctx {
 
 namespace {
 
-enum { KID_CLASSIFY = 0, KID_RING_SCAN, KID_SCATTER, KID_RING_FEATURES, KID_COMPACT, KID_TILE_BOUNDS, KID_ODOM_ASSOC, KID_LM_SOLVE,
+enum { KID_CLASSIFY = 0, KID_RING_SCAN, KID_SCATTER, KID_RING_FEATURES, KID_COMPACT, KID_GRID_BUILD, KID_ODOM_ASSOC, KID_LM_SOLVE,
        KID_RING_OFFSETS, KID_KNN_LAST, KID_PACK_BLOCKS, KID_MAP_GRID, KID_MAP_KNN_FIT, KID_VOXEL };
 const char* const kKernelNames[ALOAM_N_KERNEL_IDS] = {"k_classify", "k_ring_scan", "k_scatter", "k_ring_features", "k_compact",
-    "k_tile_bounds", "k_odom_assoc", "k_lm_solve", "k_ring_offsets", "k_knn_last", "k_pack_blocks", "k_map_grid", "k_map_knn_fit",
+    "k_rab_build(3 launches)", "k_odom_assoc", "k_lm_solve", "k_ring_offsets", "k_knn_last", "k_pack_blocks", "k_map_grid", "k_map_knn_fit",
     "k_voxel", "", ""};
 
 inline void prof_begin(aloam_ctx* c, int kid) {
@@ -99,6 +100,21 @@ inline void prof_collect(aloam_ctx* c) {
 }
 #define LAUNCH(c, kid, kernel, grid, block, smem, ...) \
   do { prof_begin(c, kid); kernel<<<grid, block, smem, (c)->stream>>>(__VA_ARGS__); prof_end(c); } while (0)
+
+// the LM kernel runs as one thread-block cluster (distributed-shared-memory reduction, see lm.cu)
+constexpr int kLmCluster = 8;
+template <typename... Args>
+void launch_lm(aloam_ctx* c, Args... args) {
+  prof_begin(c, KID_LM_SOLVE);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kLmCluster); cfg.blockDim = dim3(ALOAM_LM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kLmCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k_lm_solve, args...);
+  prof_end(c);
+}
 
 LmParams lm_params(const aloam_config& c) {
   LmParams p;
@@ -125,8 +141,8 @@ int upload_cloud(aloam_ctx* c, aloam_cloud_view v, Pt4* dst, int capacity) {
   return ALOAM_OK;
 }
 
-LastCloud last_corner(const FeatBuf& f) { return LastCloud{f.less_sharp, f.counts + 1, f.rs_ls, f.tlo_ls, f.thi_ls}; }
-LastCloud last_surf(const FeatBuf& f) { return LastCloud{f.less_flat, f.counts + 3, f.rs_lf, f.tlo_lf, f.thi_lf}; }
+LastCloud last_corner(const FeatBuf& f) { return LastCloud{f.less_sharp, f.counts + 1, f.g_ls}; }
+LastCloud last_surf(const FeatBuf& f) { return LastCloud{f.less_flat, f.counts + 3, f.g_lf}; }
 
 // feature extraction kernels on a raw scan already in device memory
 int run_features(aloam_ctx* c, const float* d_raw, int n, int stride, FeatBuf& out) {
@@ -147,10 +163,12 @@ int run_features(aloam_ctx* c, const float* d_raw, int n, int stride, FeatBuf& o
   return ALOAM_OK;
 }
 
-void run_tile_bounds(aloam_ctx* c, FeatBuf& f) {
-  const int blocks = (c->tile_cap + 7) / 8;
-  LAUNCH(c, KID_TILE_BOUNDS, k_tile_bounds, blocks, 256, 0, f.less_sharp, f.counts + 1, f.tlo_ls, f.thi_ls);
-  LAUNCH(c, KID_TILE_BOUNDS, k_tile_bounds, blocks, 256, 0, f.less_flat, f.counts + 3, f.tlo_lf, f.thi_lf);
+// index over the two "last" clouds: count -> scan -> fill (n_ls / n_lf = host upper bounds on the cloud sizes)
+void run_grid_build(aloam_ctx* c, FeatBuf& f, int n_ls, int n_lf) {
+  const int pb = (std::max(std::max(n_ls, n_lf), 1) + 255) / 256;
+  LAUNCH(c, KID_GRID_BUILD, k_rab_count, dim3(pb, 2), 256, 0, f.g_ls, f.less_sharp, f.counts + 1, f.g_lf, f.less_flat, f.counts + 3);
+  LAUNCH(c, KID_GRID_BUILD, k_rab_scan, 2, 1024, 0, f.g_ls, f.g_lf);
+  LAUNCH(c, KID_GRID_BUILD, k_rab_fill, dim3(pb, 2), 256, 0, f.g_ls, f.less_sharp, f.counts + 1, f.g_lf, f.less_flat, f.counts + 3);
 }
 
 // outer_iters x (association + LM) ; `cur` supplies sharp/flat, `last` the targets ; pose in c->d_pose
@@ -164,8 +182,8 @@ void run_register(aloam_ctx* c, const FeatBuf& cur, const FeatBuf& last, int sha
       LAUNCH(c, KID_ODOM_ASSOC, k_odom_assoc, (slots + 7) / 8, 256, 0, cur.sharp, cur.flat, cur.counts, last_corner(last),
              last_surf(last), c->d_pose, op, c->d_blocks, d_corr, sharp_slots);
     const bool last_it = it == c->cfg.outer_iters - 1;
-    LAUNCH(c, KID_LM_SOLVE, k_lm_solve, 1, ALOAM_LM_THREADS, 0, c->d_blocks, nullptr, slots, c->d_pose, lp, c->d_summary + (it & 3), 0,
-           nullptr, c->d_world, (integrate && last_it) ? 1 : 0);
+    launch_lm(c, (const BlockRec*)c->d_blocks, (const int*)nullptr, slots, c->d_pose, lp, c->d_summary + (it & 3), 0,
+              (double*)nullptr, c->d_world, (integrate && last_it) ? 1 : 0);
   }
 }
 
@@ -236,8 +254,12 @@ int aloam_destroy(aloam_ctx* c) {
                  c->d_knn_idx, c->d_knn_d};
   for (void* p : dev) if (p) cudaFree(p);
   for (FeatBuf& f : c->feat) {
-    void* fp[] = {f.sharp, f.less_sharp, f.flat, f.less_flat, f.counts, f.rs_ls, f.rs_lf, f.tlo_ls, f.thi_ls, f.tlo_lf, f.thi_lf};
+    void* fp[] = {f.sharp, f.less_sharp, f.flat, f.less_flat, f.counts, f.rs_ls, f.rs_lf};
     for (void* p : fp) if (p) cudaFree(p);
+    for (RabIndex* g : {&f.g_ls, &f.g_lf}) {
+      void* gp[] = {g->cnt, g->start, g->cell_of, g->rank_of, g->gpts};
+      for (void* p : gp) if (p) cudaFree(p);
+    }
   }
   for (Pt4* p : c->h_out) if (p) cudaFreeHost(p);
   if (c->h_ints) cudaFreeHost(c->h_ints);
@@ -277,7 +299,6 @@ int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
   c->cfg = *cfg;
   c->max_points = cfg->max_points;
   c->nblocks_max = (c->max_points + 1023) / 1024;
-  c->tile_cap = ((c->max_points + ALOAM_TILE - 1) / ALOAM_TILE + 7) / 8 * 8;
   const size_t mp = (size_t)c->max_points;
 #define TRY(e) do { if ((e) != cudaSuccess) { fprintf(stderr, "[aloam_b200] %s failed: %s\n", #e, cudaGetErrorString(cudaGetLastError())); aloam_destroy(c); return ALOAM_ERR_CUDA; } } while (0)
   TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -296,8 +317,11 @@ int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
     TRY(dalloc(&f.sharp, kMaxQueries)); TRY(dalloc(&f.flat, kMaxQueries));
     TRY(dalloc(&f.less_sharp, mp)); TRY(dalloc(&f.less_flat, mp));
     TRY(dalloc(&f.counts, 4)); TRY(dalloc(&f.rs_ls, 72)); TRY(dalloc(&f.rs_lf, 72));
-    TRY(dalloc(&f.tlo_ls, (size_t)c->tile_cap * 4)); TRY(dalloc(&f.thi_ls, (size_t)c->tile_cap * 4));
-    TRY(dalloc(&f.tlo_lf, (size_t)c->tile_cap * 4)); TRY(dalloc(&f.thi_lf, (size_t)c->tile_cap * 4));
+    for (RabIndex* g : {&f.g_ls, &f.g_lf}) {
+      TRY(dalloc(&g->cnt, (size_t)ALOAM_NB * 64)); TRY(dalloc(&g->start, (size_t)ALOAM_NB * 64 + 8));
+      TRY(dalloc(&g->cell_of, mp)); TRY(dalloc(&g->rank_of, mp)); TRY(dalloc(&g->gpts, mp));
+      TRY(cudaMemset(g->cnt, 0, (size_t)ALOAM_NB * 64 * 4)); TRY(cudaMemset(g->start, 0, ((size_t)ALOAM_NB * 64 + 8) * 4));
+    }
     TRY(cudaMemset(f.counts, 0, 16)); TRY(cudaMemset(f.rs_ls, 0, 72 * 4)); TRY(cudaMemset(f.rs_lf, 0, 72 * 4));
   }
   TRY(dalloc(&c->d_blocks, (size_t)2 * kMaxQueries)); TRY(dalloc(&c->d_corr, (size_t)2 * kMaxQueries * 4));
@@ -385,7 +409,7 @@ int aloam_odometry_set_last(aloam_ctx* c, aloam_cloud_view corner_last, aloam_cl
   CUDA_CHECK_RET(cudaMemsetAsync(c->d_err, 0, 4, c->stream));
   if (corner_last.n > 0) LAUNCH(c, KID_RING_OFFSETS, k_ring_offsets, (corner_last.n + 255) / 256, 256, 0, f.less_sharp, corner_last.n, f.rs_ls, c->d_err);
   if (surf_last.n > 0) LAUNCH(c, KID_RING_OFFSETS, k_ring_offsets, (surf_last.n + 255) / 256, 256, 0, f.less_flat, surf_last.n, f.rs_lf, c->d_err);
-  run_tile_bounds(c, f);
+  run_grid_build(c, f, corner_last.n, surf_last.n);
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints + 8, c->d_err, 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
   CUDA_CHECK_RET(cudaGetLastError());
@@ -468,7 +492,7 @@ static int scan_to_pose_impl(aloam_ctx* c, const float* d_raw, int n, int stride
   } else {
     run_register(c, cur, last, kFusedSharpSlots, kFusedFlatSlots, true, nullptr);
   }
-  run_tile_bounds(c, cur);  // index for the next scan (replaces the kd-tree rebuild, laserOdometry.cpp:567-568)
+  run_grid_build(c, cur, 64 * kMaxLessSharpPerRing, std::min(n, c->max_points));  // index for the next scan (replaces the kd-tree rebuild, laserOdometry.cpp:567-568)
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 16, c->d_world, 56, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_sc, c->d_sc + slot, sizeof(ScanScalars), cudaMemcpyDeviceToHost, c->stream));
@@ -543,8 +567,8 @@ static int run_lm_api(aloam_ctx* c, const double* blocks, int n_blocks, const do
   }
   for (int k = 0; k < 7; ++k) c->h_dbl[k] = x[k];
   CUDA_CHECK_RET(cudaMemcpyAsync(c->d_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
-  LAUNCH(c, KID_LM_SOLVE, k_lm_solve, 1, ALOAM_LM_THREADS, 0, c->d_blocks, nullptr, n_blocks, c->d_pose, lm_params(c->cfg), c->d_summary, mode,
-         c->d_out28, nullptr, 0);
+  launch_lm(c, (const BlockRec*)c->d_blocks, (const int*)nullptr, n_blocks, c->d_pose, lm_params(c->cfg), c->d_summary, mode,
+            c->d_out28, (double*)nullptr, 0);
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 8, c->d_pose, 56, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 32, c->d_out28, 28 * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(LmSummary), cudaMemcpyDeviceToHost, c->stream));

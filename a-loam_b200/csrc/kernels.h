@@ -6,8 +6,7 @@
 
 #define ALOAM_MAX_RING 4096                  // == ALOAM_MAX_RING_POINTS of the public header
 #define ALOAM_ERR_RING_TOO_LARGE_DEV (-7)    // == ALOAM_ERR_RING_TOO_LARGE
-#define ALOAM_TILE 32                        // points per AABB tile of a "last" cloud
-#define ALOAM_LM_THREADS 512
+#define ALOAM_LM_THREADS 256
 #define ALOAM_LM_MAX_TRACE 8
 #define ALOAM_N_KERNEL_IDS 16
 
@@ -29,16 +28,24 @@ __global__ void k_compact(int n_scans, const Pt4* st_sharp, const Pt4* st_less_s
                           Pt4* less_flat, int* counts, int* rs_less_sharp, int* rs_less_flat);
 
 // ---- odometry.cu
-// "last" cloud index = what replaces the kd-tree build of laserOdometry.cpp:567-568: ring offsets + 32-point AABB tiles
+// (azimuth bucket x ring) index over one cloud = what replaces a kd-tree build (laserOdometry.cpp:567-568)
+#define ALOAM_NB 128   // azimuth buckets (2.8 deg)
+struct RabIndex {
+  int* cnt;         // [NB*64] scratch counters (left zeroed by k_rab_scan)
+  int* start;       // [NB*64 + 1] first slot of cell (bucket*64 + ring) in gpts
+  int* cell_of;     // [capacity] cell of point i
+  int* rank_of;     // [capacity] rank of point i inside its cell
+  float4* gpts;     // [capacity] cell-contiguous copy: x, y, z, bits(ring << 24 | original index)
+};
 struct LastCloud {
-  const Pt4* pts;
-  const int* n;          // device scalar: number of points
-  const int* ring_start; // [65] first index of each ring (ring-major ascending cloud)
-  const float* tile_lo;  // [ntiles][4] AABB min (x,y,z,-)
-  const float* tile_hi;  // [ntiles][4] AABB max
+  const Pt4* pts;   // the cloud in its original (ring-major) order
+  const int* n;     // device scalar: number of points
+  RabIndex index;
 };
 __global__ void k_ring_offsets(const Pt4* pts, int n, int* ring_start, int* err);
-__global__ void k_tile_bounds(const Pt4* pts, const int* n_ptr, float* tile_lo, float* tile_hi);
+__global__ void k_rab_count(RabIndex a, const Pt4* pa, const int* na, RabIndex b, const Pt4* pb, const int* nb);
+__global__ void k_rab_scan(RabIndex a, RabIndex b);
+__global__ void k_rab_fill(RabIndex a, const Pt4* pa, const int* na, RabIndex b, const Pt4* pb, const int* nb);
 
 // one residual block, ready for the LM kernel (doubles; built once per association like the Ceres cost functions)
 struct __align__(8) BlockRec {

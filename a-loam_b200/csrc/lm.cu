@@ -3,20 +3,31 @@
 // :106-138 plane-norm) and everything Ceres drives around them (AutoDiff Jacobians, HuberLoss(0.1) + Corrector,
 // EigenQuaternionParameterization, trust-region loop, DENSE_QR step).
 //
-// B200 shape: the whole solve is ONE kernel launch and never returns to the host.  Each pass evaluates every
-// residual block with the closed-form tangent Jacobian (SURVEY.md 8a "Residual math"), accumulates the 28
-// numbers that the 6-dof problem reduces to -- upper triangle of J^T J (21), J^T r (6), cost (1) -- with a
-// fixed-shape warp-shuffle + shared-memory tree (deterministic, no float atomics), and thread 0 takes the
-// trust-region decision exactly as Ceres' TrustRegionMinimizer / LevenbergMarquardtStrategy would:
+// B200 shape: the whole solve is ONE launch of ONE thread-block cluster (8 CTAs x 512 threads, co-scheduled on one
+// GPC) and never returns to the host.  Each pass evaluates every residual block with the closed-form tangent
+// Jacobian (SURVEY.md 8a "Residual math") and reduces the 28 numbers the 6-dof problem boils down to -- upper
+// triangle of J^T J (21), J^T r (6), cost (1):
+//     thread  -> warp   : transposed butterfly (31 shuffles instead of 28 x 5), lane L ends up owning number L
+//     warp    -> CTA    : shared memory, fixed order
+//     CTA     -> cluster: every CTA reads all 8 partial vectors through DISTRIBUTED SHARED MEMORY in rank order,
+//                         so all CTAs hold bit-identical totals after one cluster barrier (double-buffered).
+// No float atomics anywhere => run-to-run deterministic.  Thread 0 of every CTA then takes the SAME trust-region
+// decision redundantly (no broadcast step), exactly as Ceres' TrustRegionMinimizer / LevenbergMarquardtStrategy:
 //   Jacobi scaling 1/(1+||J_j||) fixed at iteration 0, D^2 = clamp(diag(Js^T Js), 1e-6, 1e32) (re-used after a
 //   rejected step), (Js^T Js + D^2/radius) y = Js^T r  [normal-equation form of Ceres' QR on [Js; sqrt(D^2/radius)]],
-//   model_cost_change, Plus(), parameter / function tolerance tests, rho > 1e-3 accept with radius/(max(1/3,1-(2rho-1)^3)),
-//   reject with radius/decrease_factor, decrease_factor *= 2.
-// Because the candidate evaluation already carries J^T J and J^T r, an accepted step needs no second pass
-// (Ceres evaluates cost-only, then re-evaluates with Jacobians): <= 1 + max_iters passes per solve instead of <= 1 + 2*max_iters.
+//   model_cost_change, Plus(), parameter / function tolerance tests, rho > 1e-3 accept with
+//   radius / max(1/3, 1-(2 rho-1)^3), reject with radius / decrease_factor, decrease_factor *= 2.
+// The candidate evaluation already carries J^T J and J^T r, so an accepted step needs no second pass (Ceres
+// evaluates cost-only, then re-evaluates with Jacobians): <= 1 + max_iters passes per solve instead of <= 1 + 2 max_iters.
+//
+// This file is compiled WITH fused multiply-add (the only one): the solve is double precision and is compared to the
+// oracle at 1e-9, not bit for bit; the float32 decisions that must be bit-exact live in features.cu / odometry.cu.
 #include <cfloat>
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace aloam {
 
@@ -40,6 +51,17 @@ __device__ __forceinline__ void accumulate_row(double* acc, const double j[6], d
   for (int a = 0; a < 6; ++a) acc[21 + a] += j[a] * r;
 }
 
+__device__ __forceinline__ void huber_rho(double huber_a, double sq, double& rho0, double& sr) {
+  const double bb = huber_a * huber_a;
+  if (sq > bb) {
+    const double rr = sqrt(sq);
+    rho0 = 2.0 * huber_a * rr - bb;
+    sr = sqrt(fmax(DBL_MIN, huber_a / rr));   // Corrector: rho'' <= 0 => scale residual and Jacobian by sqrt(rho')
+  } else {
+    rho0 = sq; sr = 1.0;
+  }
+}
+
 __device__ __forceinline__ void eval_block(const BlockRec& rb, const double* x, double huber_a, double* acc) {
   // lp = R(q) cp + t   (s == 1 for every block the reference builds; slerp(1, q) == q)
   const V3 u{x[0], x[1], x[2]};
@@ -57,22 +79,17 @@ __device__ __forceinline__ void eval_block(const BlockRec& rb, const double* x, 
     const V3 la{lp.x - a.x, lp.y - a.y, lp.z - a.z}, lb{lp.x - b.x, lp.y - b.y, lp.z - b.z};
     const V3 nu = crossd(la, lb);
     const double dn = rb.s;  // |a - b|
-    double r[3] = {nu.x / dn, nu.y / dn, nu.z / dn};
+    const double r[3] = {nu.x / dn, nu.y / dn, nu.z / dn};
     const V3 wv{(b.x - a.x) / dn, (b.y - a.y) / dn, (b.z - a.z) / dn};
     // d r / d lp = [wv]x ; rows: n0 = (0,-wz,wy), n1 = (wz,0,-wx), n2 = (-wy,wx,0)
-    const V3 n0{0.0, -wv.z, wv.y}, n1{wv.z, 0.0, -wv.x}, n2{-wv.y, wv.x, 0.0};
-    const double sq = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-    double rho0, rho1;
-    const double bb = huber_a * huber_a;
-    if (sq > bb) { const double rr = sqrt(sq); rho0 = 2.0 * huber_a * rr - bb; rho1 = fmax(DBL_MIN, huber_a / rr); }
-    else { rho0 = sq; rho1 = 1.0; }
+    const V3 ns[3] = {V3{0.0, -wv.z, wv.y}, V3{wv.z, 0.0, -wv.x}, V3{-wv.y, wv.x, 0.0}};
+    double rho0, sr;
+    huber_rho(huber_a, r[0] * r[0] + r[1] * r[1] + r[2] * r[2], rho0, sr);
     acc[27] += 0.5 * rho0;
-    const double sr = sqrt(rho1);
-    const V3 ns[3] = {n0, n1, n2};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const V3 t = crossd(Rp, ns[k]);  // n^T (-2 [Rp]x) = 2 (Rp x n)^T
-      double j[6] = {2.0 * t.x * sr, 2.0 * t.y * sr, 2.0 * t.z * sr, ns[k].x * sr, ns[k].y * sr, ns[k].z * sr};
+      const V3 t = crossd(Rp, ns[k]);
+      const double j[6] = {2.0 * t.x * sr, 2.0 * t.y * sr, 2.0 * t.z * sr, ns[k].x * sr, ns[k].y * sr, ns[k].z * sr};
       accumulate_row(acc, j, r[k] * sr);
     }
   } else {
@@ -84,21 +101,33 @@ __device__ __forceinline__ void eval_block(const BlockRec& rb, const double* x, 
       n = V3{rb.a[0], rb.a[1], rb.a[2]};
       r = n.x * lp.x + n.y * lp.y + n.z * lp.z + rb.s;
     }
-    const double sq = r * r;
-    double rho0, rho1;
-    const double bb = huber_a * huber_a;
-    if (sq > bb) { const double rr = sqrt(sq); rho0 = 2.0 * huber_a * rr - bb; rho1 = fmax(DBL_MIN, huber_a / rr); }
-    else { rho0 = sq; rho1 = 1.0; }
+    double rho0, sr;
+    huber_rho(huber_a, r * r, rho0, sr);
     acc[27] += 0.5 * rho0;
-    const double sr = sqrt(rho1);
     const V3 t = crossd(Rp, n);
-    double j[6] = {2.0 * t.x * sr, 2.0 * t.y * sr, 2.0 * t.z * sr, n.x * sr, n.y * sr, n.z * sr};
+    const double j[6] = {2.0 * t.x * sr, 2.0 * t.y * sr, 2.0 * t.z * sr, n.x * sr, n.y * sr, n.z * sr};
     accumulate_row(acc, j, r * sr);
   }
 }
 
+// 32 values per lane -> lane L holds the warp total of value L (fixed summation tree)
+__device__ __forceinline__ double warp_transpose_reduce(double (&v)[32]) {
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = upper ? v[i] : v[i + half];
+      const double keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
 // ceres::EigenQuaternionParameterization::Plus + plain addition on t
-__device__ void plus7(const double* x, const double* d, double* o) {
+__device__ __forceinline__ void plus7(const double* x, const double* d, double* o) {
   const double n = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
   if (n > 0.0) {
     const double s = sin(n) / n;
@@ -114,38 +143,64 @@ __device__ void plus7(const double* x, const double* d, double* o) {
   o[4] = x[4] + d[3]; o[5] = x[5] + d[4]; o[6] = x[6] + d[5];
 }
 
-__device__ __forceinline__ int tri(int a, int b) {  // index of (a,b), a<=b, in the packed upper triangle
-  return a * 6 - a * (a - 1) / 2 + (b - a);
+// trust-region state of one solve; lives in shared memory, touched by thread 0 only
+struct TrState {
+  double x[7], xc[7], H[6][6], g[6], scale[6], diag[6];
+  double cost, radius, decrease_factor, mcc, gmax, x_norm;
+  int reuse_diag, last_successful, iteration, num_invalid, num_successful, num_evals, termination, trace_rows;
+};
+
+__device__ double gradient_max(const double* x, const double* g) {
+  double ng[6], xp[7];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) ng[k] = -g[k];
+  plus7(x, ng, xp);
+  double m = 0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) m = fmax(m, fabs(xp[k] - x[k]));
+  return m;
 }
 
-// solve (A) y = b, A symmetric positive definite 6x6 (full storage), Cholesky
-__device__ bool chol_solve6(double A[6][6], const double b[6], double y[6]) {
+// (Hs + diag/radius) y = b by Cholesky ; returns false on breakdown
+__device__ bool chol_solve6(const double Hs[6][6], const double* dg, double radius, const double* b, double* y) {
+  double L[6][6];
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double d = A[j][j];
-    for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
+    double d = Hs[j][j] + dg[j] / radius;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) if (k < j) d -= L[j][k] * L[j][k];
     if (!(d > 0.0)) return false;
     d = sqrt(d);
-    A[j][j] = d;
-    for (int i = j + 1; i < 6; ++i) {
-      double s = A[i][j];
-      for (int k = 0; k < j; ++k) s -= A[i][k] * A[j][k];
-      A[i][j] = s / d;
+    L[j][j] = d;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (i > j) {
+        double s = Hs[i][j];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k < j) s -= L[i][k] * L[j][k];
+        L[i][j] = s / d;
+      }
     }
   }
   double z[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
-    for (int k = 0; k < i; ++k) s -= A[i][k] * z[k];
-    z[i] = s / A[i][i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) if (k < i) s -= L[i][k] * z[k];
+    z[i] = s / L[i][i];
   }
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = z[i];
-    for (int k = i + 1; k < 6; ++k) s -= A[k][i] * y[k];
-    y[i] = s / A[i][i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) if (k > i) s -= L[k][i] * y[k];
+    y[i] = s / L[i][i];
   }
-  for (int i = 0; i < 6; ++i)
-    if (!isfinite(y[i])) return false;
-  return true;
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ok = ok && isfinite(y[i]);
+  return ok;
 }
 
 }  // namespace
@@ -170,186 +225,209 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
                                                     int n_blocks_host, double* __restrict__ x7, LmParams prm,
                                                     LmSummary* __restrict__ summary, int mode, double* __restrict__ out28,
                                                     double* __restrict__ world7, int integrate) {
-  __shared__ double s_part[NW][28];
-  __shared__ double s_tot[28];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
+  __shared__ double s_part[NW][32];
+  __shared__ double s_cta[2][32];   // this CTA's partial totals, double-buffered by pass parity (read by the whole cluster)
+  __shared__ double s_tot[32];
   __shared__ double s_x[7];
   __shared__ int s_go;
   __shared__ int s_cnt[2];
+  __shared__ TrState T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = n_blocks_ptr ? *n_blocks_ptr : n_blocks_host;
+  const int gtid = (int)crank * NT + tid, gstride = (int)csize * NT;
+  const bool writer = crank == 0 && tid == 0;
+  int pass = 0;
 
   if (tid < 7) s_x[tid] = x7[tid];
-  if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
   __syncthreads();
 
-  // residual-block census (n_edge / n_plane), once
-  {
-    int ne = 0, np = 0;
-    for (int b = tid; b < n; b += NT) { int t = blocks[b].type; ne += (t == 0); np += (t > 0); }
-    for (int d = 16; d > 0; d >>= 1) { ne += __shfl_xor_sync(0xffffffffu, ne, d); np += __shfl_xor_sync(0xffffffffu, np, d); }
-    if (lane == 0) { atomicAdd(&s_cnt[0], ne); atomicAdd(&s_cnt[1], np); }
-  }
-
-  auto evaluate = [&]() {
+  // one evaluation of all residual blocks at s_x -> s_tot[0..27] (identical in every CTA of the cluster).
+  // `census` additionally counts edge / plane blocks (slots 28 / 29 of the same reduction, first pass only).
+  auto evaluate = [&](bool census) {
     double x[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) x[k] = s_x[k];
-    double acc[28];
+    double acc[32];
 #pragma unroll
-    for (int k = 0; k < 28; ++k) acc[k] = 0.0;
-    for (int b = tid; b < n; b += NT) {
+    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+    for (int b = gtid; b < n; b += gstride) {
       const BlockRec rb = blocks[b];
-      if (rb.type >= 0) eval_block(rb, x, prm.huber_a, acc);
+      if (rb.type >= 0) {
+        eval_block(rb, x, prm.huber_a, acc);
+        if (census) { acc[28] += (rb.type == 0) ? 1.0 : 0.0; acc[29] += (rb.type > 0) ? 1.0 : 0.0; }
+      }
     }
-#pragma unroll
-    for (int k = 0; k < 28; ++k) {
-      double v = acc[k];
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-      if (lane == 0) s_part[warp][k] = v;
-    }
+    const double mine = warp_transpose_reduce(acc);
+    s_part[warp][lane] = mine;
     __syncthreads();
-    if (tid < 28) {
+    if (tid < 32) {
       double v = 0.0;
 #pragma unroll
       for (int w2 = 0; w2 < NW; ++w2) v += s_part[w2][tid];
+      s_cta[pass & 1][tid] = v;
+    }
+    cluster.sync();
+    if (tid < 32) {
+      double v = 0.0;
+      for (unsigned r = 0; r < csize; ++r) {
+        const double* remote = cluster.map_shared_rank(&s_cta[pass & 1][0], r);
+        v += remote[tid];
+      }
       s_tot[tid] = v;
     }
+    ++pass;
     __syncthreads();
   };
 
-  evaluate();
+  evaluate(true);
 
   if (mode == 1) {
-    if (tid < 28) out28[tid] = s_tot[tid];
+    if (crank == 0 && tid < 28) out28[tid] = s_tot[tid];
+    cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
     return;
   }
 
-  // ---------------- thread-0 trust-region state
-  double x[7], H[21], g[6], cost = 0, scale[6], diag[6], radius = prm.initial_radius, decrease_factor = 2.0;
-  double xc[7], mcc = 0, gmax = 0, x_norm = 0;
-  bool reuse_diag = false, last_successful = false;
-  int iteration = 0, num_invalid = 0, num_successful = 0, num_evals = 1, termination = 0, trace_rows = 0;
-  const int n_res = s_cnt[0] + s_cnt[1];
-
-  auto gradient_max = [&](const double* xx, const double* gg) {
-    double ng[6], xp[7];
-    for (int k = 0; k < 6; ++k) ng[k] = -gg[k];
-    plus7(xx, ng, xp);
-    double m = 0;
-    for (int k = 0; k < 7; ++k) m = fmax(m, fabs(xp[k] - xx[k]));
-    return m;
-  };
   auto trace = [&](double c, double cc, double gm, double sn, double rd, double rad, int valid, int succ) {
-    if (trace_rows < ALOAM_LM_MAX_TRACE) {
-      double* o = summary->trace[trace_rows++];
-      o[0] = c; o[1] = cc; o[2] = gm; o[3] = sn; o[4] = rd; o[5] = rad; o[6] = valid; o[7] = succ;
+    if (T.trace_rows < ALOAM_LM_MAX_TRACE) {
+      if (writer) {
+        double* o = summary->trace[T.trace_rows];
+        o[0] = c; o[1] = cc; o[2] = gm; o[3] = sn; o[4] = rd; o[5] = rad; o[6] = valid; o[7] = succ;
+      }
+      ++T.trace_rows;
     }
   };
-  // produce the next candidate (-> s_x, s_go = 1) or stop (s_go = 0)
+  // produce the next candidate (-> s_x, s_go = 1) or stop (s_go = 0) ; thread 0 only
   auto next_candidate = [&]() {
     for (;;) {
-      if (iteration >= prm.max_iters) { termination = 0; s_go = 0; return; }
-      if (last_successful && gmax <= prm.gradient_tolerance) { termination = 1; s_go = 0; return; }
-      if (radius < prm.min_radius) { termination = 5; s_go = 0; return; }
-      ++iteration;
-      last_successful = false;
-      if (!reuse_diag)
-        for (int j = 0; j < 6; ++j) diag[j] = fmin(fmax(scale[j] * scale[j] * H[tri(j, j)], prm.min_lm_diagonal), prm.max_lm_diagonal);
-      double A[6][6], Hs[6][6], b[6], y[6];
-      for (int a = 0; a < 6; ++a) {
-        for (int c = a; c < 6; ++c) { double v = scale[a] * H[tri(a, c)] * scale[c]; Hs[a][c] = v; Hs[c][a] = v; }
-        b[a] = scale[a] * g[a];
+      if (T.iteration >= prm.max_iters) { T.termination = 0; s_go = 0; return; }
+      if (T.last_successful && T.gmax <= prm.gradient_tolerance) { T.termination = 1; s_go = 0; return; }
+      if (T.radius < prm.min_radius) { T.termination = 5; s_go = 0; return; }
+      ++T.iteration;
+      T.last_successful = 0;
+      if (!T.reuse_diag) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) T.diag[j] = fmin(fmax(T.scale[j] * T.scale[j] * T.H[j][j], prm.min_lm_diagonal), prm.max_lm_diagonal);
       }
-      for (int a = 0; a < 6; ++a)
-        for (int c = 0; c < 6; ++c) A[a][c] = Hs[a][c] + (a == c ? diag[a] / radius : 0.0);
-      bool ok = chol_solve6(A, b, y);
-      reuse_diag = true;
+      double Hs[6][6], b[6], y[6], dg[6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) Hs[a][c] = T.scale[a] * T.H[a][c] * T.scale[c];
+        b[a] = T.scale[a] * T.g[a];
+        dg[a] = T.diag[a];
+      }
+      const bool ok = chol_solve6(Hs, dg, T.radius, b, y);
+      T.reuse_diag = 1;
       double step[6];
-      mcc = 0;
+      double mcc = 0;
       if (ok) {
-        for (int k = 0; k < 6; ++k) step[k] = -y[k];
         // model_cost_change = -(Js step)^T (r + Js step / 2) = -step^T Js^T r - 1/2 step^T Js^T Js step
         double sb = 0, shs = 0;
+#pragma unroll
         for (int a = 0; a < 6; ++a) {
-          sb += step[a] * b[a];
+          step[a] = -y[a];
+          sb -= y[a] * b[a];
           double t = 0;
-          for (int c = 0; c < 6; ++c) t += Hs[a][c] * step[c];
-          shs += step[a] * t;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) t -= Hs[a][c] * y[c];
+          shs -= y[a] * t;
         }
         mcc = -sb - 0.5 * shs;
       }
+      T.mcc = mcc;
       if (!(ok && mcc > 0.0)) {  // invalid step
-        if (++num_invalid >= prm.max_invalid) { trace(cost, 0, gmax, 0, 0, radius, 0, 0); termination = 5; s_go = 0; return; }
-        radius *= 0.5;
-        reuse_diag = true;
-        trace(cost, 0, gmax, 0, 0, radius, 0, 0);
+        if (++T.num_invalid >= prm.max_invalid) { trace(T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0); T.termination = 5; s_go = 0; return; }
+        T.radius *= 0.5;
+        trace(T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0);
         continue;
       }
-      num_invalid = 0;
+      T.num_invalid = 0;
       double delta[6];
-      for (int k = 0; k < 6; ++k) delta[k] = step[k] * scale[k];
-      plus7(x, delta, xc);
-      for (int k = 0; k < 7; ++k) s_x[k] = xc[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) delta[k] = step[k] * T.scale[k];
+      plus7(T.x, delta, T.xc);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) s_x[k] = T.xc[k];
       s_go = 1;
       return;
     }
   };
+  auto load_totals = [&]() {   // s_tot -> T.H (full symmetric), T.g
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int c = a; c < 6; ++c) { T.H[a][c] = s_tot[k]; T.H[c][a] = s_tot[k]; ++k; }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) T.g[a] = s_tot[21 + a];
+  };
 
   if (tid == 0) {
-    for (int k = 0; k < 7; ++k) x[k] = s_x[k];
-    for (int k = 0; k < 21; ++k) H[k] = s_tot[k];
-    for (int k = 0; k < 6; ++k) g[k] = s_tot[21 + k];
-    cost = s_tot[27];
-    summary->initial_cost = cost;
-    summary->n_edge = s_cnt[0]; summary->n_plane = s_cnt[1];
-    if (n_res == 0) {  // Ceres: nothing to optimise, parameters untouched
-      termination = 4; s_go = 0;
+    s_cnt[0] = (int)(s_tot[28] + 0.5); s_cnt[1] = (int)(s_tot[29] + 0.5);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) T.x[k] = s_x[k];
+    load_totals();
+    T.cost = s_tot[27];
+    T.radius = prm.initial_radius; T.decrease_factor = 2.0; T.mcc = 0; T.gmax = 0;
+    T.reuse_diag = 0; T.last_successful = 0; T.iteration = 0; T.num_invalid = 0; T.num_successful = 0; T.num_evals = 1;
+    T.termination = 0; T.trace_rows = 0;
+    if (writer) { summary->initial_cost = T.cost; summary->n_edge = s_cnt[0]; summary->n_plane = s_cnt[1]; }
+    if (s_cnt[0] + s_cnt[1] == 0) {  // Ceres: nothing to optimise, parameters untouched
+      T.termination = 4; s_go = 0;
     } else {
-      for (int j = 0; j < 6; ++j) scale[j] = 1.0 / (1.0 + sqrt(H[tri(j, j)]));
-      gmax = gradient_max(x, g);
-      x_norm = 0; for (int k = 0; k < 7; ++k) x_norm += x[k] * x[k]; x_norm = sqrt(x_norm);
-      trace(cost, 0, gmax, 0, 0, radius, 0, 0);
-      if (gmax <= prm.gradient_tolerance) { termination = 1; s_go = 0; }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) T.scale[j] = 1.0 / (1.0 + sqrt(T.H[j][j]));
+      T.gmax = gradient_max(T.x, T.g);
+      double xn = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) xn += T.x[k] * T.x[k];
+      T.x_norm = sqrt(xn);
+      trace(T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0);
+      if (T.gmax <= prm.gradient_tolerance) { T.termination = 1; s_go = 0; }
       else next_candidate();
     }
   }
   __syncthreads();
 
   while (s_go) {
-    evaluate();
+    evaluate(false);
     if (tid == 0) {
-      ++num_evals;
+      ++T.num_evals;
       const double cand_cost = s_tot[27];
       double sn = 0;
-      for (int k = 0; k < 7; ++k) sn += (x[k] - xc[k]) * (x[k] - xc[k]);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) sn += (T.x[k] - T.xc[k]) * (T.x[k] - T.xc[k]);
       sn = sqrt(sn);
-      const double cost_change = cost - cand_cost;
-      if (sn <= prm.parameter_tolerance * (x_norm + prm.parameter_tolerance)) {
-        trace(cost, 0, gmax, sn, 0, radius, 1, 0); termination = 2; s_go = 0;
-      } else if (fabs(cost_change) <= prm.function_tolerance * cost) {
-        trace(cost, cost_change, gmax, sn, 0, radius, 1, 0); termination = 3; s_go = 0;
+      const double cost_change = T.cost - cand_cost;
+      if (sn <= prm.parameter_tolerance * (T.x_norm + prm.parameter_tolerance)) {
+        trace(T.cost, 0, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 2; s_go = 0;
+      } else if (fabs(cost_change) <= prm.function_tolerance * T.cost) {
+        trace(T.cost, cost_change, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 3; s_go = 0;
       } else {
-        const double rho = cost_change / mcc;
+        const double rho = cost_change / T.mcc;
         if (rho > prm.min_relative_decrease) {
-          for (int k = 0; k < 7; ++k) x[k] = xc[k];
-          x_norm = 0; for (int k = 0; k < 7; ++k) x_norm += x[k] * x[k]; x_norm = sqrt(x_norm);
-          for (int k = 0; k < 21; ++k) H[k] = s_tot[k];
-          for (int k = 0; k < 6; ++k) g[k] = s_tot[21 + k];
-          cost = cand_cost;
-          gmax = gradient_max(x, g);
-          last_successful = true;
-          ++num_successful;
-          radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3.0));
-          radius = fmin(prm.max_radius, radius);
-          decrease_factor = 2.0;
-          reuse_diag = false;
-          trace(cost, cost_change, gmax, sn, rho, radius, 1, 1);
+          double xn = 0;
+#pragma unroll
+          for (int k = 0; k < 7; ++k) { T.x[k] = T.xc[k]; xn += T.xc[k] * T.xc[k]; }
+          T.x_norm = sqrt(xn);
+          load_totals();
+          T.cost = cand_cost;
+          T.gmax = gradient_max(T.x, T.g);
+          T.last_successful = 1;
+          ++T.num_successful;
+          const double tq = 2.0 * rho - 1.0;
+          T.radius = fmin(prm.max_radius, T.radius / fmax(1.0 / 3.0, 1.0 - tq * tq * tq));
+          T.decrease_factor = 2.0;
+          T.reuse_diag = 0;
+          trace(T.cost, cost_change, T.gmax, sn, rho, T.radius, 1, 1);
         } else {
-          radius = radius / decrease_factor;
-          decrease_factor *= 2.0;
-          reuse_diag = true;
-          trace(cost, cost_change, gmax, sn, rho, radius, 1, 0);
+          T.radius = T.radius / T.decrease_factor;
+          T.decrease_factor *= 2.0;
+          T.reuse_diag = 1;
+          trace(T.cost, cost_change, T.gmax, sn, rho, T.radius, 1, 0);
         }
         next_candidate();
       }
@@ -357,19 +435,20 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
     __syncthreads();
   }
 
-  if (tid == 0) {
-    for (int k = 0; k < 7; ++k) x7[k] = x[k];
-    summary->termination = termination;
-    summary->num_iterations = iteration;
-    summary->num_successful = num_successful;
-    summary->num_jac_evals = num_evals;
-    summary->final_cost = cost;
-    summary->trace_rows = trace_rows;
+  if (writer) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) x7[k] = T.x[k];
+    summary->termination = T.termination;
+    summary->num_iterations = T.iteration;
+    summary->num_successful = T.num_successful;
+    summary->num_jac_evals = T.num_evals;
+    summary->final_cost = T.cost;
+    summary->trace_rows = T.trace_rows;
     if (integrate && world7) {
       // laserOdometry.cpp:504-505  t_w += q_w * t_last_curr ; q_w = q_w * q_last_curr
       const V3 u{world7[0], world7[1], world7[2]};
       const double w = world7[3];
-      const V3 v{x[4], x[5], x[6]};
+      const V3 v{T.x[4], T.x[5], T.x[6]};
       V3 uv = crossd(u, v);
       uv.x += uv.x; uv.y += uv.y; uv.z += uv.z;
       const V3 c2 = crossd(u, uv);
@@ -377,13 +456,14 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
       world7[5] += v.y + w * uv.y + c2.y;
       world7[6] += v.z + w * uv.z + c2.z;
       const double ax = world7[0], ay = world7[1], az = world7[2], aw = world7[3];
-      const double bx = x[0], by = x[1], bz = x[2], bw = x[3];
+      const double bx = T.x[0], by = T.x[1], bz = T.x[2], bw = T.x[3];
       world7[3] = aw * bw - ax * bx - ay * by - az * bz;
       world7[0] = aw * bx + ax * bw + ay * bz - az * by;
       world7[1] = aw * by + ay * bw + az * bx - ax * bz;
       world7[2] = aw * bz + az * bw + ax * by - ay * bx;
     }
   }
+  cluster.sync();  // no CTA may exit while another can still read its shared memory
 }
 
 }  // namespace aloam

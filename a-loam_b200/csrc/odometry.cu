@@ -1,16 +1,20 @@
 // Scan-to-scan correspondence search on the GPU -- replaces laserOdometry.cpp:111-129 (TransformToStart),
 // :299-483 (the two association loops) and :567-568 (the kd-tree builds).
 //
-// Index (k_tile_bounds): the "last" clouds are ring-major and, inside a ring, azimuth ordered, so 32 consecutive
-// points are spatially compact.  One AABB per 32-point tile + the ring offset table is the whole index; it costs
-// one pass over the cloud instead of two O(M log M) kd-tree builds per frame.
-// Search (k_odom_assoc): ONE WARP PER QUERY.  Lanes test 32 tile boxes at a time against the current best
-// (exact lower bound: same float expression, monotone rounding => no slack needed), surviving tiles are read
-// with one coalesced 512-byte float4 load per tile, candidates are reduced with warp REDUX arg-min.
-// The result is the exact nearest neighbour under the (distance, index) order, i.e. what FLANN returns up to
-// exact-distance ties.  The ring-window scans of :312-361 / :402-455 reuse the same routine on the index
-// ranges the ring offset table gives, with the reference's visiting order as tie-break
-// (forward ascending first, then backward descending, strict '<').
+// Index = a dense (azimuth bucket x ring) table per "last" cloud instead of a kd-tree (k_rab_* kernels): a counting
+//   sort of the cloud into ALOAM_NB x 64 cells, bucket-major, so that "all rings of an azimuth bucket" and "rings
+//   rc-2..rc+2 of an azimuth bucket" are both contiguous slices of one float4 array (x, y, z, ring<<24 | index).
+//   The order of points inside a cell depends on atomic timing, but every search below compares candidates on
+//   (distance, original index / visiting rank), so results are a pure function of the input.
+// Search = ONE WARP PER QUERY, exact.  The clouds live in the sensor frame of the last scan, so a point whose
+//   azimuth differs from the query's by at least a has distance >= rho_q * sin(a) from it.  The warp streams the
+//   query's own bucket, then buckets +-1, +-2, ... with coalesced float4 loads (4 in flight per lane) and REDUX
+//   arg-min; after +-k buckets a best distance below rho_q*sin(k*w) is final.  The sweep stops at the latest when
+//   that bound exceeds the reference's own threshold (DISTANCE_SQ_THRESHOLD = 25 m^2), beyond which the reference
+//   discards the match anyway, or when the whole circle has been read.
+// The 2nd / 3rd correspondence points of :312-361 / :402-455 use the same sweep restricted to the ring slice
+// rc-2..rc+2, with candidates ranked by the reference's visiting order (forward ascending first, then backward
+// descending, strict '<'), so ties resolve exactly as the sequential loops do.
 #include <climits>
 #include <cfloat>
 #include "common.cuh"
@@ -18,6 +22,8 @@
 
 namespace aloam {
 
+// validates that a cloud handed in through the C ABI is in ascending ring order (the reference's windowed scans
+// :312-361 assume it) and that every int(intensity) is a legal ring
 __global__ void k_ring_offsets(const Pt4* __restrict__ pts, int n, int* __restrict__ ring_start, int* __restrict__ err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -34,86 +40,108 @@ __global__ void k_ring_offsets(const Pt4* __restrict__ pts, int n, int* __restri
     for (int k = r + 1; k <= 64; ++k) ring_start[k] = n;
 }
 
-__global__ void __launch_bounds__(256) k_tile_bounds(const Pt4* __restrict__ pts, const int* __restrict__ n_ptr,
-                                                     float* __restrict__ tile_lo, float* __restrict__ tile_hi) {
-  const int n = *n_ptr;
-  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int i = t * ALOAM_TILE + lane;
-  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  if (i < n) {
-    Pt4 p = pts[i];
-    lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z;
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
-      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
-    }
-  if (lane == 0) {  // tiles past the end of the cloud get an empty box (never selected)
-    reinterpret_cast<float4*>(tile_lo)[t] = make_float4(lo[0], lo[1], lo[2], 0.f);
-    reinterpret_cast<float4*>(tile_hi)[t] = make_float4(hi[0], hi[1], hi[2], 0.f);
-  }
+// ---------------------------------------------------------------------------------------------------------------
+// index build: counting sort of the cloud into (azimuth bucket, ring) cells, bucket-major
+namespace {
+constexpr float kPiF = 3.14159265358979f;
+constexpr float kBucketW = 2.0f * kPiF / (float)ALOAM_NB;   // bucket width [rad]
+
+__device__ __forceinline__ int bucket_of(float x, float y) {
+  int b = (int)((atan2f(y, x) + kPiF) * ((float)ALOAM_NB / (2.0f * kPiF)));
+  return min(max(b, 0), ALOAM_NB - 1);
+}
+}  // namespace
+
+// blockIdx.y selects the cloud (0 = a, 1 = b)
+__global__ void k_rab_count(RabIndex a, const Pt4* __restrict__ pa, const int* __restrict__ na, RabIndex b,
+                            const Pt4* __restrict__ pb, const int* __restrict__ nb) {
+  const RabIndex& g = blockIdx.y == 0 ? a : b;
+  const Pt4* __restrict__ pts = blockIdx.y == 0 ? pa : pb;
+  const int n = blockIdx.y == 0 ? *na : *nb;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Pt4 p = pts[i];
+  const int ring = min(max((int)p.i, 0), 63);
+  const int cell = bucket_of(p.x, p.y) * 64 + ring;
+  g.cell_of[i] = cell;
+  g.rank_of[i] = atomicAdd(&g.cnt[cell], 1);
 }
 
+// one CTA per cloud: exclusive scan of the ALOAM_NB*64 cell counts -> start[], and reset the counts for the next build
+__global__ void __launch_bounds__(1024) k_rab_scan(RabIndex a, RabIndex b) {
+  const RabIndex& g = blockIdx.x == 0 ? a : b;
+  constexpr int NC = ALOAM_NB * 64, PER = NC / 1024;
+  __shared__ int s_w[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  int v[PER], sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { v[k] = g.cnt[t * PER + k]; g.cnt[t * PER + k] = 0; sum += v[k]; }
+  int incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int x = s_w[lane], inc = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+    s_w[lane] = inc - x;
+  }
+  __syncthreads();
+  int run = s_w[w] + incl - sum;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { g.start[t * PER + k] = run; run += v[k]; }
+  if (t == 1023) g.start[NC] = run;
+}
+
+__global__ void k_rab_fill(RabIndex a, const Pt4* __restrict__ pa, const int* __restrict__ na, RabIndex b,
+                           const Pt4* __restrict__ pb, const int* __restrict__ nb) {
+  const RabIndex& g = blockIdx.y == 0 ? a : b;
+  const Pt4* __restrict__ pts = blockIdx.y == 0 ? pa : pb;
+  const int n = blockIdx.y == 0 ? *na : *nb;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Pt4 p = pts[i];
+  const int cell = g.cell_of[i];
+  g.gpts[g.start[cell] + g.rank_of[i]] = make_float4(p.x, p.y, p.z, __int_as_float(((cell & 63) << 24) | i));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// search
 namespace {
 
-// lower bound of the float squared distance from q to any point inside the box (same expression shape as sqdist3)
-__device__ __forceinline__ float box_bound(float4 lo, float4 hi, float qx, float qy, float qz) {
-  float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.f);
-  float dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.f);
-  float dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.f);
-  return dx * dx + dy * dy + dz * dz;
+// f(x, y, z, packed) for every point of cells [cell_lo, cell_hi] (a contiguous slice of gpts); coalesced, 4 loads in flight
+template <typename F>
+__device__ __forceinline__ void visit_cells(const RabIndex& g, int cell_lo, int cell_hi, F&& f) {
+  const int lane = (int)lane_id();
+  const int e0 = g.start[cell_lo], e1 = g.start[cell_hi + 1];
+  int e = e0 + lane;
+  for (; e + 96 < e1; e += 128) {
+    const float4 p0 = __ldg(g.gpts + e), p1 = __ldg(g.gpts + e + 32), p2 = __ldg(g.gpts + e + 64), p3 = __ldg(g.gpts + e + 96);
+    f(p0.x, p0.y, p0.z, __float_as_int(p0.w)); f(p1.x, p1.y, p1.z, __float_as_int(p1.w));
+    f(p2.x, p2.y, p2.z, __float_as_int(p2.w)); f(p3.x, p3.y, p3.z, __float_as_int(p3.w));
+  }
+  for (; e < e1; e += 32) {
+    const float4 p = __ldg(g.gpts + e);
+    f(p.x, p.y, p.z, __float_as_int(p.w));
+  }
 }
 
-// Exact arg-min of the float squared distance over indices [j0, j1) of `c`, restricted to d2 <= limit on entry.
-// descending = false : ties -> smallest index ; true : ties -> largest index (reference visiting order).
-// Returns the warp-uniform (d2, j) ; j = -1 when nothing is at distance <= limit.
-__device__ __forceinline__ void range_argmin(const LastCloud& c, float qx, float qy, float qz, int j0, int j1,
-                                             bool descending, float limit, float& out_d, int& out_j) {
-  const unsigned lane = lane_id();
-  float best_d = limit;  // per lane
-  int best_j = -1;
-  float wbest = limit;   // warp-uniform pruning bound
-  if (j1 > j0) {
-    const int t_first = j0 / ALOAM_TILE, t_last = (j1 - 1) / ALOAM_TILE;
-    const float4* tlo = reinterpret_cast<const float4*>(c.tile_lo);
-    const float4* thi = reinterpret_cast<const float4*>(c.tile_hi);
-    const int ntl = t_last - t_first + 1;
-    for (int g = 0; g < ntl; g += 32) {
-      // lane k looks at the k-th tile of this group in visiting order
-      int k = g + (int)lane;
-      int t = descending ? (t_last - k) : (t_first + k);
-      float bound = FLT_MAX;
-      if (k < ntl) bound = box_bound(__ldg(tlo + t), __ldg(thi + t), qx, qy, qz);
-      unsigned m = __ballot_sync(0xffffffffu, bound <= wbest);
-      while (m) {
-        int src = __ffs(m) - 1;
-        m &= m - 1;
-        float b = __shfl_sync(0xffffffffu, bound, src);
-        if (b > wbest) continue;
-        int tt = descending ? (t_last - (g + src)) : (t_first + g + src);
-        int j = tt * ALOAM_TILE + (int)lane;
-        float d2 = FLT_MAX;
-        if (j >= j0 && j < j1) {
-          Pt4 p = c.pts[j];
-          d2 = sqdist3(p.x, p.y, p.z, qx, qy, qz);
-          // a lane sees its indices in visiting order, so strict '<' keeps the first visited among equals;
-          // d2 == limit on first hit is allowed in (callers re-check the strict threshold)
-          if (d2 < best_d || (best_j < 0 && d2 == best_d)) { best_d = d2; best_j = j; }
-        }
-        unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(d2));
-        wbest = fminf(wbest, __uint_as_float(mb));
-      }
-    }
-  }
-  // combine lanes: (d2, visiting rank)
-  int rank = best_j < 0 ? INT_MAX : (descending ? (j1 - 1 - best_j) : (best_j - j0));
-  float d = best_j < 0 ? FLT_MAX : best_d;
-  warp_argmin(d, rank);
-  out_d = d;
-  out_j = (rank == INT_MAX || d == FLT_MAX) ? -1 : (descending ? (j1 - 1 - rank) : (j0 + rank));
+// Visit ring slice [r_lo, r_hi] of azimuth buckets bq-k and bq+k (k == 0: bucket bq only; the two coincide when 2k == NB)
+template <typename F>
+__device__ __forceinline__ void visit_ring_step(const RabIndex& g, int bq, int k, int r_lo, int r_hi, F&& f) {
+  const int b0 = (bq - k + ALOAM_NB) % ALOAM_NB, b1 = (bq + k) % ALOAM_NB;
+  visit_cells(g, b0 * 64 + r_lo, b0 * 64 + r_hi, f);
+  if (b1 != b0) visit_cells(g, b1 * 64 + r_lo, b1 * 64 + r_hi, f);
+}
+
+// After buckets bq-k .. bq+k have been seen, every unseen point is at azimuth distance >= k*w from q, hence at
+// distance >= rho_q * sin(k*w) (k*w < pi/2).  1e-4 rad absorbs atan2f / bucket rounding.  Returns the squared safe radius.
+__device__ __forceinline__ float safe_radius_sq(float rho_q, int k) {
+  const float ang = (float)k * kBucketW - 1e-4f;
+  const float s = ang >= 0.5f * kPiF ? 1.0f : sinf(fmaxf(ang, 0.f));
+  const float r = rho_q * s;
+  return r * r * 0.9999f;
 }
 
 struct D3 { double x, y, z; };
@@ -137,6 +165,32 @@ __device__ __forceinline__ void store_none(BlockRec* b, int* corr) {
   if (corr) { corr[0] = -1; corr[1] = -1; corr[2] = -1; corr[3] = 0; }
 }
 
+constexpr int kBig = 1 << 25;       // separates forward ranks [0, 2^24) from backward ranks
+
+// exact nearest neighbour of q with d2 < limit (strict); returns index or -1, d2 in out_d.  Ties -> smaller index.
+__device__ __forceinline__ int rab_nearest(const RabIndex& g, float qx, float qy, float qz, float limit, float& out_d) {
+  const int bq = bucket_of(qx, qy);
+  const float rho = sqrtf(qx * qx + qy * qy);
+  float best_d = limit; int best_i = INT_MAX;
+  float wd = FLT_MAX; int wi = INT_MAX;
+  auto f = [&](float x, float y, float z, int packed) {
+    const float d2 = sqdist3(x, y, z, qx, qy, qz);
+    const int idx = packed & 0xffffff;
+    if (d2 < best_d || (d2 == best_d && best_i != INT_MAX && idx < best_i)) { best_d = d2; best_i = idx; }
+  };
+  visit_ring_step(g, bq, 0, 0, 63, f);
+  for (int k = 1; 2 * k <= ALOAM_NB; ++k) {
+    visit_ring_step(g, bq, k, 0, 63, f);
+    wd = best_i == INT_MAX ? FLT_MAX : best_d; wi = best_i;
+    warp_argmin(wd, wi);
+    const float safe2 = safe_radius_sq(rho, k);
+    if ((wi != INT_MAX && wd < safe2) || safe2 >= limit) break;
+  }
+  if (wi == INT_MAX) { wd = best_i == INT_MAX ? FLT_MAX : best_d; wi = best_i; warp_argmin(wd, wi); }
+  out_d = wd;
+  return (wi == INT_MAX || wd == FLT_MAX) ? -1 : wi;
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ sharp, const Pt4* __restrict__ flat,
@@ -152,7 +206,7 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
   int* co = corr ? corr + 4 * wid : nullptr;
   if (qi >= nq) { if (lane == 0) store_none(out, co); return; }
   const LastCloud& L = is_corner ? corner : surf;
-  const int n_last = *L.n;
+  const RabIndex& g = L.index;
   const Pt4 cur = is_corner ? sharp[qi] : flat[qi];
   double pose[7];
 #pragma unroll
@@ -162,52 +216,76 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
   const float thr = (float)prm.dist_sq_thresh;
 
   // nearest neighbour (kdtree*Last->nearestKSearch(pointSel, 1, ...), :302,390) then `< DISTANCE_SQ_THRESHOLD`
-  float d1; int closest;
-  range_argmin(L, qx, qy, qz, 0, n_last, false, thr, d1, closest);
+  float d1;
+  const int closest = rab_nearest(g, qx, qy, qz, thr, d1);
   if (closest < 0 || !((double)d1 < prm.dist_sq_thresh)) { if (lane == 0) store_none(out, co); return; }
-  const int rc = (int)L.pts[closest].i;                       // closestPointScanID
-  // rings rc-2 .. rc+2 survive the `> rc + NEARBY_SCAN` / `< rc - NEARBY_SCAN` break tests (:319,345,405,433)
+  const int rc = (int)L.pts[closest].i;  // closestPointScanID
+  // rings rc-up .. rc+up survive the `> rc + NEARBY_SCAN` / `< rc - NEARBY_SCAN` break tests (:319,345,405,433)
   int up = 0; while ((double)(rc + up + 1) <= (double)rc + prm.nearby_scan) ++up;
-  const int r_lo = max(rc - up, 0), r_hi = min(rc + up + 1, 64);
-  const int* rs = L.ring_start;
-  const int fwd_other0 = rs[min(rc + 1, 64)], fwd_other1 = rs[r_hi];
-  const int bwd_other0 = rs[r_lo], bwd_other1 = rs[rc];
+
+  // second search: class 2 / class 3 minima in the reference's visiting order.
+  //   corner: class 2 = other rings within +-up (forward = higher rings first, :312-361)
+  //   surf  : class 2 = same ring (forward = indices after `closest`, :416-420,444-448),
+  //           class 3 = other rings within +-up (:422-426,449-454)
+  float b2 = thr, b3 = thr; int r2 = INT_MAX, r3 = INT_MAX;
+  float w2 = FLT_MAX, w3 = FLT_MAX; int k2 = INT_MAX, k3 = INT_MAX;
+  {
+    const int bq = bucket_of(qx, qy);
+    const float rho = sqrtf(qx * qx + qy * qy);
+    const int r_lo = max(rc - up, 0), r_hi = min(rc + up, 63);
+    auto f = [&](float x, float y, float z, int packed) {
+      const int idx = packed & 0xffffff, ring = packed >> 24;
+      const int dr = ring - rc;
+      const float d2 = sqdist3(x, y, z, qx, qy, qz);
+      if (dr == 0) {
+        if (is_corner || idx == closest) return;
+        const int rank = idx > closest ? (idx - closest) : (kBig + (closest - idx));
+        if (d2 < b2 || (d2 == b2 && r2 != INT_MAX && rank < r2)) { b2 = d2; r2 = rank; }
+      } else {
+        const int rank = dr > 0 ? idx : (kBig + (kBig - idx));
+        if (is_corner) { if (d2 < b2 || (d2 == b2 && r2 != INT_MAX && rank < r2)) { b2 = d2; r2 = rank; } }
+        else { if (d2 < b3 || (d2 == b3 && r3 != INT_MAX && rank < r3)) { b3 = d2; r3 = rank; } }
+      }
+    };
+    visit_ring_step(g, bq, 0, r_lo, r_hi, f);
+    for (int k = 1; 2 * k <= ALOAM_NB; ++k) {
+      visit_ring_step(g, bq, k, r_lo, r_hi, f);
+      w2 = r2 == INT_MAX ? FLT_MAX : b2; k2 = r2; warp_argmin(w2, k2);
+      const float safe2 = safe_radius_sq(rho, k);
+      bool done = k2 != INT_MAX && w2 < safe2;
+      if (!is_corner) {
+        w3 = r3 == INT_MAX ? FLT_MAX : b3; k3 = r3; warp_argmin(w3, k3);
+        done = done && k3 != INT_MAX && w3 < safe2;
+      }
+      if (done || safe2 >= thr) break;
+    }
+    if (k2 == INT_MAX) { w2 = r2 == INT_MAX ? FLT_MAX : b2; k2 = r2; warp_argmin(w2, k2); }
+    if (!is_corner && k3 == INT_MAX) { w3 = r3 == INT_MAX ? FLT_MAX : b3; k3 = r3; warp_argmin(w3, k3); }
+  }
+  // rank -> index
+  int j2 = -1, j3 = -1;
+  if (k2 != INT_MAX && w2 != FLT_MAX) {
+    if (is_corner) j2 = k2 < kBig ? k2 : (kBig - (k2 - kBig));
+    else j2 = k2 < kBig ? (closest + k2) : (closest - (k2 - kBig));
+  }
+  if (!is_corner && k3 != INT_MAX && w3 != FLT_MAX) j3 = k3 < kBig ? k3 : (kBig - (k3 - kBig));
 
   if (is_corner) {
-    // minPointInd2: forward over higher rings (:312-335), then backward over lower rings (:338-361)
-    float df, db; int jf, jb;
-    range_argmin(L, qx, qy, qz, fwd_other0, fwd_other1, false, thr, df, jf);
-    if (jf >= 0 && !(df < thr)) jf = -1;
-    range_argmin(L, qx, qy, qz, bwd_other0, bwd_other1, true, jf >= 0 ? df : thr, db, jb);
-    int second = jf;
-    if (jb >= 0 && db < (jf >= 0 ? df : thr)) second = jb;
-    if (second < 0) { if (lane == 0) store_none(out, co); return; }
+    if (j2 < 0) { if (lane == 0) store_none(out, co); return; }
     if (lane == 0) {
-      const Pt4 a = L.pts[closest], b = L.pts[second];
+      const Pt4 a = L.pts[closest], b = L.pts[j2];
       out->cp[0] = cur.x; out->cp[1] = cur.y; out->cp[2] = cur.z;
       out->a[0] = a.x; out->a[1] = a.y; out->a[2] = a.z;
       out->b[0] = b.x; out->b[1] = b.y; out->b[2] = b.z;
       const double ex = (double)a.x - (double)b.x, ey = (double)a.y - (double)b.y, ez = (double)a.z - (double)b.z;
       out->s = sqrt(ex * ex + ey * ey + ez * ez);  // de.norm(), lidarFactor.hpp:36-40
       out->type = 0;
-      if (co) { co[0] = closest; co[1] = second; co[2] = -1; co[3] = 1; }
+      if (co) { co[0] = closest; co[1] = j2; co[2] = -1; co[3] = 1; }
     }
   } else {
-    // minPointInd2: same ring, forward part then backward part ; minPointInd3: other rings (:402-455)
-    float df, db; int jf, jb;
-    range_argmin(L, qx, qy, qz, closest + 1, rs[min(rc + 1, 64)], false, thr, df, jf);
-    if (jf >= 0 && !(df < thr)) jf = -1;
-    range_argmin(L, qx, qy, qz, rs[rc], closest, true, jf >= 0 ? df : thr, db, jb);
-    int m2 = jf;
-    if (jb >= 0 && db < (jf >= 0 ? df : thr)) m2 = jb;
-    range_argmin(L, qx, qy, qz, fwd_other0, fwd_other1, false, thr, df, jf);
-    if (jf >= 0 && !(df < thr)) jf = -1;
-    range_argmin(L, qx, qy, qz, bwd_other0, bwd_other1, true, jf >= 0 ? df : thr, db, jb);
-    int m3 = jf;
-    if (jb >= 0 && db < (jf >= 0 ? df : thr)) m3 = jb;
-    if (m2 < 0 || m3 < 0) { if (lane == 0) store_none(out, co); return; }
+    if (j2 < 0 || j3 < 0) { if (lane == 0) store_none(out, co); return; }
     if (lane == 0) {
-      const Pt4 pj = L.pts[closest], pl = L.pts[m2], pm = L.pts[m3];
+      const Pt4 pj = L.pts[closest], pl = L.pts[j2], pm = L.pts[j3];
       out->cp[0] = cur.x; out->cp[1] = cur.y; out->cp[2] = cur.z;
       out->a[0] = pj.x; out->a[1] = pj.y; out->a[2] = pj.z;
       // ljm_norm = (j - l) x (j - m), normalised (lidarFactor.hpp:64-65)
@@ -219,19 +297,19 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
       out->b[0] = nrm.x; out->b[1] = nrm.y; out->b[2] = nrm.z;
       out->s = 1.0;
       out->type = 1;
-      if (co) { co[0] = closest; co[1] = m2; co[2] = m3; co[3] = 1; }
+      if (co) { co[0] = closest; co[1] = j2; co[2] = j3; co[3] = 1; }
     }
   }
 }
 
-// exact 1-NN of arbitrary queries against a "last" cloud (aloam_knn, which = 0/1)
+// exact 1-NN of arbitrary queries against a "last" cloud (aloam_knn, which = 0/1): no distance limit
 __global__ void __launch_bounds__(256) k_knn_last(LastCloud cloud, const Pt4* __restrict__ queries, int nq,
                                                   int* __restrict__ idx, float* __restrict__ sqd) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wid >= nq) return;
   const Pt4 q = queries[wid];
-  float d; int j;
-  range_argmin(cloud, q.x, q.y, q.z, 0, *cloud.n, false, FLT_MAX, d, j);
+  float d;
+  const int j = rab_nearest(cloud.index, q.x, q.y, q.z, FLT_MAX, d);
   if (lane_id() == 0) { idx[wid] = j; sqd[wid] = j < 0 ? __int_as_float(0x7f800000) : d; }
 }
 
