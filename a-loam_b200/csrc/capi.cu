@@ -626,6 +626,18 @@ int aloam_profile_read(aloam_ctx* c, double* ms_sum, long long* count, const cha
   return n;
 }
 long long aloam_launch_count(aloam_ctx* c) { return c ? c->launches : 0; }
+// SM-clock cycle counts of the LM solves of the last register / scan_to_pose call: out[2*it] = whole solve, out[2*it+1] = evaluation passes
+int aloam_debug_lm_cycles(aloam_ctx* c, long long* out, int outer) {
+  if (!c || !out) return ALOAM_ERR_INVALID_ARG;
+  for (int it = 0; it < outer && it < 4; ++it) { const LmSummary& s = c->h_summary[it]; out[5 * it] = s.cyc_total; out[5 * it + 1] = s.cyc_eval; out[5 * it + 2] = s.cyc_chol; out[5 * it + 3] = s.cyc_plus; out[5 * it + 4] = s.cyc_grad; }
+  return ALOAM_OK;
+}
+int aloam_debug_feature_cycles(aloam_ctx* c, long long* out64x8) {
+  if (!c || !out64x8) return ALOAM_ERR_INVALID_ARG;
+  cudaSetDevice(c->cfg.device);
+  features_debug_cycles(out64x8);
+  return ALOAM_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ mapping (mapping.cu)
 int aloam_map_upload_impl(aloam_ctx* c, aloam_cloud_view corner_map, aloam_cloud_view surf_map);

@@ -242,19 +242,87 @@ __global__ void __launch_bounds__(CT) k_scatter(const float* __restrict__ raw, i
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
-__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* a, int P) {
+// Bitonic sort of NT*E 64-bit keys held E per thread (element index i = t*E + s).  Compare-exchange partners at
+// distance j live in the same thread (j < E: registers), in another lane of the warp (E <= j < 32E: shuffles) or in
+// another warp (j >= 32E: one shared-memory exchange, conflict-free [slot][thread] layout).  For 2048 keys on 256
+// threads that is 30 register + 30 shuffle + 6 shared-memory passes instead of 66 shared-memory passes.
+template <int E, int NT>
+__device__ __forceinline__ void hybrid_bitonic(unsigned long long (&v)[E], unsigned long long* buf) {
+  const int t = (NT == 32) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  constexpr int P = E * NT;
+#pragma unroll 1
   for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-        int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        int hi = lo + j;
-        unsigned long long x = a[lo], y = a[hi];
-        bool asc = (lo & k) == 0;
-        if ((x > y) == asc) { a[lo] = y; a[hi] = x; }
+#pragma unroll 1
+    for (int j = k >> 1; j >= E; j >>= 1) {
+      const int tx = j / E;  // partner thread = t ^ tx, same slot
+      if (NT > 32 && tx >= 32) {
+#pragma unroll
+        for (int s2 = 0; s2 < E; ++s2) buf[s2 * NT + t] = v[s2];
+        __syncthreads();
+#pragma unroll
+        for (int s2 = 0; s2 < E; ++s2) {
+          const unsigned long long o = buf[s2 * NT + (t ^ tx)];
+          const int i = t * E + s2;
+          const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+          v[s2] = keep_min ? (v[s2] < o ? v[s2] : o) : (v[s2] > o ? v[s2] : o);
+        }
+        __syncthreads();
+      } else {
+#pragma unroll
+        for (int s2 = 0; s2 < E; ++s2) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[s2], tx);
+          const int i = t * E + s2;
+          const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+          v[s2] = keep_min ? (v[s2] < o ? v[s2] : o) : (v[s2] > o ? v[s2] : o);
+        }
       }
-      __syncthreads();
+    }
+#pragma unroll
+    for (int jj = E / 2; jj >= 1; jj >>= 1) {
+      if (jj < k) {
+#pragma unroll
+        for (int s2 = 0; s2 < E; ++s2) {
+          if ((s2 & jj) == 0) {
+            const int i = t * E + s2;
+            const bool up = (i & k) == 0;
+            const unsigned long long x = v[s2], y = v[s2 | jj];
+            if ((x > y) == up) { v[s2] = y; v[s2 | jj] = x; }
+          }
+        }
+      }
     }
   }
+}
+
+// one warp sorts the curvature keys of one sixth of a ring (scanRegistration.cpp:288) and leaves them in out[0..len)
+template <int E>
+__device__ __forceinline__ void warp_sort_segment(const float* curv, int sp, int len, unsigned long long* out) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long v[E];
+#pragma unroll
+  for (int s2 = 0; s2 < E; ++s2) {
+    const int m = lane * E + s2;
+    v[s2] = m < len ? (((unsigned long long)__float_as_uint(curv[sp + m]) << 12) | (unsigned)(sp + m)) : ~0ull;
+  }
+  hybrid_bitonic<E, 32>(v, nullptr);
+#pragma unroll
+  for (int s2 = 0; s2 < E; ++s2) {
+    const int m = lane * E + s2;
+    if (m < len) out[m] = v[s2];
+  }
+}
+
+// the whole CTA (256 threads) sorts P = 256*E voxel keys ; key_of(i) supplies the key of slot i ; result in keys[0..P)
+template <int E, typename KeyOf>
+__device__ __forceinline__ void cta_sort_keys(unsigned long long* keys, KeyOf&& key_of) {
+  const int t = threadIdx.x;
+  unsigned long long v[E];
+#pragma unroll
+  for (int s2 = 0; s2 < E; ++s2) v[s2] = key_of(t * E + s2);
+  hybrid_bitonic<E, 256>(v, keys);
+#pragma unroll
+  for (int s2 = 0; s2 < E; ++s2) keys[t * E + s2] = v[s2];
+  __syncthreads();
 }
 
 // gap bit i = |p[i+1]-p[i]|^2 > 0.05 (float expression compared with the double literal, :324)
@@ -279,9 +347,87 @@ __device__ __forceinline__ void set_bits(unsigned* m, int lo, int hi) {  // sing
 
 }  // namespace
 
+// One sixth of a ring (:282-398 minus the sort): positions [sp, ep], lane owns positions sp + 32 s + lane.
+// spill_in : bit k set = position sp + k was marked in cloudNeighborPicked by the previous segment's picks (k < 5).
+// Results (warp-uniform): `less` = positions picked in the sharp walk in pick order (the first two are the sharp
+// points), `flat` = positions of the flat walk, spill_out = marks this segment leaves on positions ep+1 .. ep+5.
+template <int NS>
+__device__ __forceinline__ void pick_segment(const float* curv, const unsigned char* fb, int sp, int ep, unsigned spill_in,
+                                             unsigned short* less, int& n_less, unsigned short* flat, int& n_flat,
+                                             unsigned& spill_out) {
+  const int lane = threadIdx.x & 31;
+  float c[NS];
+  unsigned valid = 0, pk = 0;   // bit s: slot s is inside the segment / is marked in cloudNeighborPicked
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) {
+    const int p = sp + s2 * 32 + lane;
+    c[s2] = 0.f;
+    if (p <= ep) { c[s2] = curv[p]; valid |= 1u << s2; }
+  }
+  if (lane < 5 && sp + lane <= ep) pk |= (spill_in >> lane) & 1u;   // slot 0 of lanes 0..4
+  spill_out = 0;
+  // marks the slot of this lane that falls inside [lo, hi] (at most one: the range is <= 11 long) ; records the spill
+  auto mark = [&](int lo, int hi) {
+    const int t = (lane - (lo - sp)) & 31;
+    const int p = lo + t;
+    if (p <= hi && p >= sp && p <= ep) pk |= 1u << ((p - sp) >> 5);
+    if (hi > ep) spill_out |= ((1u << (hi - ep)) - 1u) & ~((lo > ep + 1) ? ((1u << (lo - ep - 1)) - 1u) : 0u);
+  };
+  n_less = 0; n_flat = 0;
+  // ---- largest curvature first (:291-344): eligible = !picked && c > 0.1 ; ties -> larger index (top of the sorted run)
+  unsigned el = 0;
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) if ((double)c[s2] > 0.1) el |= 1u << s2;
+  el &= valid;
+  for (;;) {
+    const unsigned e = el & ~pk;
+    unsigned bb = 0; int bs = -1;
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) {
+      const unsigned cb = __float_as_uint(c[s2]);
+      if (((e >> s2) & 1u) && cb >= bb) { bb = cb; bs = s2; }   // later slot = larger position wins a tie inside a lane
+    }
+    if (!__any_sync(0xffffffffu, bs >= 0)) break;
+    const unsigned mx = __reduce_max_sync(0xffffffffu, bs >= 0 ? bb : 0u);
+    const int cand = (bs >= 0 && bb == mx) ? (sp + bs * 32 + lane) : -1;
+    const int win = __reduce_max_sync(0xffffffffu, cand);
+    if (n_less >= 20) break;          // the 21st eligible point ends the walk unpicked (:312-315)
+    const unsigned char r = fb[win];
+    if (lane == 0) less[n_less] = (unsigned short)win;
+    ++n_less;
+    mark(win - (r >> 4), win + (r & 15));
+  }
+  // ---- smallest curvature first (:346-390): eligible = !picked && c < 0.1 ; ties -> smaller index ; 4th pick not marked
+  el = 0;
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) if ((double)c[s2] < 0.1) el |= 1u << s2;
+  el &= valid;
+  for (;;) {
+    const unsigned e = el & ~pk;
+    unsigned bb = 0xffffffffu; int bs = -1;
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) {
+      const unsigned cb = __float_as_uint(c[s2]);
+      if (((e >> s2) & 1u) && cb < bb) { bb = cb; bs = s2; }    // earlier slot = smaller position wins a tie inside a lane
+    }
+    if (!__any_sync(0xffffffffu, bs >= 0)) break;
+    const unsigned mn = __reduce_min_sync(0xffffffffu, bs >= 0 ? bb : 0xffffffffu);
+    const int cand = (bs >= 0 && bb == mn) ? (sp + bs * 32 + lane) : 0x7fffffff;
+    const int win = __reduce_min_sync(0xffffffffu, cand);
+    if (lane == 0) flat[n_flat] = (unsigned short)win;
+    ++n_flat;
+    if (n_flat >= 4) break;
+    const unsigned char r = fb[win];
+    mark(win - (r >> 4), win + (r & 15));
+  }
+  __syncwarp();
+}
+
+__device__ long long g_dbg_cycles[64 * 8];   // per-ring phase time stamps (clock64) of the last k_ring_features launch
+
 // dynamic shared memory layout (bytes): pts 16*MAXR | keys 8*MAXR | curv 4*MAXR | label MAXR | gap 4*(MAXR/32+2) | picked same
 constexpr int MAXR = ALOAM_MAX_RING;
-size_t ring_features_smem_bytes() { return (size_t)MAXR * (16 + 8 + 4 + 1) + 2 * 4 * (MAXR / 32 + 2) + 64; }
+size_t ring_features_smem_bytes() { return (size_t)MAXR * (16 + 8 + 4 + 1 + 1) + 2 * 4 * (MAXR / 32 + 2) + 64; }
 
 __global__ void __launch_bounds__(256) k_ring_features(const Pt4* __restrict__ full, const int* __restrict__ ring_start,
                                                        int n_scans, float leaf, Pt4* __restrict__ st_sharp,
@@ -296,6 +442,10 @@ __global__ void __launch_bounds__(256) k_ring_features(const Pt4* __restrict__ f
   signed char* label = reinterpret_cast<signed char*>(smem + (size_t)MAXR * 28);
   unsigned* gap = reinterpret_cast<unsigned*>(smem + (size_t)MAXR * 29);
   unsigned* picked = gap + (MAXR / 32 + 2);
+  unsigned char* fb = reinterpret_cast<unsigned char*>(picked + (MAXR / 32 + 2));   // [MAXR]
+  __shared__ unsigned short s_less[6][20], s_flat[6][4];
+  __shared__ int s_nl[6], s_nf[6];
+  __shared__ unsigned s_spill[6];
   __shared__ int s_i[16];
   __shared__ float s_red[6][8];
 
@@ -316,6 +466,8 @@ __global__ void __launch_bounds__(256) k_ring_features(const Pt4* __restrict__ f
   int P = 32;
   while (P < nr) P <<= 1;
 
+  long long* dbg = g_dbg_cycles + ring * 8;
+  if (tid == 0) dbg[0] = clock64();
   for (int i = tid; i < nr; i += blockDim.x) pts[i] = full[g0 + i];
   for (int i = tid; i < MAXR / 32 + 2; i += blockDim.x) { gap[i] = 0; picked[i] = 0; }
   __syncthreads();
@@ -342,93 +494,71 @@ __global__ void __launch_bounds__(256) k_ring_features(const Pt4* __restrict__ f
     unsigned bal = __ballot_sync(0xffffffffu, g);
     if (lane == 0) gap[base >> 5] = bal;
   }
-  // sort keys: [segment 3b | curvature bits 32b | local index 12b] ; positions outside [s_loc, e_loc-1] -> segment 7
+  // suppression reach of every position (:319-342): fb = forward count | backward count << 4, from the gap bits
   const int span = e_loc - s_loc;
-  for (int i = tid; i < P; i += blockDim.x) {
-    unsigned long long key = ~0ull;
-    if (i >= s_loc && i < e_loc) {
-      // segment j covers [s + span*j/6, s + span*(j+1)/6 - 1] (:284-285)
-      int j = 0;
-      while (j < 5 && i > s_loc + span * (j + 1) / 6 - 1) ++j;
-      key = ((unsigned long long)j << 44) | ((unsigned long long)__float_as_uint(curv[i]) << 12) | (unsigned)i;
-    }
-    keys[i] = key;
+  __syncthreads();
+  for (int i = tid; i < nr; i += blockDim.x) {
+    unsigned char v = 0;
+    if (i >= 5 && i < nr - 5) { int lo, hi; suppress_range(gap, i, lo, hi); v = (unsigned char)((hi - i) | ((i - lo) << 4)); }
+    fb[i] = v;
   }
   __syncthreads();
-  bitonic_sort_u64(keys, P);
+  if (tid == 0) { dbg[1] = clock64(); dbg[2] = dbg[1]; }
 
-  // greedy picks: one warp walks the six segments in order (marks spill into the next segment, :319-342)
-  if (warp == 0) {
-    int n_sharp = 0, n_less_sharp = 0, n_flat = 0;
-    Pt4* o_sharp = st_sharp + ring * 12;
-    Pt4* o_less = st_less_sharp + ring * 120;
-    Pt4* o_flat = st_flat + ring * 24;
-    for (int j = 0; j < 6; ++j) {
-      const int sp = s_loc + span * j / 6, ep = s_loc + span * (j + 1) / 6 - 1;
-      const int lo_s = sp - s_loc, hi_s = ep - s_loc;  // range in the sorted array
-      // ---- largest curvature first (:291-344)
-      int n_large = 0;
-      bool done = false;
-      for (int top = hi_s; top >= lo_s && !done; top -= 32) {
-        int pos = top - lane;
-        bool in = pos >= lo_s;
-        unsigned long long key = in ? keys[pos] : 0ull;
-        int ind = (int)(key & 0xfffu);
-        float c = __uint_as_float((unsigned)(key >> 12));
-        bool elig = in && !((picked[ind >> 5] >> (ind & 31)) & 1u) && ((double)c > 0.1);
-        for (;;) {
-          unsigned m = __ballot_sync(0xffffffffu, elig);
-          if (!m) break;
-          int leader = __ffs(m) - 1;
-          int lind = __shfl_sync(0xffffffffu, ind, leader);
-          ++n_large;
-          if (n_large > 20) { done = true; break; }
-          int lo, hi; suppress_range(gap, lind, lo, hi);
-          if (lane == 0) {
-            Pt4 p = pts[lind];
-            if (n_large <= 2) { label[lind] = 2; o_sharp[n_sharp] = p; o_less[n_less_sharp] = p; }
-            else { label[lind] = 1; o_less[n_less_sharp] = p; }
-            set_bits(picked, lo, hi);
-          }
-          if (n_large <= 2) ++n_sharp;
-          ++n_less_sharp;
-          elig = elig && !(ind >= lo && ind <= hi);
-        }
-        __syncwarp();
-      }
-      // ---- smallest curvature first (:346-390) ; the 4th pick is emitted but not marked
-      int n_small = 0;
-      done = false;
-      for (int bot = lo_s; bot <= hi_s && !done; bot += 32) {
-        int pos = bot + lane;
-        bool in = pos <= hi_s;
-        unsigned long long key = in ? keys[pos] : 0ull;
-        int ind = (int)(key & 0xfffu);
-        float c = __uint_as_float((unsigned)(key >> 12));
-        bool elig = in && !((picked[ind >> 5] >> (ind & 31)) & 1u) && ((double)c < 0.1);
-        for (;;) {
-          unsigned m = __ballot_sync(0xffffffffu, elig);
-          if (!m) break;
-          int leader = __ffs(m) - 1;
-          int lind = __shfl_sync(0xffffffffu, ind, leader);
-          ++n_small;
-          int lo = lind, hi = lind;
-          if (n_small < 4) suppress_range(gap, lind, lo, hi);
-          if (lane == 0) {
-            label[lind] = -1;
-            o_flat[n_flat] = pts[lind];
-            if (n_small < 4) set_bits(picked, lo, hi);
-          }
-          ++n_flat;
-          if (n_small >= 4) { done = true; break; }
-          elig = elig && !(ind >= lo && ind <= hi);
-        }
-        __syncwarp();
+  // greedy picks (:291-390).  std::sort + walk == repeatedly taking the arg-max (arg-min) of the still-eligible
+  // points under the (curvature, index) order, so no sort is needed: one warp keeps a segment's curvatures in
+  // registers (position sp + 32 s + lane in slot s) and performs <= 20 + 4 REDUX selections.
+  // The six segments of a ring depend on each other only through the <= 5 marks a segment spills onto the start of
+  // the next one (:319-330).  Warps 0..5 therefore process the six segments CONCURRENTLY assuming an empty spill;
+  // a segment is re-run (in order) only if a position actually spilled onto it is one of its own picks -- removing a
+  // point that never wins a selection cannot change any selection, so otherwise the speculative result is exact.
+  auto run_segment = [&](int w, unsigned spill_in) {
+    const int sp = s_loc + span * w / 6, ep = s_loc + span * (w + 1) / 6 - 1;
+    int nl, nf; unsigned so;
+    if (ep - sp + 1 <= 12 * 32) pick_segment<12>(curv, fb, sp, ep, spill_in, s_less[w], nl, s_flat[w], nf, so);
+    else pick_segment<24>(curv, fb, sp, ep, spill_in, s_less[w], nl, s_flat[w], nf, so);
+    if (lane == 0) { s_nl[w] = nl; s_nf[w] = nf; s_spill[w] = so; }
+  };
+  if (warp < 6) run_segment(warp, 0u);
+  __syncthreads();
+  for (int w = 1; w < 6; ++w) {
+    if (warp == w) {
+      const unsigned in = s_spill[w - 1];
+      if (in != 0u) {
+        const int sp = s_loc + span * w / 6;
+        const int nl = s_nl[w], nf = s_nf[w];
+        bool hit = false;
+        if (lane < nl) { const int k = (int)s_less[w][lane] - sp; hit = k < 5 && ((in >> k) & 1u); }
+        if (lane >= 24 && lane - 24 < nf) { const int k = (int)s_flat[w][lane - 24] - sp; hit = hit || (k < 5 && ((in >> k) & 1u)); }
+        if (__any_sync(0xffffffffu, hit)) run_segment(w, in);
       }
     }
-    if (lane == 0) { counts[0] = n_sharp; counts[1] = n_less_sharp; counts[2] = n_flat; }
+    __syncthreads();
+  }
+  // labels (:303,309,355) and ring-ordered outputs (ring, segment, pick order) from the per-segment lists
+  if (tid < 6 * 24) {
+    const int w = tid / 24, i = tid % 24;
+    int o_sh = 0, o_ls = 0, o_fl = 0;
+    for (int v = 0; v < w; ++v) { o_sh += min(2, s_nl[v]); o_ls += s_nl[v]; o_fl += s_nf[v]; }
+    if (i < s_nl[w]) {
+      const int p = s_less[w][i];
+      label[p] = i < 2 ? 2 : 1;
+      if (i < 2) st_sharp[ring * 12 + o_sh + i] = pts[p];
+      st_less_sharp[ring * 120 + o_ls + i] = pts[p];
+    }
+    if (i >= 20 && i - 20 < s_nf[w]) {
+      const int p = s_flat[w][i - 20];
+      label[p] = -1;
+      st_flat[ring * 24 + o_fl + (i - 20)] = pts[p];
+    }
+    if (tid == 0) {
+      int a2 = 0, b2 = 0, c2 = 0;
+      for (int v = 0; v < 6; ++v) { a2 += min(2, s_nl[v]); b2 += s_nl[v]; c2 += s_nf[v]; }
+      counts[0] = a2; counts[1] = b2; counts[2] = c2;
+    }
   }
   __syncthreads();
+  if (tid == 0) dbg[3] = clock64();
   if (dbg_label) for (int i = tid; i < nr; i += blockDim.x) dbg_label[g0 + i] = label[i];
 
   // ---- less-flat candidates = positions [s_loc, e_loc-1] with label <= 0 (:392-398), voxel-filtered per ring (:401-407)
@@ -469,23 +599,27 @@ __global__ void __launch_bounds__(256) k_ring_features(const Pt4* __restrict__ f
   }
   const bool any_cand = mn[0] <= mx[0];
   const bool overflow = any_cand && (dxyz[0] * dxyz[1] * dxyz[2] > (long long)INT_MAX);
-  // keys: [voxel idx 32b | local position 12b], non-candidates last
-  for (int i = tid; i < P; i += blockDim.x) {
-    unsigned long long key = ~0ull;
-    if (i >= s_loc && i < e_loc && label[i] <= 0) {
-      unsigned idx = 0;
-      if (!overflow) {
-        int i0 = (int)(floorf(pts[i].x * inv) - (float)min_b[0]);
-        int i1 = (int)(floorf(pts[i].y * inv) - (float)min_b[1]);
-        int i2 = (int)(floorf(pts[i].z * inv) - (float)min_b[2]);
-        idx = (unsigned)(i0 + i1 * div_b[0] + i2 * div_b[0] * div_b[1]);
-      }
-      key = ((unsigned long long)idx << 12) | (unsigned)i;
+  // keys: [voxel idx 32b | local position 12b], non-candidates last ; sorted by the whole CTA
+  // (overflow case: idx = 0 everywhere => position order, i.e. output = input, PCL's early return)
+  auto voxel_key = [&](int i) -> unsigned long long {
+    if (!(i >= s_loc && i < e_loc && label[i] <= 0)) return ~0ull;
+    unsigned idx = 0;
+    if (!overflow) {
+      const int i0 = (int)(floorf(pts[i].x * inv) - (float)min_b[0]);
+      const int i1 = (int)(floorf(pts[i].y * inv) - (float)min_b[1]);
+      const int i2 = (int)(floorf(pts[i].z * inv) - (float)min_b[2]);
+      idx = (unsigned)(i0 + i1 * div_b[0] + i2 * div_b[0] * div_b[1]);
     }
-    keys[i] = key;
-  }
+    return ((unsigned long long)idx << 12) | (unsigned)i;
+  };
+  if (P < 512) P = 512;
   __syncthreads();
-  bitonic_sort_u64(keys, P);  // overflow case: idx = 0 everywhere => position order (output = input, PCL's early return)
+  if (tid == 0) dbg[4] = clock64();
+  if (P == 512) cta_sort_keys<2>(keys, voxel_key);
+  else if (P == 1024) cta_sort_keys<4>(keys, voxel_key);
+  else if (P == 2048) cta_sort_keys<8>(keys, voxel_key);
+  else cta_sort_keys<16>(keys, voxel_key);
+  if (tid == 0) dbg[5] = clock64();
 
   // head flags -> output slots ; each thread owns E consecutive sorted slots
   const int E = P / (int)blockDim.x > 0 ? P / (int)blockDim.x : 1;
@@ -529,8 +663,10 @@ __global__ void __launch_bounds__(256) k_ring_features(const Pt4* __restrict__ f
     Pt4 o; o.x = sx / nf; o.y = sy / nf; o.z = sz / nf; o.i = si / nf;
     o_lf[slot++] = o;
   }
-  if (tid == 0) counts[3] = total;
+  if (tid == 0) { counts[3] = total; dbg[6] = clock64(); }
 }
+
+void features_debug_cycles(long long* host64x8) { cudaMemcpyFromSymbol(host64x8, g_dbg_cycles, sizeof(long long) * 64 * 8); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // ring-ordered concatenation of the staged per-ring outputs ; also ring_start tables of the two "less" clouds

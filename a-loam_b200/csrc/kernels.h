@@ -6,7 +6,7 @@
 
 #define ALOAM_MAX_RING 4096                  // == ALOAM_MAX_RING_POINTS of the public header
 #define ALOAM_ERR_RING_TOO_LARGE_DEV (-7)    // == ALOAM_ERR_RING_TOO_LARGE
-#define ALOAM_LM_THREADS 256
+#define ALOAM_LM_THREADS 288
 #define ALOAM_LM_MAX_TRACE 8
 #define ALOAM_N_KERNEL_IDS 16
 
@@ -14,6 +14,7 @@ namespace aloam {
 
 // ---- features.cu
 size_t ring_features_smem_bytes();
+void features_debug_cycles(long long* host64x8);
 __global__ void k_classify(const float* raw, int n, int stride, int n_scans, float thres2, int8_t* ring_out, int* hist,
                            ScanScalars* sc);
 __global__ void k_ring_scan(const float* raw, int stride, int nblocks, int n_scans, const int* hist, int* offsets,
@@ -52,7 +53,7 @@ struct __align__(8) BlockRec {
   double cp[3];  // curr_point (untransformed)
   double a[3];   // edge: last_point_a          plane: last_point_j      plane-norm: unit normal
   double b[3];   // edge: last_point_b          plane: ljm_norm          plane-norm: unused
-  double s;      // edge: |a-b|  (de.norm())    plane: unused            plane-norm: negative_OA_dot_norm
+  double s;      // edge: 1 / |a-b| (1 / de.norm()) plane: unused         plane-norm: negative_OA_dot_norm
   int type;      // 0 edge, 1 plane, 2 plane-norm, -1 = no residual (query without correspondence)
   int pad;
 };
@@ -76,6 +77,7 @@ struct LmSummary {
   int n_edge, n_plane;      // residual blocks by kind
   double initial_cost, final_cost;
   int trace_rows; int pad;
+  long long cyc_total, cyc_eval, cyc_chol, cyc_plus, cyc_grad;   // SM clock cycles (thread 0 of CTA 0): whole solve / evaluation passes / step solve / Plus / gradient norm
   double trace[ALOAM_LM_MAX_TRACE][8];
 };
 // mode 0: full trust-region solve, x updated in place ; mode 1: one evaluation, out28 = [JtJ upper 21, g 6, cost]

@@ -54,9 +54,9 @@ __device__ __forceinline__ void accumulate_row(double* acc, const double j[6], d
 __device__ __forceinline__ void huber_rho(double huber_a, double sq, double& rho0, double& sr) {
   const double bb = huber_a * huber_a;
   if (sq > bb) {
-    const double rr = sqrt(sq);
+    const double irr = rsqrt(sq), rr = sq * irr;
     rho0 = 2.0 * huber_a * rr - bb;
-    sr = sqrt(fmax(DBL_MIN, huber_a / rr));   // Corrector: rho'' <= 0 => scale residual and Jacobian by sqrt(rho')
+    sr = sqrt(fmax(DBL_MIN, huber_a * irr));   // Corrector: rho'' <= 0 => scale residual and Jacobian by sqrt(rho')
   } else {
     rho0 = sq; sr = 1.0;
   }
@@ -78,9 +78,9 @@ __device__ __forceinline__ void eval_block(const BlockRec& rb, const double* x, 
     const V3 a{rb.a[0], rb.a[1], rb.a[2]}, b{rb.b[0], rb.b[1], rb.b[2]};
     const V3 la{lp.x - a.x, lp.y - a.y, lp.z - a.z}, lb{lp.x - b.x, lp.y - b.y, lp.z - b.z};
     const V3 nu = crossd(la, lb);
-    const double dn = rb.s;  // |a - b|
-    const double r[3] = {nu.x / dn, nu.y / dn, nu.z / dn};
-    const V3 wv{(b.x - a.x) / dn, (b.y - a.y) / dn, (b.z - a.z) / dn};
+    const double idn = rb.s;  // 1 / |a - b|
+    const double r[3] = {nu.x * idn, nu.y * idn, nu.z * idn};
+    const V3 wv{(b.x - a.x) * idn, (b.y - a.y) * idn, (b.z - a.z) * idn};
     // d r / d lp = [wv]x ; rows: n0 = (0,-wz,wy), n1 = (wz,0,-wx), n2 = (-wy,wx,0)
     const V3 ns[3] = {V3{0.0, -wv.z, wv.y}, V3{wv.z, 0.0, -wv.x}, V3{-wv.y, wv.x, 0.0}};
     double rho0, sr;
@@ -150,7 +150,11 @@ struct TrState {
   int reuse_diag, last_successful, iteration, num_invalid, num_successful, num_evals, termination, trace_rows;
 };
 
-__device__ double gradient_max(const double* x, const double* g) {
+// max-norm of Plus(x, -g) - x.  The translation part is |g_t| exactly; the quaternion part (sin / cos / sqrt in double)
+// is only evaluated when it can change the `<= tol` decision, i.e. when the translation part is already <= tol.
+__device__ double gradient_max(const double* x, const double* g, double tol) {
+  const double mt = fmax(fmax(fabs(g[3]), fabs(g[4])), fabs(g[5]));
+  if (mt > tol) return mt;
   double ng[6], xp[7];
 #pragma unroll
   for (int k = 0; k < 6; ++k) ng[k] = -g[k];
@@ -163,22 +167,23 @@ __device__ double gradient_max(const double* x, const double* g) {
 
 // (Hs + diag/radius) y = b by Cholesky ; returns false on breakdown
 __device__ bool chol_solve6(const double Hs[6][6], const double* dg, double radius, const double* b, double* y) {
-  double L[6][6];
+  // L holds the strict lower triangle, inv[j] = 1 / L[j][j]  (one rsqrt per column, no divisions)
+  double L[6][6], inv[6];
+  const double ir = 1.0 / radius;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double d = Hs[j][j] + dg[j] / radius;
+    double d = Hs[j][j] + dg[j] * ir;
 #pragma unroll
     for (int k = 0; k < 6; ++k) if (k < j) d -= L[j][k] * L[j][k];
     if (!(d > 0.0)) return false;
-    d = sqrt(d);
-    L[j][j] = d;
+    inv[j] = rsqrt(d);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       if (i > j) {
         double s = Hs[i][j];
 #pragma unroll
         for (int k = 0; k < 6; ++k) if (k < j) s -= L[i][k] * L[j][k];
-        L[i][j] = s / d;
+        L[i][j] = s * inv[j];
       }
     }
   }
@@ -188,14 +193,14 @@ __device__ bool chol_solve6(const double Hs[6][6], const double* dg, double radi
     double s = b[i];
 #pragma unroll
     for (int k = 0; k < 6; ++k) if (k < i) s -= L[i][k] * z[k];
-    z[i] = s / L[i][i];
+    z[i] = s * inv[i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = z[i];
 #pragma unroll
     for (int k = 0; k < 6; ++k) if (k > i) s -= L[k][i] * y[k];
-    y[i] = s / L[i][i];
+    y[i] = s * inv[i];
   }
   bool ok = true;
 #pragma unroll
@@ -213,9 +218,9 @@ __global__ void k_pack_blocks(const double* __restrict__ packed, int n, BlockRec
   r.type = (int)p[0];
   for (int k = 0; k < 3; ++k) { r.cp[k] = p[1 + k]; r.a[k] = p[4 + k]; r.b[k] = p[7 + k]; }
   r.s = p[10];
-  if (r.type == 0) {  // edge: the kernel wants |a-b| ; s of the packed form is the (always 1) interpolation ratio
+  if (r.type == 0) {  // edge: the kernel wants 1/|a-b| ; s of the packed form is the (always 1) interpolation ratio
     const double ex = r.a[0] - r.b[0], ey = r.a[1] - r.b[1], ez = r.a[2] - r.b[2];
-    r.s = sqrt(ex * ex + ey * ey + ez * ez);
+    r.s = 1.0 / sqrt(ex * ex + ey * ey + ez * ez);
   }
   r.pad = 0;
   out[i] = r;
@@ -239,6 +244,8 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
   const int gtid = (int)crank * NT + tid, gstride = (int)csize * NT;
   const bool writer = crank == 0 && tid == 0;
   int pass = 0;
+  const long long clk0 = clock64();
+  long long clk_eval = 0, clk_chol = 0, clk_plus = 0, clk_grad = 0;
 
   if (tid < 7) s_x[tid] = x7[tid];
   __syncthreads();
@@ -246,6 +253,7 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
   // one evaluation of all residual blocks at s_x -> s_tot[0..27] (identical in every CTA of the cluster).
   // `census` additionally counts edge / plane blocks (slots 28 / 29 of the same reduction, first pass only).
   auto evaluate = [&](bool census) {
+    const long long ce0 = clock64();
     double x[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) x[k] = s_x[k];
@@ -269,16 +277,19 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
       s_cta[pass & 1][tid] = v;
     }
     cluster.sync();
+    if (tid < 32 * (int)csize && tid < NT) {   // one remote read per thread, all CTAs' partials in flight at once
+      const double* remote = cluster.map_shared_rank(&s_cta[pass & 1][0], (unsigned)(tid >> 5));
+      s_part[tid >> 5][tid & 31] = remote[tid & 31];
+    }
+    __syncthreads();
     if (tid < 32) {
       double v = 0.0;
-      for (unsigned r = 0; r < csize; ++r) {
-        const double* remote = cluster.map_shared_rank(&s_cta[pass & 1][0], r);
-        v += remote[tid];
-      }
+      for (unsigned r = 0; r < csize; ++r) v += s_part[r][tid];   // rank order => identical totals in every CTA
       s_tot[tid] = v;
     }
     ++pass;
     __syncthreads();
+    clk_eval += clock64() - ce0;
   };
 
   evaluate(true);
@@ -310,6 +321,7 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
 #pragma unroll
         for (int j = 0; j < 6; ++j) T.diag[j] = fmin(fmax(T.scale[j] * T.scale[j] * T.H[j][j], prm.min_lm_diagonal), prm.max_lm_diagonal);
       }
+      const long long cc0 = clock64();
       double Hs[6][6], b[6], y[6], dg[6];
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
@@ -337,6 +349,7 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
         mcc = -sb - 0.5 * shs;
       }
       T.mcc = mcc;
+      clk_chol += clock64() - cc0;
       if (!(ok && mcc > 0.0)) {  // invalid step
         if (++T.num_invalid >= prm.max_invalid) { trace(T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0); T.termination = 5; s_go = 0; return; }
         T.radius *= 0.5;
@@ -347,7 +360,9 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
       double delta[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) delta[k] = step[k] * T.scale[k];
+      const long long cp0 = clock64();
       plus7(T.x, delta, T.xc);
+      clk_plus += clock64() - cp0;
 #pragma unroll
       for (int k = 0; k < 7; ++k) s_x[k] = T.xc[k];
       s_go = 1;
@@ -380,7 +395,7 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
     } else {
 #pragma unroll
       for (int j = 0; j < 6; ++j) T.scale[j] = 1.0 / (1.0 + sqrt(T.H[j][j]));
-      T.gmax = gradient_max(T.x, T.g);
+      T.gmax = gradient_max(T.x, T.g, prm.gradient_tolerance);
       double xn = 0;
 #pragma unroll
       for (int k = 0; k < 7; ++k) xn += T.x[k] * T.x[k];
@@ -415,7 +430,9 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
           T.x_norm = sqrt(xn);
           load_totals();
           T.cost = cand_cost;
-          T.gmax = gradient_max(T.x, T.g);
+          const long long cg0 = clock64();
+          T.gmax = gradient_max(T.x, T.g, prm.gradient_tolerance);
+          clk_grad += clock64() - cg0;
           T.last_successful = 1;
           ++T.num_successful;
           const double tq = 2.0 * rho - 1.0;
@@ -444,6 +461,8 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
     summary->num_jac_evals = T.num_evals;
     summary->final_cost = T.cost;
     summary->trace_rows = T.trace_rows;
+    summary->cyc_total = clock64() - clk0;
+    summary->cyc_eval = clk_eval; summary->cyc_chol = clk_chol; summary->cyc_plus = clk_plus; summary->cyc_grad = clk_grad;
     if (integrate && world7) {
       // laserOdometry.cpp:504-505  t_w += q_w * t_last_curr ; q_w = q_w * q_last_curr
       const V3 u{world7[0], world7[1], world7[2]};

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
       out->a[0] = a.x; out->a[1] = a.y; out->a[2] = a.z;
       out->b[0] = b.x; out->b[1] = b.y; out->b[2] = b.z;
       const double ex = (double)a.x - (double)b.x, ey = (double)a.y - (double)b.y, ez = (double)a.z - (double)b.z;
-      out->s = sqrt(ex * ex + ey * ey + ez * ez);  // de.norm(), lidarFactor.hpp:36-40
+      out->s = 1.0 / sqrt(ex * ex + ey * ey + ez * ez);  // 1 / de.norm(), lidarFactor.hpp:36-40 (the LM kernel multiplies)
       out->type = 0;
       if (co) { co[0] = closest; co[1] = j2; co[2] = -1; co[3] = 1; }
     }

@@ -144,6 +144,7 @@ int aloam_debug_features(aloam_ctx* ctx, float* curvature, int* label, int* scan
 int aloam_profile_enable(aloam_ctx* ctx, int on);
 int aloam_profile_read(aloam_ctx* ctx, double* ms_sum, long long* count, const char** names, int capacity);
 long long aloam_launch_count(aloam_ctx* ctx);
+int aloam_debug_lm_cycles(aloam_ctx* ctx, long long* out, int outer_iters); /* SM cycles: [solve, evaluation passes] per outer iteration */
 
 #ifdef __cplusplus
 }
