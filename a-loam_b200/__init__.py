@@ -21,7 +21,8 @@ EXPORTED_SYMBOLS = [
     "aloam_default_config", "aloam_create", "aloam_destroy", "aloam_strerror", "aloam_extract_features",
     "aloam_odometry_set_last", "aloam_odometry_register", "aloam_map_upload", "aloam_mapping_register",
     "aloam_voxel_filter", "aloam_scan_to_pose", "aloam_scan_to_pose_device", "aloam_reset_odometry", "aloam_knn",
-    "aloam_odometry_associate", "aloam_normal_equations", "aloam_solve", "aloam_debug_features",
+    "aloam_odometry_associate", "aloam_normal_equations", "aloam_solve", "aloam_debug_features", "aloam_mapping_associate",
+    "aloam_comm_unique_id", "aloam_comm_init", "aloam_profile_enable", "aloam_profile_read", "aloam_launch_count",
 ]
 
 
@@ -90,6 +91,9 @@ def lib():
         L.aloam_profile_read.argtypes = [C.c_void_p, dp, C.POINTER(C.c_longlong), C.POINTER(C.c_char_p), C.c_int]
         L.aloam_launch_count.argtypes = [C.c_void_p]
         L.aloam_launch_count.restype = C.c_longlong
+        L.aloam_mapping_associate.argtypes = [C.c_void_p, cv, cv, dp, dp]
+        L.aloam_comm_unique_id.argtypes = [C.c_char_p]
+        L.aloam_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
         _LIB = L
     return _LIB
 
@@ -204,6 +208,24 @@ class Aloam:
         st = Stats()
         _check(lib().aloam_mapping_register(self._h, a, b, _dp(x), C.byref(st)))
         return x, st.as_dict()
+
+    def mapping_associate(self, corner_stack, surf_stack, x):
+        """per stack point [query, type (-1 rejected, 0 edge, 2 plane-norm), p0(3), p1(3), d, nn(5)] (corner rows first)"""
+        a, ka = _view(corner_stack)
+        b, kb = _view(surf_stack)
+        fits = np.zeros((max(a.n + b.n, 1), 14))
+        _check(lib().aloam_mapping_associate(self._h, a, b, _dp(np.ascontiguousarray(x, np.float64)), _dp(fits)))
+        return fits[:a.n + b.n]
+
+    # --- multi-GPU map sharding: rank 0 makes the id, everybody joins (ship the id with torch.distributed)
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        _check(lib().aloam_comm_unique_id(buf))
+        return bytes(buf.raw)
+
+    def comm_init(self, rank, world, unique_id):
+        _check(lib().aloam_comm_init(self._h, rank, world, C.create_string_buffer(bytes(unique_id), 128)))
 
     def voxel_filter(self, cloud, leaf):
         a, ka = _view(cloud)

@@ -10,210 +10,13 @@
 #include "../../include/aloam_b200.h"
 #include "kernels.h"
 
-using namespace aloam;
-
-namespace {
-
-constexpr int kMaxSharpPerRing = 12, kMaxLessSharpPerRing = 120, kMaxFlatPerRing = 24;
-constexpr int kFusedSharpSlots = 64 * kMaxSharpPerRing;  // 768
-constexpr int kFusedFlatSlots = 64 * kMaxFlatPerRing;    // 1536
-constexpr int kMaxQueries = 16384;                       // API-path capacity for sharp / flat query clouds
-
-struct FeatBuf {
-  Pt4 *sharp = nullptr, *less_sharp = nullptr, *flat = nullptr, *less_flat = nullptr;
-  int* counts = nullptr;           // [4] n_sharp, n_less_sharp, n_flat, n_less_flat (device)
-  int *rs_ls = nullptr, *rs_lf = nullptr;  // ring_start tables [65+]
-  RabIndex g_ls = {}, g_lf = {};           // (azimuth bucket x ring) indices over less_sharp / less_flat
-};
-
-}  // namespace
-
-struct aloam_ctx {
-  aloam_config cfg;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int max_points = 0, nblocks_max = 0;
-  // raw scan + ring binning
-  float* d_raw = nullptr;
-  int8_t* d_ring = nullptr;
-  int *d_hist = nullptr, *d_offsets = nullptr, *d_ring_start = nullptr, *d_scan_start = nullptr, *d_scan_end = nullptr;
-  ScanScalars* d_sc = nullptr;  // [2]
-  Pt4* d_full = nullptr;
-  float* d_curv = nullptr;
-  int8_t* d_label = nullptr;
-  Pt4 *st_sharp = nullptr, *st_less_sharp = nullptr, *st_flat = nullptr, *st_less_flat = nullptr;
-  int* st_counts = nullptr;
-  FeatBuf feat[2];
-  // odometry
-  BlockRec* d_blocks = nullptr;
-  int* d_corr = nullptr;
-  double *d_pose = nullptr, *d_world = nullptr, *d_out28 = nullptr, *d_packed = nullptr;
-  LmSummary* d_summary = nullptr;  // [4]
-  int* d_err = nullptr;
-  Pt4* d_query = nullptr;
-  int* d_knn_idx = nullptr;
-  float* d_knn_d = nullptr;
-  // pinned host mirrors
-  Pt4* h_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  int* h_ints = nullptr;        // scratch ints (counts etc.)
-  double* h_dbl = nullptr;      // scratch doubles
-  LmSummary* h_summary = nullptr;
-  ScanScalars* h_sc = nullptr;
-  // per-kernel profiler (bench.py roofline leg) + cumulative launch counter
-  bool prof_on = false;
-  cudaEvent_t prof_ev[64] = {};
-  int prof_kid[32] = {};
-  int prof_n = 0;
-  double prof_ms[ALOAM_N_KERNEL_IDS] = {};
-  long long prof_cnt[ALOAM_N_KERNEL_IDS] = {};
-  long long launches = 0;
-  // state
-  int parity = 0;         // ScanScalars slot of the next scan
-  int frame = 0;          // fused pipeline: scans seen
-  int cur = 0;            // fused pipeline: feat[] slot of the most recent scan
-  bool have_last = false; // API path: set_last called
-  int last_n_full = 0;
-};
-
-namespace {
-
-enum { KID_CLASSIFY = 0, KID_RING_SCAN, KID_SCATTER, KID_RING_FEATURES, KID_COMPACT, KID_GRID_BUILD, KID_ODOM_ASSOC, KID_LM_SOLVE,
-       KID_RING_OFFSETS, KID_KNN_LAST, KID_PACK_BLOCKS, KID_MAP_GRID, KID_MAP_KNN_FIT, KID_VOXEL };
-const char* const kKernelNames[ALOAM_N_KERNEL_IDS] = {"k_classify", "k_ring_scan", "k_scatter", "k_ring_features", "k_compact",
-    "k_rab_build(3 launches)", "k_odom_assoc", "k_lm_solve", "k_ring_offsets", "k_knn_last", "k_pack_blocks", "k_map_grid", "k_map_knn_fit",
-    "k_voxel", "", ""};
-
-inline void prof_begin(aloam_ctx* c, int kid) {
-  ++c->launches;
-  if (c->prof_on && c->prof_n < 32) { cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream); c->prof_kid[c->prof_n] = kid; }
-}
-inline void prof_end(aloam_ctx* c) {
-  if (c->prof_on && c->prof_n < 32) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream); ++c->prof_n; }
-}
-// call after the stream has been synchronised
-inline void prof_collect(aloam_ctx* c) {
-  for (int i = 0; i < c->prof_n; ++i) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]) == cudaSuccess) { c->prof_ms[c->prof_kid[i]] += ms; ++c->prof_cnt[c->prof_kid[i]]; }
-  }
-  c->prof_n = 0;
-}
-#define LAUNCH(c, kid, kernel, grid, block, smem, ...) \
-  do { prof_begin(c, kid); kernel<<<grid, block, smem, (c)->stream>>>(__VA_ARGS__); prof_end(c); } while (0)
-
-// the LM kernel runs as one thread-block cluster (distributed-shared-memory reduction, see lm.cu)
-constexpr int kLmCluster = 8;
-template <typename... Args>
-void launch_lm(aloam_ctx* c, Args... args) {
-  prof_begin(c, KID_LM_SOLVE);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(kLmCluster); cfg.blockDim = dim3(ALOAM_LM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = kLmCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, k_lm_solve, args...);
-  prof_end(c);
-}
-
-LmParams lm_params(const aloam_config& c) {
-  LmParams p;
-  p.max_iters = c.inner_iters; p.huber_a = c.huber;
-  p.initial_radius = 1e4; p.max_radius = 1e16; p.min_radius = 1e-32;
-  p.min_relative_decrease = 1e-3; p.min_lm_diagonal = 1e-6; p.max_lm_diagonal = 1e32;
-  p.function_tolerance = 1e-6; p.gradient_tolerance = 1e-10; p.parameter_tolerance = 1e-8;
-  p.max_invalid = 5;
-  return p;
-}
-
-template <typename T> cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
-template <typename T> cudaError_t halloc(T** p, size_t n) { return cudaMallocHost((void**)p, n * sizeof(T)); }
-
-int upload_cloud(aloam_ctx* c, aloam_cloud_view v, Pt4* dst, int capacity) {
-  if (v.n < 0 || (v.n > 0 && !v.data) || (v.stride_floats != 4 && v.stride_floats != 8 && v.n > 0)) return ALOAM_ERR_INVALID_ARG;
-  if (v.n > capacity) return ALOAM_ERR_CAPACITY;
-  if (v.n == 0) return ALOAM_OK;
-  if (v.stride_floats == 4) {
-    CUDA_CHECK_RET(cudaMemcpyAsync(dst, v.data, (size_t)v.n * 16, cudaMemcpyHostToDevice, c->stream));
-  } else {
-    CUDA_CHECK_RET(cudaMemcpy2DAsync(dst, 16, v.data, (size_t)v.stride_floats * 4, 16, v.n, cudaMemcpyHostToDevice, c->stream));
-  }
-  return ALOAM_OK;
-}
-
-LastCloud last_corner(const FeatBuf& f) { return LastCloud{f.less_sharp, f.counts + 1, f.g_ls}; }
-LastCloud last_surf(const FeatBuf& f) { return LastCloud{f.less_flat, f.counts + 3, f.g_lf}; }
-
-// feature extraction kernels on a raw scan already in device memory
-int run_features(aloam_ctx* c, const float* d_raw, int n, int stride, FeatBuf& out) {
-  const int nb = (n + 1023) / 1024;
-  const float thres = c->cfg.minimum_range;
-  ScanScalars* sc = c->d_sc + c->parity;
-  ScanScalars* sc_next = c->d_sc + (c->parity ^ 1);
-  LAUNCH(c, KID_CLASSIFY, k_classify, nb, 256, 0, d_raw, n, stride, c->cfg.n_scans, thres * thres, c->d_ring, c->d_hist, sc);
-  LAUNCH(c, KID_RING_SCAN, k_ring_scan, 1, 1024, 0, d_raw, stride, nb, c->cfg.n_scans, c->d_hist, c->d_offsets, c->d_ring_start,
-         c->d_scan_start, c->d_scan_end, sc, sc_next);
-  LAUNCH(c, KID_SCATTER, k_scatter, nb, 256, 0, d_raw, n, stride, c->d_ring, c->d_offsets, sc, c->d_full);
-  LAUNCH(c, KID_RING_FEATURES, k_ring_features, c->cfg.n_scans, 256, ring_features_smem_bytes(), c->d_full, c->d_ring_start,
-         c->cfg.n_scans, 0.2f, c->st_sharp, c->st_less_sharp, c->st_flat, c->st_less_flat, c->st_counts, c->d_curv, c->d_label, sc);
-  LAUNCH(c, KID_COMPACT, k_compact, c->cfg.n_scans, 128, 0, c->cfg.n_scans, c->st_sharp, c->st_less_sharp, c->st_flat,
-         c->st_less_flat, c->st_counts, out.sharp, out.less_sharp, out.flat, out.less_flat, out.counts, out.rs_ls, out.rs_lf);
-  c->parity ^= 1;
-  CUDA_CHECK_RET(cudaGetLastError());
-  return ALOAM_OK;
-}
-
-// index over the two "last" clouds: count -> scan -> fill (n_ls / n_lf = host upper bounds on the cloud sizes)
-void run_grid_build(aloam_ctx* c, FeatBuf& f, int n_ls, int n_lf) {
-  const int pb = (std::max(std::max(n_ls, n_lf), 1) + 255) / 256;
-  LAUNCH(c, KID_GRID_BUILD, k_rab_count, dim3(pb, 2), 256, 0, f.g_ls, f.less_sharp, f.counts + 1, f.g_lf, f.less_flat, f.counts + 3);
-  LAUNCH(c, KID_GRID_BUILD, k_rab_scan, 2, 1024, 0, f.g_ls, f.g_lf);
-  LAUNCH(c, KID_GRID_BUILD, k_rab_fill, dim3(pb, 2), 256, 0, f.g_ls, f.less_sharp, f.counts + 1, f.g_lf, f.less_flat, f.counts + 3);
-}
-
-// outer_iters x (association + LM) ; `cur` supplies sharp/flat, `last` the targets ; pose in c->d_pose
-void run_register(aloam_ctx* c, const FeatBuf& cur, const FeatBuf& last, int sharp_slots, int flat_slots, bool integrate,
-                  int* d_corr) {
-  OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan};
-  const LmParams lp = lm_params(c->cfg);
-  const int slots = sharp_slots + flat_slots;
-  for (int it = 0; it < c->cfg.outer_iters; ++it) {
-    if (slots > 0)
-      LAUNCH(c, KID_ODOM_ASSOC, k_odom_assoc, (slots + 7) / 8, 256, 0, cur.sharp, cur.flat, cur.counts, last_corner(last),
-             last_surf(last), c->d_pose, op, c->d_blocks, d_corr, sharp_slots);
-    const bool last_it = it == c->cfg.outer_iters - 1;
-    launch_lm(c, (const BlockRec*)c->d_blocks, (const int*)nullptr, slots, c->d_pose, lp, c->d_summary + (it & 3), 0,
-              (double*)nullptr, c->d_world, (integrate && last_it) ? 1 : 0);
-  }
-}
-
-void fill_stats(aloam_ctx* c, aloam_stats* st, int outer, int flags, float ms) {
-  if (!st) return;
-  std::memset(st, 0, sizeof(*st));
-  st->flags = flags;
-  st->ms_total = ms;
-  for (int it = 0; it < outer && it < 4; ++it) {
-    const LmSummary& s = c->h_summary[it];
-    st->lm_iters += s.num_iterations;
-    st->accepted_steps += s.num_successful;
-    st->termination[it] = s.termination;
-    if (it == outer - 1) {
-      st->n_corner_corr = s.n_edge; st->n_plane_corr = s.n_plane;
-      st->init_cost = s.initial_cost; st->final_cost = s.final_cost;
-      if (s.n_edge + s.n_plane < 10) st->flags |= ALOAM_FLAG_FEW_CORRESPONDENCES;
-    }
-  }
-}
-
-int check_view(const aloam_cloud_view& v) {
-  if (v.n < 0) return ALOAM_ERR_INVALID_ARG;
-  if (v.n > 0 && (!v.data || (v.stride_floats != 4 && v.stride_floats != 8))) return ALOAM_ERR_INVALID_ARG;
-  return ALOAM_OK;
-}
-
-}  // namespace
+#include "ctx.h"
 
 extern "C" {
+
+void aloam_map_free_impl(aloam_ctx* c);
+void aloam_comm_free_impl(aloam_ctx* c);
+int aloam_map_knn_impl(aloam_ctx* c, int which, aloam_cloud_view queries, int k, int* idx, float* sqdist);
 
 void aloam_default_config(aloam_config* cfg, int n_scans) {
   if (!cfg) return;
@@ -261,6 +64,8 @@ int aloam_destroy(aloam_ctx* c) {
       for (void* p : gp) if (p) cudaFree(p);
     }
   }
+  aloam_map_free_impl(c);
+  aloam_comm_free_impl(c);
   for (Pt4* p : c->h_out) if (p) cudaFreeHost(p);
   if (c->h_ints) cudaFreeHost(c->h_ints);
   if (c->h_dbl) cudaFreeHost(c->h_dbl);
@@ -556,7 +361,8 @@ int aloam_knn(aloam_ctx* c, int which, aloam_cloud_view queries, int k, int* idx
     CUDA_CHECK_RET(cudaGetLastError());
     return ALOAM_OK;
   }
-  return ALOAM_ERR_STATE;  // map trees: see aloam_map_upload
+  if (which == 2 || which == 3) return aloam_map_knn_impl(c, which, queries, k, idx, sqdist);
+  return ALOAM_ERR_INVALID_ARG;
 }
 
 static int run_lm_api(aloam_ctx* c, const double* blocks, int n_blocks, const double x[7], int mode) {

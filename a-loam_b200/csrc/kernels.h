@@ -63,6 +63,33 @@ __global__ void k_odom_assoc(const Pt4* sharp, const Pt4* flat, const int* feat_
                              int* corr /*[(n_sharp+n_flat)][4] a,b,c,valid*/, int max_sharp);
 __global__ void k_knn_last(LastCloud cloud, const Pt4* queries, int nq, int* idx, float* sqd);
 
+// ---- mapping.cu
+// hash grid over a map cloud = what replaces the kd-tree builds of laserMapping.cpp:558-559
+struct GridTable {
+  unsigned long long* keys;  // [mask+1] packed cell coordinates, ~0 = empty
+  int* cnt;                  // [mask+1] points in the cell
+  int* start;                // [mask+1] first slot of the cell in gpts
+  int* cursor;               // [1] storage cursor
+  int* slot_of;              // [capacity] table slot of point i
+  int* rank_of;              // [capacity] rank of point i inside its cell
+  float4* gpts;              // [capacity] cell-contiguous copy: x, y, z, bits(original index)
+  unsigned mask;             // table size - 1 (power of two)
+  float cs, inv_cs;          // cell edge [m]
+};
+struct MapCloud {
+  Pt4* pts;     // uploaded cloud, original order
+  int n;        // host-known size
+  GridTable grid;
+};
+__global__ void k_grid_clear(GridTable a, GridTable b);
+__global__ void k_grid_insert(GridTable a, const Pt4* pa, int na, GridTable b, const Pt4* pb, int nb);
+__global__ void k_grid_alloc(GridTable a, GridTable b);
+__global__ void k_grid_fill(GridTable a, const Pt4* pa, int na, GridTable b, const Pt4* pb, int nb);
+// 5-NN + line / plane fit + residual block per stack point (laserMapping.cpp:577-687); queries = corner then surf
+__global__ void k_map_assoc(const Pt4* corner_stack, int n_corner, const Pt4* surf_stack, int n_surf, MapCloud corner_map,
+                            MapCloud surf_map, const double* pose7, BlockRec* blocks, double* fits, int shard_rank, int shard_count);
+__global__ void k_map_knn(MapCloud map, const Pt4* queries, int nq, int k, int* idx, float* sqd);
+
 // ---- lm.cu
 struct LmParams {
   int max_iters;
@@ -84,6 +111,10 @@ struct LmSummary {
 // integrate != 0 : after the solve compose the world pose (laserOdometry.cpp:504-505): world7 <- world7 (+) x
 __global__ void k_lm_solve(const BlockRec* blocks, const int* n_blocks_ptr, int n_blocks_host, double* x7,
                            LmParams prm, LmSummary* summary, int mode, double* out28, double* world7, int integrate);
+// sharded solve: per-evaluation kernels around an ncclAllReduce (see lm.cu, comm.cu)
+size_t lm_state_bytes();
+__global__ void k_lm_eval_shard(const BlockRec* blocks, int n, const double* x7, void* state, int first, double huber_a, double* local32);
+__global__ void k_lm_tr_shard(void* state, const double* tot32, double* x7, int first, int last, LmParams prm, LmSummary* summary);
 // packs API-side residual blocks (11 doubles) into BlockRec
 __global__ void k_pack_blocks(const double* packed, int n, BlockRec* out);
 

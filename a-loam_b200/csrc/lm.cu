@@ -143,11 +143,13 @@ __device__ __forceinline__ void plus7(const double* x, const double* d, double* 
   o[4] = x[4] + d[3]; o[5] = x[5] + d[4]; o[6] = x[6] + d[5];
 }
 
-// trust-region state of one solve; lives in shared memory, touched by thread 0 only
+// trust-region state of one solve (thread 0 only).  Shared memory in k_lm_solve, global memory in the sharded path.
 struct TrState {
   double x[7], xc[7], H[6][6], g[6], scale[6], diag[6];
   double cost, radius, decrease_factor, mcc, gmax, x_norm;
   int reuse_diag, last_successful, iteration, num_invalid, num_successful, num_evals, termination, trace_rows;
+  int go;       // 1: xc holds a candidate that must be evaluated next ; 0: the solve is over
+  int n_res;
 };
 
 // max-norm of Plus(x, -g) - x.  The translation part is |g_t| exactly; the quaternion part (sin / cos / sqrt in double)
@@ -208,6 +210,203 @@ __device__ bool chol_solve6(const double Hs[6][6], const double* dg, double radi
   return ok;
 }
 
+__device__ __forceinline__ void tr_trace(TrState& T, LmSummary* summary, bool writer, double c, double cc, double gm, double sn,
+                                         double rd, double rad, int valid, int succ) {
+  if (T.trace_rows < ALOAM_LM_MAX_TRACE) {
+    if (writer) {
+      double* o = summary->trace[T.trace_rows];
+      o[0] = c; o[1] = cc; o[2] = gm; o[3] = sn; o[4] = rd; o[5] = rad; o[6] = valid; o[7] = succ;
+    }
+    ++T.trace_rows;
+  }
+}
+
+// totals (28 numbers) -> T.H (full symmetric), T.g
+__device__ __forceinline__ void tr_load_totals(TrState& T, const double* tot) {
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+#pragma unroll
+    for (int c = a; c < 6; ++c) { T.H[a][c] = tot[k]; T.H[c][a] = tot[k]; ++k; }
+  }
+#pragma unroll
+  for (int a = 0; a < 6; ++a) T.g[a] = tot[21 + a];
+}
+
+// produce the next candidate (-> T.xc, T.go = 1) or stop (T.go = 0)
+__device__ void tr_next_candidate(TrState& T, const LmParams& prm, LmSummary* summary, bool writer) {
+  for (;;) {
+    if (T.iteration >= prm.max_iters) { T.termination = 0; T.go = 0; return; }
+    if (T.last_successful && T.gmax <= prm.gradient_tolerance) { T.termination = 1; T.go = 0; return; }
+    if (T.radius < prm.min_radius) { T.termination = 5; T.go = 0; return; }
+    ++T.iteration;
+    T.last_successful = 0;
+    if (!T.reuse_diag) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) T.diag[j] = fmin(fmax(T.scale[j] * T.scale[j] * T.H[j][j], prm.min_lm_diagonal), prm.max_lm_diagonal);
+    }
+    double Hs[6][6], b[6], y[6], dg[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) Hs[a][c] = T.scale[a] * T.H[a][c] * T.scale[c];
+      b[a] = T.scale[a] * T.g[a];
+      dg[a] = T.diag[a];
+    }
+    const bool ok = chol_solve6(Hs, dg, T.radius, b, y);
+    T.reuse_diag = 1;
+    double mcc = 0;
+    if (ok) {
+      // model_cost_change = -(Js step)^T (r + Js step / 2) = -step^T Js^T r - 1/2 step^T Js^T Js step,  step = -y
+      double sb = 0, shs = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        sb -= y[a] * b[a];
+        double t = 0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) t -= Hs[a][c] * y[c];
+        shs -= y[a] * t;
+      }
+      mcc = -sb - 0.5 * shs;
+    }
+    T.mcc = mcc;
+    if (!(ok && mcc > 0.0)) {  // invalid step
+      if (++T.num_invalid >= prm.max_invalid) { tr_trace(T, summary, writer, T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0); T.termination = 5; T.go = 0; return; }
+      T.radius *= 0.5;
+      tr_trace(T, summary, writer, T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0);
+      continue;
+    }
+    T.num_invalid = 0;
+    double delta[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) delta[k] = -y[k] * T.scale[k];
+    plus7(T.x, delta, T.xc);
+    T.go = 1;
+    return;
+  }
+}
+
+// iteration 0: totals of the evaluation at x ; tot[28], tot[29] = number of edge / plane blocks
+__device__ void tr_start(TrState& T, const double* x, const double* tot, const LmParams& prm, LmSummary* summary, bool writer) {
+  const int ne = (int)(tot[28] + 0.5), np = (int)(tot[29] + 0.5);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { T.x[k] = x[k]; T.xc[k] = x[k]; }
+  tr_load_totals(T, tot);
+  T.cost = tot[27];
+  T.radius = prm.initial_radius; T.decrease_factor = 2.0; T.mcc = 0; T.gmax = 0;
+  T.reuse_diag = 0; T.last_successful = 0; T.iteration = 0; T.num_invalid = 0; T.num_successful = 0; T.num_evals = 1;
+  T.termination = 0; T.trace_rows = 0; T.n_res = ne + np; T.go = 0;
+  if (writer) { summary->initial_cost = T.cost; summary->n_edge = ne; summary->n_plane = np; }
+  if (ne + np == 0) { T.termination = 4; return; }  // Ceres: nothing to optimise, parameters untouched
+#pragma unroll
+  for (int j = 0; j < 6; ++j) T.scale[j] = 1.0 / (1.0 + sqrt(T.H[j][j]));
+  T.gmax = gradient_max(T.x, T.g, prm.gradient_tolerance);
+  double xn = 0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) xn += T.x[k] * T.x[k];
+  T.x_norm = sqrt(xn);
+  tr_trace(T, summary, writer, T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0);
+  if (T.gmax <= prm.gradient_tolerance) { T.termination = 1; return; }
+  tr_next_candidate(T, prm, summary, writer);
+}
+
+// after the evaluation of candidate T.xc: tolerance tests, accept / reject, next candidate
+__device__ void tr_after_eval(TrState& T, const double* tot, const LmParams& prm, LmSummary* summary, bool writer) {
+  ++T.num_evals;
+  const double cand_cost = tot[27];
+  double sn = 0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) sn += (T.x[k] - T.xc[k]) * (T.x[k] - T.xc[k]);
+  sn = sqrt(sn);
+  const double cost_change = T.cost - cand_cost;
+  if (sn <= prm.parameter_tolerance * (T.x_norm + prm.parameter_tolerance)) {
+    tr_trace(T, summary, writer, T.cost, 0, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 2; T.go = 0; return;
+  }
+  if (fabs(cost_change) <= prm.function_tolerance * T.cost) {
+    tr_trace(T, summary, writer, T.cost, cost_change, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 3; T.go = 0; return;
+  }
+  const double rho = cost_change / T.mcc;
+  if (rho > prm.min_relative_decrease) {
+    double xn = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { T.x[k] = T.xc[k]; xn += T.xc[k] * T.xc[k]; }
+    T.x_norm = sqrt(xn);
+    tr_load_totals(T, tot);
+    T.cost = cand_cost;
+    T.gmax = gradient_max(T.x, T.g, prm.gradient_tolerance);
+    T.last_successful = 1;
+    ++T.num_successful;
+    const double tq = 2.0 * rho - 1.0;
+    T.radius = fmin(prm.max_radius, T.radius / fmax(1.0 / 3.0, 1.0 - tq * tq * tq));
+    T.decrease_factor = 2.0;
+    T.reuse_diag = 0;
+    tr_trace(T, summary, writer, T.cost, cost_change, T.gmax, sn, rho, T.radius, 1, 1);
+  } else {
+    T.radius = T.radius / T.decrease_factor;
+    T.decrease_factor *= 2.0;
+    T.reuse_diag = 1;
+    tr_trace(T, summary, writer, T.cost, cost_change, T.gmax, sn, rho, T.radius, 1, 0);
+  }
+  tr_next_candidate(T, prm, summary, writer);
+}
+
+__device__ void tr_finish(const TrState& T, double* x7, LmSummary* summary) {
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x7[k] = T.x[k];
+  summary->termination = T.termination;
+  summary->num_iterations = T.iteration;
+  summary->num_successful = T.num_successful;
+  summary->num_jac_evals = T.num_evals;
+  summary->final_cost = T.cost;
+  summary->trace_rows = T.trace_rows;
+}
+
+// every thread of the cluster evaluates its share of the blocks at x ; afterwards s_tot[0..31] holds the cluster-wide
+// totals in every CTA (slots 28 / 29 = edge / plane block counts)
+template <typename Cluster>
+__device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRec* __restrict__ blocks, int n, const double* xs,
+                                                 double huber_a, double (*s_part)[32], double (*s_cta)[32], double* s_tot, int& pass) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
+  const int gtid = (int)crank * NT + tid, gstride = (int)csize * NT;
+  double x[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) x[k] = xs[k];
+  double acc[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+  for (int b = gtid; b < n; b += gstride) {
+    const BlockRec rb = blocks[b];
+    if (rb.type >= 0) {
+      eval_block(rb, x, huber_a, acc);
+      acc[28] += (rb.type == 0) ? 1.0 : 0.0;
+      acc[29] += (rb.type > 0) ? 1.0 : 0.0;
+    }
+  }
+  const double mine = warp_transpose_reduce(acc);
+  s_part[warp][lane] = mine;
+  __syncthreads();
+  if (tid < 32) {
+    double v = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) v += s_part[w2][tid];
+    s_cta[pass & 1][tid] = v;
+  }
+  cluster.sync();
+  if (tid < 32 * (int)csize && tid < NT) {   // one remote read per thread, all CTAs' partials in flight at once
+    const double* remote = cluster.map_shared_rank(&s_cta[pass & 1][0], (unsigned)(tid >> 5));
+    s_part[tid >> 5][tid & 31] = remote[tid & 31];
+  }
+  __syncthreads();
+  if (tid < 32) {
+    double v = 0.0;
+    for (unsigned r = 0; r < csize; ++r) v += s_part[r][tid];   // rank order => identical totals in every CTA
+    s_tot[tid] = v;
+  }
+  ++pass;
+  __syncthreads();
+}
+
 }  // namespace
 
 __global__ void k_pack_blocks(const double* __restrict__ packed, int n, BlockRec* __restrict__ out) {
@@ -231,238 +430,37 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
                                                     LmSummary* __restrict__ summary, int mode, double* __restrict__ out28,
                                                     double* __restrict__ world7, int integrate) {
   cg::cluster_group cluster = cg::this_cluster();
-  const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
   __shared__ double s_part[NW][32];
   __shared__ double s_cta[2][32];   // this CTA's partial totals, double-buffered by pass parity (read by the whole cluster)
   __shared__ double s_tot[32];
   __shared__ double s_x[7];
-  __shared__ int s_go;
-  __shared__ int s_cnt[2];
   __shared__ TrState T;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int n = n_blocks_ptr ? *n_blocks_ptr : n_blocks_host;
-  const int gtid = (int)crank * NT + tid, gstride = (int)csize * NT;
-  const bool writer = crank == 0 && tid == 0;
+  const bool writer = cluster.block_rank() == 0 && tid == 0;
   int pass = 0;
   const long long clk0 = clock64();
-  long long clk_eval = 0, clk_chol = 0, clk_plus = 0, clk_grad = 0;
 
   if (tid < 7) s_x[tid] = x7[tid];
   __syncthreads();
-
-  // one evaluation of all residual blocks at s_x -> s_tot[0..27] (identical in every CTA of the cluster).
-  // `census` additionally counts edge / plane blocks (slots 28 / 29 of the same reduction, first pass only).
-  auto evaluate = [&](bool census) {
-    const long long ce0 = clock64();
-    double x[7];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) x[k] = s_x[k];
-    double acc[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-    for (int b = gtid; b < n; b += gstride) {
-      const BlockRec rb = blocks[b];
-      if (rb.type >= 0) {
-        eval_block(rb, x, prm.huber_a, acc);
-        if (census) { acc[28] += (rb.type == 0) ? 1.0 : 0.0; acc[29] += (rb.type > 0) ? 1.0 : 0.0; }
-      }
-    }
-    const double mine = warp_transpose_reduce(acc);
-    s_part[warp][lane] = mine;
-    __syncthreads();
-    if (tid < 32) {
-      double v = 0.0;
-#pragma unroll
-      for (int w2 = 0; w2 < NW; ++w2) v += s_part[w2][tid];
-      s_cta[pass & 1][tid] = v;
-    }
-    cluster.sync();
-    if (tid < 32 * (int)csize && tid < NT) {   // one remote read per thread, all CTAs' partials in flight at once
-      const double* remote = cluster.map_shared_rank(&s_cta[pass & 1][0], (unsigned)(tid >> 5));
-      s_part[tid >> 5][tid & 31] = remote[tid & 31];
-    }
-    __syncthreads();
-    if (tid < 32) {
-      double v = 0.0;
-      for (unsigned r = 0; r < csize; ++r) v += s_part[r][tid];   // rank order => identical totals in every CTA
-      s_tot[tid] = v;
-    }
-    ++pass;
-    __syncthreads();
-    clk_eval += clock64() - ce0;
-  };
-
-  evaluate(true);
+  cluster_evaluate(cluster, blocks, n, s_x, prm.huber_a, s_part, s_cta, s_tot, pass);
 
   if (mode == 1) {
-    if (crank == 0 && tid < 28) out28[tid] = s_tot[tid];
+    if (cluster.block_rank() == 0 && tid < 28) out28[tid] = s_tot[tid];
     cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
     return;
   }
-
-  auto trace = [&](double c, double cc, double gm, double sn, double rd, double rad, int valid, int succ) {
-    if (T.trace_rows < ALOAM_LM_MAX_TRACE) {
-      if (writer) {
-        double* o = summary->trace[T.trace_rows];
-        o[0] = c; o[1] = cc; o[2] = gm; o[3] = sn; o[4] = rd; o[5] = rad; o[6] = valid; o[7] = succ;
-      }
-      ++T.trace_rows;
-    }
-  };
-  // produce the next candidate (-> s_x, s_go = 1) or stop (s_go = 0) ; thread 0 only
-  auto next_candidate = [&]() {
-    for (;;) {
-      if (T.iteration >= prm.max_iters) { T.termination = 0; s_go = 0; return; }
-      if (T.last_successful && T.gmax <= prm.gradient_tolerance) { T.termination = 1; s_go = 0; return; }
-      if (T.radius < prm.min_radius) { T.termination = 5; s_go = 0; return; }
-      ++T.iteration;
-      T.last_successful = 0;
-      if (!T.reuse_diag) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) T.diag[j] = fmin(fmax(T.scale[j] * T.scale[j] * T.H[j][j], prm.min_lm_diagonal), prm.max_lm_diagonal);
-      }
-      const long long cc0 = clock64();
-      double Hs[6][6], b[6], y[6], dg[6];
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) Hs[a][c] = T.scale[a] * T.H[a][c] * T.scale[c];
-        b[a] = T.scale[a] * T.g[a];
-        dg[a] = T.diag[a];
-      }
-      const bool ok = chol_solve6(Hs, dg, T.radius, b, y);
-      T.reuse_diag = 1;
-      double step[6];
-      double mcc = 0;
-      if (ok) {
-        // model_cost_change = -(Js step)^T (r + Js step / 2) = -step^T Js^T r - 1/2 step^T Js^T Js step
-        double sb = 0, shs = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-          step[a] = -y[a];
-          sb -= y[a] * b[a];
-          double t = 0;
-#pragma unroll
-          for (int c = 0; c < 6; ++c) t -= Hs[a][c] * y[c];
-          shs -= y[a] * t;
-        }
-        mcc = -sb - 0.5 * shs;
-      }
-      T.mcc = mcc;
-      clk_chol += clock64() - cc0;
-      if (!(ok && mcc > 0.0)) {  // invalid step
-        if (++T.num_invalid >= prm.max_invalid) { trace(T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0); T.termination = 5; s_go = 0; return; }
-        T.radius *= 0.5;
-        trace(T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0);
-        continue;
-      }
-      T.num_invalid = 0;
-      double delta[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) delta[k] = step[k] * T.scale[k];
-      const long long cp0 = clock64();
-      plus7(T.x, delta, T.xc);
-      clk_plus += clock64() - cp0;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) s_x[k] = T.xc[k];
-      s_go = 1;
-      return;
-    }
-  };
-  auto load_totals = [&]() {   // s_tot -> T.H (full symmetric), T.g
-    int k = 0;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-#pragma unroll
-      for (int c = a; c < 6; ++c) { T.H[a][c] = s_tot[k]; T.H[c][a] = s_tot[k]; ++k; }
-    }
-#pragma unroll
-    for (int a = 0; a < 6; ++a) T.g[a] = s_tot[21 + a];
-  };
-
-  if (tid == 0) {
-    s_cnt[0] = (int)(s_tot[28] + 0.5); s_cnt[1] = (int)(s_tot[29] + 0.5);
-#pragma unroll
-    for (int k = 0; k < 7; ++k) T.x[k] = s_x[k];
-    load_totals();
-    T.cost = s_tot[27];
-    T.radius = prm.initial_radius; T.decrease_factor = 2.0; T.mcc = 0; T.gmax = 0;
-    T.reuse_diag = 0; T.last_successful = 0; T.iteration = 0; T.num_invalid = 0; T.num_successful = 0; T.num_evals = 1;
-    T.termination = 0; T.trace_rows = 0;
-    if (writer) { summary->initial_cost = T.cost; summary->n_edge = s_cnt[0]; summary->n_plane = s_cnt[1]; }
-    if (s_cnt[0] + s_cnt[1] == 0) {  // Ceres: nothing to optimise, parameters untouched
-      T.termination = 4; s_go = 0;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 6; ++j) T.scale[j] = 1.0 / (1.0 + sqrt(T.H[j][j]));
-      T.gmax = gradient_max(T.x, T.g, prm.gradient_tolerance);
-      double xn = 0;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) xn += T.x[k] * T.x[k];
-      T.x_norm = sqrt(xn);
-      trace(T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0);
-      if (T.gmax <= prm.gradient_tolerance) { T.termination = 1; s_go = 0; }
-      else next_candidate();
-    }
-  }
+  // thread 0 of EVERY CTA takes the same decision from the same totals (no broadcast needed)
+  if (tid == 0) tr_start(T, s_x, s_tot, prm, summary, writer);
   __syncthreads();
-
-  while (s_go) {
-    evaluate(false);
-    if (tid == 0) {
-      ++T.num_evals;
-      const double cand_cost = s_tot[27];
-      double sn = 0;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) sn += (T.x[k] - T.xc[k]) * (T.x[k] - T.xc[k]);
-      sn = sqrt(sn);
-      const double cost_change = T.cost - cand_cost;
-      if (sn <= prm.parameter_tolerance * (T.x_norm + prm.parameter_tolerance)) {
-        trace(T.cost, 0, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 2; s_go = 0;
-      } else if (fabs(cost_change) <= prm.function_tolerance * T.cost) {
-        trace(T.cost, cost_change, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 3; s_go = 0;
-      } else {
-        const double rho = cost_change / T.mcc;
-        if (rho > prm.min_relative_decrease) {
-          double xn = 0;
-#pragma unroll
-          for (int k = 0; k < 7; ++k) { T.x[k] = T.xc[k]; xn += T.xc[k] * T.xc[k]; }
-          T.x_norm = sqrt(xn);
-          load_totals();
-          T.cost = cand_cost;
-          const long long cg0 = clock64();
-          T.gmax = gradient_max(T.x, T.g, prm.gradient_tolerance);
-          clk_grad += clock64() - cg0;
-          T.last_successful = 1;
-          ++T.num_successful;
-          const double tq = 2.0 * rho - 1.0;
-          T.radius = fmin(prm.max_radius, T.radius / fmax(1.0 / 3.0, 1.0 - tq * tq * tq));
-          T.decrease_factor = 2.0;
-          T.reuse_diag = 0;
-          trace(T.cost, cost_change, T.gmax, sn, rho, T.radius, 1, 1);
-        } else {
-          T.radius = T.radius / T.decrease_factor;
-          T.decrease_factor *= 2.0;
-          T.reuse_diag = 1;
-          trace(T.cost, cost_change, T.gmax, sn, rho, T.radius, 1, 0);
-        }
-        next_candidate();
-      }
-    }
+  while (T.go) {
+    cluster_evaluate(cluster, blocks, n, T.xc, prm.huber_a, s_part, s_cta, s_tot, pass);
+    if (tid == 0) tr_after_eval(T, s_tot, prm, summary, writer);
     __syncthreads();
   }
-
   if (writer) {
-#pragma unroll
-    for (int k = 0; k < 7; ++k) x7[k] = T.x[k];
-    summary->termination = T.termination;
-    summary->num_iterations = T.iteration;
-    summary->num_successful = T.num_successful;
-    summary->num_jac_evals = T.num_evals;
-    summary->final_cost = T.cost;
-    summary->trace_rows = T.trace_rows;
+    tr_finish(T, x7, summary);
     summary->cyc_total = clock64() - clk0;
-    summary->cyc_eval = clk_eval; summary->cyc_chol = clk_chol; summary->cyc_plus = clk_plus; summary->cyc_grad = clk_grad;
     if (integrate && world7) {
       // laserOdometry.cpp:504-505  t_w += q_w * t_last_curr ; q_w = q_w * q_last_curr
       const V3 u{world7[0], world7[1], world7[2]};
@@ -483,6 +481,47 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
     }
   }
   cluster.sync();  // no CTA may exit while another can still read its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sharded solve (map split over GPUs): the same trust-region logic, but every evaluation is
+//   k_lm_eval_shard (this rank's blocks -> local 32-vector)  ->  ncclAllReduce(sum, 32 doubles)  ->  k_lm_tr_shard
+// all stream-ordered, no host round trip: the schedule is fixed (1 + max_iters evaluations); once the state says
+// "stop" the remaining kernels return immediately.  Every rank runs the identical step on identical totals.
+size_t lm_state_bytes() { return sizeof(TrState); }
+
+__global__ void __launch_bounds__(NT, 1) k_lm_eval_shard(const BlockRec* __restrict__ blocks, int n, const double* __restrict__ x7,
+                                                         void* state, int first, double huber_a, double* __restrict__ local32) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ double s_part[NW][32];
+  __shared__ double s_cta[2][32];
+  __shared__ double s_tot[32];
+  __shared__ double s_x[7];
+  const TrState* T = reinterpret_cast<const TrState*>(state);
+  const int tid = threadIdx.x;
+  const bool active = first || T->go;   // uniform over the grid and over all ranks
+  if (tid < 7) s_x[tid] = first ? x7[tid] : T->xc[tid];
+  __syncthreads();
+  int pass = 0;
+  if (active) {
+    cluster_evaluate(cluster, blocks, n, s_x, huber_a, s_part, s_cta, s_tot, pass);
+    if (cluster.block_rank() == 0 && tid < 32) local32[tid] = s_tot[tid];
+  } else if (cluster.block_rank() == 0 && tid < 32) {
+    local32[tid] = 0.0;
+  }
+  cluster.sync();
+}
+
+__global__ void k_lm_tr_shard(void* state, const double* __restrict__ tot32, double* __restrict__ x7, int first, int last,
+                              LmParams prm, LmSummary* __restrict__ summary) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  TrState& T = *reinterpret_cast<TrState*>(state);
+  if (first) tr_start(T, x7, tot32, prm, summary, true);
+  else if (T.go) tr_after_eval(T, tot32, prm, summary, true);
+  if (last || !T.go) {
+    if (last && T.go) { T.go = 0; }   // cannot happen: the schedule covers max_iters evaluations
+    tr_finish(T, x7, summary);
+  }
 }
 
 }  // namespace aloam
