@@ -56,3 +56,21 @@ def pose(index):
     t = np.zeros(3)
     _lib().synth_pose(index, q.ctypes.data_as(C.POINTER(C.c_double)), t.ctypes.data_as(C.POINTER(C.c_double)))
     return q, t
+
+
+def voxel_downsample(cloud, leaf):
+    """Voxel-centroid downsample used to BUILD synthetic maps (numpy; same grid rule as pcl::VoxelGrid, float64 sums --
+    it only has to produce a plausible map, the parity-relevant VoxelGrid lives in the oracle / CUDA path)."""
+    cloud = np.ascontiguousarray(cloud, np.float32)
+    if len(cloud) == 0:
+        return cloud.copy()
+    ijk = np.floor(cloud[:, :3] / np.float32(leaf)).astype(np.int64)
+    ijk -= ijk.min(0)
+    dims = ijk.max(0) + 1
+    key = ijk[:, 0] + dims[0] * (ijk[:, 1] + dims[1] * ijk[:, 2])
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
+    sums = np.add.reduceat(cloud[order].astype(np.float64), starts, axis=0)
+    counts = np.diff(np.r_[starts, len(ks)])[:, None]
+    return (sums / counts).astype(np.float32)
