@@ -65,6 +65,7 @@ int aloam_destroy(aloam_ctx* c) {
     }
   }
   aloam_map_free_impl(c);
+  { void* vp[] = {c->d_vox_keys[0], c->d_vox_keys[1], c->d_vox_vals[0], c->d_vox_vals[1], c->d_vox_hist, c->d_vox_offs, c->d_vox_misc}; for (void* p : vp) if (p) cudaFree(p); }
   aloam_comm_free_impl(c);
   for (Pt4* p : c->h_out) if (p) cudaFreeHost(p);
   if (c->h_ints) cudaFreeHost(c->h_ints);

@@ -64,6 +64,10 @@ struct aloam_ctx {
   Pt4 *d_stack_corner = nullptr, *d_stack_surf = nullptr;
   double* d_fits = nullptr;      // [queries][14] debug / test records of the line / plane fits
   BlockRec* d_map_blocks = nullptr;
+  // general voxel filter (voxel.cu): radix-sort ping-pong buffers, histograms, small scalars
+  unsigned* d_vox_keys[2] = {nullptr, nullptr};
+  int* d_vox_vals[2] = {nullptr, nullptr};
+  int *d_vox_hist = nullptr, *d_vox_offs = nullptr, *d_vox_misc = nullptr;
   // pinned host mirrors
   Pt4* h_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int* h_ints = nullptr;        // scratch ints (counts etc.)

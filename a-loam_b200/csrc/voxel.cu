@@ -1,5 +1,290 @@
-// pcl::VoxelGrid<PointXYZI> on an arbitrary cloud (laserMapping.cpp:543-549: the scan stacks) -- general GPU
-// implementation (stable LSD radix sort on the voxel index + ordered float centroids).
+// pcl::VoxelGrid<PointXYZI>::applyFilter on an arbitrary cloud -- the scan-stack filters of laserMapping.cpp:543-549
+// (downSizeFilterCorner / downSizeFilterSurf) as a general GPU routine (the per-ring 0.2 m instance of
+// scanRegistration.cpp:401-407 is fused into k_ring_features).  Semantics per SURVEY.md 8a "V":
+//   bounding box -> min_b / div_b -> voxel index (float multiply, floor) -> sort by index -> one output per occupied
+//   voxel in ascending index order = float32 centroid of x, y, z, intensity accumulated in sorted order.
+// PCL's std::sort is unstable; here ties are resolved by point index (a STABLE least-significant-digit radix sort on
+// the voxel index, 8 bits per pass, as many passes as the index range needs), which is the CANONICAL order of the oracle.
+#include <climits>
+#include <cfloat>
 #include "ctx.h"
-extern "C" int aloam_voxel_filter_impl(aloam_ctx* c, aloam_cloud_view in, float leaf, aloam_cloud_view* out);
-#include "voxel_impl.inc"
+
+namespace aloam {
+
+namespace {
+constexpr int VT = 256, VCH = 1024, VIT = VCH / VT;
+
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : (i ^ 0x7fffffff); }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : (i ^ 0x7fffffff)); }
+}  // namespace
+
+// mm6: ordered-int encoded [min x,y,z | max x,y,z], pre-set to +inf / -inf encodings
+__global__ void k_vox_bbox(const Pt4* __restrict__ pts, int n, int* __restrict__ mm6) {
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const Pt4 p = pts[i];
+    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm6[a], f2ord(lo[a])); atomicMax(&mm6[3 + a], f2ord(hi[a])); }
+  }
+}
+
+struct VoxParams { float inv; int min_b[3]; int div0, div01; };
+
+__global__ void k_vox_keys(const Pt4* __restrict__ pts, int n, VoxParams vp, unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Pt4 p = pts[i];
+  const int i0 = (int)(floorf(p.x * vp.inv) - (float)vp.min_b[0]);
+  const int i1 = (int)(floorf(p.y * vp.inv) - (float)vp.min_b[1]);
+  const int i2 = (int)(floorf(p.z * vp.inv) - (float)vp.min_b[2]);
+  keys[i] = (unsigned)(i0 + i1 * vp.div0 + i2 * vp.div01);
+  vals[i] = i;
+}
+
+__global__ void __launch_bounds__(VT) k_radix_hist(const unsigned* __restrict__ keys, int n, int shift, int* __restrict__ hist) {
+  __shared__ int s_h[256];
+  const int tid = threadIdx.x;
+  s_h[tid] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < VIT; ++it) {
+    const int i = blockIdx.x * VCH + it * VT + tid;
+    if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & 255u], 1);
+  }
+  __syncthreads();
+  hist[blockIdx.x * 256 + tid] = s_h[tid];
+}
+
+// one CTA, 1024 threads: thread (bin = t >> 2, quarter = t & 3) ; offsets are digit-major over all blocks
+__global__ void __launch_bounds__(1024) k_radix_scan(const int* __restrict__ hist, int nblocks, int* __restrict__ offsets) {
+  __shared__ int s_tot[256];
+  __shared__ int s_start[257];
+  const int t = threadIdx.x, bin = t >> 2, q = t & 3;
+  const int per = (nblocks + 3) / 4;
+  const int b0 = min(nblocks, q * per), b1 = min(nblocks, b0 + per);
+  int local = 0;
+  for (int b = b0; b < b1; ++b) local += hist[b * 256 + bin];
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 4; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d, 4); if (q >= d) incl += v; }
+  if (q == 3) s_tot[bin] = incl;
+  __syncthreads();
+  if (t < 32) {  // exclusive scan of 256 bin totals, 8 per lane
+    int v[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = s_tot[t * 8 + k]; sum += v[k]; }
+    int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (t >= d) inc += u; }
+    int run = inc - sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s_start[t * 8 + k] = run; run += v[k]; }
+  }
+  __syncthreads();
+  int running = s_start[bin] + (incl - local);
+  for (int b = b0; b < b1; ++b) { offsets[b * 256 + bin] = running; running += hist[b * 256 + bin]; }
+}
+
+__global__ void __launch_bounds__(VT) k_radix_scatter(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in, int n,
+                                                      int shift, const int* __restrict__ offsets, unsigned* __restrict__ keys_out,
+                                                      int* __restrict__ vals_out) {
+  __shared__ int s_cnt[VIT * (VT / 32)][256];   // [slot = it*8 + warp][digit] -> exclusive prefix over slots
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  for (int k = tid; k < VIT * (VT / 32) * 256; k += VT) (&s_cnt[0][0])[k] = 0;
+  __syncthreads();
+  int dig[VIT], rank[VIT];
+#pragma unroll
+  for (int it = 0; it < VIT; ++it) {
+    const int i = blockIdx.x * VCH + it * VT + tid;
+    const int d = i < n ? (int)((keys_in[i] >> shift) & 255u) : -1;
+    dig[it] = d;
+    const unsigned grp = __match_any_sync(0xffffffffu, d);
+    rank[it] = __popc(grp & ((1u << lane) - 1u));
+    if (d >= 0 && rank[it] == 0) s_cnt[it * (VT / 32) + w][d] = __popc(grp);
+  }
+  __syncthreads();
+  {
+    int run = offsets[blockIdx.x * 256 + tid];
+#pragma unroll
+    for (int k = 0; k < VIT * (VT / 32); ++k) { const int c = s_cnt[k][tid]; s_cnt[k][tid] = run; run += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < VIT; ++it) {
+    if (dig[it] < 0) continue;
+    const int i = blockIdx.x * VCH + it * VT + tid;
+    const int dst = s_cnt[it * (VT / 32) + w][dig[it]] + rank[it];
+    keys_out[dst] = keys_in[i];
+    vals_out[dst] = vals_in[i];
+  }
+}
+
+// number of voxel heads (first element of each run of equal keys) per block of VCH sorted elements
+__global__ void __launch_bounds__(VT) k_vox_heads(const unsigned* __restrict__ keys, int n, int* __restrict__ block_heads) {
+  __shared__ int s_c;
+  if (threadIdx.x == 0) s_c = 0;
+  __syncthreads();
+  int c = 0;
+#pragma unroll
+  for (int it = 0; it < VIT; ++it) {
+    const int i = blockIdx.x * VCH + it * VT + threadIdx.x;
+    if (i < n && (i == 0 || keys[i] != keys[i - 1])) ++c;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_c, c);
+  __syncthreads();
+  if (threadIdx.x == 0) block_heads[blockIdx.x] = s_c;
+}
+
+__global__ void __launch_bounds__(1024) k_vox_blockscan(int* __restrict__ block_heads, int nblocks, int* __restrict__ total) {
+  __shared__ int s_w[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int per = (nblocks + 1023) / 1024;
+  int sum = 0;
+  for (int k = 0; k < per; ++k) { const int b = t * per + k; if (b < nblocks) sum += block_heads[b]; }
+  int incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int x = s_w[lane], inc = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+    s_w[lane] = inc - x;
+    if (lane == 31) *total = inc;
+  }
+  __syncthreads();
+  int run = s_w[w] + incl - sum;
+  for (int k = 0; k < per; ++k) { const int b = t * per + k; if (b < nblocks) { const int c = block_heads[b]; block_heads[b] = run; run += c; } }
+}
+
+// every head sums its run in sorted order (float, like pcl::CentroidPoint) and writes voxel number (block offset + local rank)
+__global__ void __launch_bounds__(VT) k_vox_emit(const Pt4* __restrict__ pts, const unsigned* __restrict__ keys, const int* __restrict__ vals,
+                                                 int n, const int* __restrict__ block_offsets, Pt4* __restrict__ out) {
+  __shared__ int s_w[VT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int base = blockIdx.x * VCH + tid * VIT;   // this thread owns VIT consecutive sorted slots
+  int heads = 0;
+  bool is_head[VIT];
+#pragma unroll
+  for (int k = 0; k < VIT; ++k) {
+    const int i = base + k;
+    is_head[k] = i < n && (i == 0 || keys[i] != keys[i - 1]);
+    heads += is_head[k] ? 1 : 0;
+  }
+  int incl = heads;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int v = 0; v < w; ++v) wbase += s_w[v];
+  int slot = block_offsets[blockIdx.x] + wbase + incl - heads;
+#pragma unroll
+  for (int k = 0; k < VIT; ++k) {
+    if (!is_head[k]) continue;
+    const int i = base + k;
+    const unsigned key = keys[i];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int cnt = 0;
+    for (int j = i; j < n && keys[j] == key; ++j) {
+      const Pt4 p = pts[vals[j]];
+      sx += p.x; sy += p.y; sz += p.z; si += p.i;
+      ++cnt;
+    }
+    const float nf = (float)cnt;
+    Pt4 o; o.x = sx / nf; o.y = sy / nf; o.z = sz / nf; o.i = si / nf;
+    out[slot++] = o;
+  }
+}
+
+}  // namespace aloam
+
+using namespace aloam;
+
+extern "C" int aloam_voxel_filter_impl(aloam_ctx* c, aloam_cloud_view in, float leaf, aloam_cloud_view* out) {
+  if (!c || !out || !(leaf > 0.f)) return ALOAM_ERR_INVALID_ARG;
+  int rc = check_view(in); if (rc) return rc;
+  if (in.n > c->max_points) return ALOAM_ERR_CAPACITY;
+  out->data = reinterpret_cast<const float*>(c->h_out[4]); out->n = 0; out->stride_floats = 4;
+  if (in.n == 0) return ALOAM_OK;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  const int n = in.n;
+  if (!c->d_vox_keys[0]) {
+    const size_t mp = (size_t)c->max_points;
+    const int nb_max = (c->max_points + VCH - 1) / VCH;
+    CUDA_CHECK_RET(cudaMalloc((void**)&c->d_vox_keys[0], mp * 4)); CUDA_CHECK_RET(cudaMalloc((void**)&c->d_vox_keys[1], mp * 4));
+    CUDA_CHECK_RET(cudaMalloc((void**)&c->d_vox_vals[0], mp * 4)); CUDA_CHECK_RET(cudaMalloc((void**)&c->d_vox_vals[1], mp * 4));
+    CUDA_CHECK_RET(cudaMalloc((void**)&c->d_vox_hist, (size_t)nb_max * 256 * 4)); CUDA_CHECK_RET(cudaMalloc((void**)&c->d_vox_offs, (size_t)nb_max * 256 * 4));
+    CUDA_CHECK_RET(cudaMalloc((void**)&c->d_vox_misc, 64 * 4 + (size_t)nb_max * 4));
+  }
+  Pt4* d_in = c->d_query;        // staging buffers that already exist in the context
+  Pt4* d_out = c->d_full;
+  rc = upload_cloud(c, in, d_in, c->max_points); if (rc) return rc;
+  int* mm6 = c->d_vox_misc; int* d_total = c->d_vox_misc + 8; int* block_heads = c->d_vox_misc + 64;
+  const int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+  std::memcpy(c->h_ints + 32, init, sizeof(init));
+  CUDA_CHECK_RET(cudaMemcpyAsync(mm6, c->h_ints + 32, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, KID_VOXEL, k_vox_bbox, std::min((n + 255) / 256, 592), 256, 0, d_in, n, mm6);
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints + 40, mm6, 24, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  // host replica of PCL's index-range computation (needs the box; also decides the number of radix passes)
+  float mn[3], mx[3];
+  for (int a = 0; a < 3; ++a) {
+    int lo = c->h_ints[40 + a], hi = c->h_ints[43 + a];
+    lo = lo >= 0 ? lo : (lo ^ 0x7fffffff); hi = hi >= 0 ? hi : (hi ^ 0x7fffffff);
+    std::memcpy(&mn[a], &lo, 4); std::memcpy(&mx[a], &hi, 4);
+  }
+  const float inv = 1.0f / leaf;
+  long long dxyz[3]; int min_b[3], div_b[3];
+  for (int a = 0; a < 3; ++a) {
+    dxyz[a] = (long long)((mx[a] - mn[a]) * inv) + 1;
+    min_b[a] = (int)std::floor(mn[a] * inv);
+    div_b[a] = (int)std::floor(mx[a] * inv) - min_b[a] + 1;
+  }
+  const int nblk = (n + VCH - 1) / VCH;
+  if (dxyz[0] * dxyz[1] * dxyz[2] > (long long)INT_MAX) {   // "leaf size is too small": PCL returns the input unchanged
+    CUDA_CHECK_RET(cudaMemcpyAsync(c->h_out[4], d_in, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+    out->n = n;
+    return ALOAM_OK;
+  }
+  VoxParams vp; vp.inv = inv; vp.min_b[0] = min_b[0]; vp.min_b[1] = min_b[1]; vp.min_b[2] = min_b[2];
+  vp.div0 = div_b[0]; vp.div01 = div_b[0] * div_b[1];
+  LAUNCH(c, KID_VOXEL, k_vox_keys, (n + 255) / 256, 256, 0, d_in, n, vp, c->d_vox_keys[0], c->d_vox_vals[0]);
+  const unsigned long long cells = (unsigned long long)div_b[0] * (unsigned long long)div_b[1] * (unsigned long long)div_b[2];
+  int bits = 1; while (bits < 32 && (1ull << bits) < cells) ++bits;
+  int cur = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    LAUNCH(c, KID_VOXEL, k_radix_hist, nblk, VT, 0, c->d_vox_keys[cur], n, shift, c->d_vox_hist);
+    LAUNCH(c, KID_VOXEL, k_radix_scan, 1, 1024, 0, c->d_vox_hist, nblk, c->d_vox_offs);
+    LAUNCH(c, KID_VOXEL, k_radix_scatter, nblk, VT, 0, c->d_vox_keys[cur], c->d_vox_vals[cur], n, shift, c->d_vox_offs, c->d_vox_keys[cur ^ 1],
+           c->d_vox_vals[cur ^ 1]);
+    cur ^= 1;
+  }
+  LAUNCH(c, KID_VOXEL, k_vox_heads, nblk, VT, 0, c->d_vox_keys[cur], n, block_heads);
+  LAUNCH(c, KID_VOXEL, k_vox_blockscan, 1, 1024, 0, block_heads, nblk, d_total);
+  LAUNCH(c, KID_VOXEL, k_vox_emit, nblk, VT, 0, d_in, c->d_vox_keys[cur], c->d_vox_vals[cur], n, block_heads, d_out);
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints + 48, d_total, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK_RET(cudaGetLastError());
+  const int m = c->h_ints[48];
+  if (m > 0) {
+    CUDA_CHECK_RET(cudaMemcpyAsync(c->h_out[4], d_out, (size_t)m * 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  }
+  prof_collect(c);
+  out->n = m;
+  return ALOAM_OK;
+}

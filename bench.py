@@ -140,6 +140,116 @@ def cpu_pipeline_two_stage(orc, synth, scans, warmup):
     return time.perf_counter() - t_start
 
 
+def _rot(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def bench_mapping(args, synth, rank, world, local_rank):
+    """BASELINE configs[2]/[3]: HDL-64 scan-to-map against a synthetic voxel map of 1M points per GPU (200k corner +
+    800k surf), 2 outer x <= 4 inner LM iterations (<= 10 normal-equation builds).  A step = index build over the
+    resident submap (what replaces the reference's per-frame kd-tree builds) + 2 x (5-NN + fits) + LM.  With
+    --gpus N the map is N x 1M points split into x-slabs over the ranks (one ncclAllReduce of the 6x6/6x1 system per
+    evaluation); every rank holds the same stacks.  `e2e` additionally uploads the shard from host memory each step."""
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("a-loam_b200")
+    shard = importlib.import_module("a-loam_b200.shard")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K, W = args.steps, max(args.warmup, 3)
+    total_pts = args.map_points or 1_000_000 * world
+    ctx = pkg.Aloam(n_scans=64, device=local_rank, max_points=200000, max_map_points=int(total_pts * 1.05 / world) + 200000)
+    # base map: features of 12 scans at their true poses (product's own extraction), voxel-filtered at 0.4 / 0.8
+    corner, surf = [], []
+    for k in list(range(0, 24, 2)):
+        f = ctx.extract_features(synth.scan(SENSOR, k))
+        qk, tk = synth.pose(k); R = _rot(qk)
+        for src, dst in [(f["less_sharp"], corner), (f["less_flat"], surf)]:
+            w = src.copy(); w[:, :3] = (src[:, :3].astype(np.float64) @ R.T + tk).astype(np.float32); dst.append(w)
+    cbase = synth.voxel_downsample(np.concatenate(corner), 0.4)
+    sbase = synth.voxel_downsample(np.concatenate(surf), 0.8)
+    rng = np.random.default_rng(20240901 + 3)
+
+    def tile(base, target):
+        """replicate the base map with jitter on a lattice of offsets (parallel streets / stacked levels) to `target` points"""
+        out = [base]
+        n = len(base); k = 0
+        while n < target:
+            k += 1
+            off = np.array([0.0, 45.0 * ((k + 1) // 2) * (1 if k % 2 else -1), 0.0], np.float32)
+            c = base.copy(); c[:, :3] += off + rng.normal(0, 0.02, (len(base), 3)).astype(np.float32)
+            out.append(c); n += len(c)
+        return np.ascontiguousarray(np.concatenate(out)[:target])
+    cmap = tile(cbase, total_pts // 5)
+    smap = tile(sbase, total_pts - total_pts // 5)
+    my_c, my_s = shard.shard_cloud(cmap, rank, world), shard.shard_cloud(smap, rank, world)
+    stacks = []
+    for k in range(1, 1 + W + K):
+        f = ctx.extract_features(synth.scan(SENSOR, (2 * k + 1) % 24))
+        stacks.append((ctx.voxel_filter(f["less_sharp"], 0.4), ctx.voxel_filter(f["less_flat"], 0.8), (2 * k + 1) % 24))
+    if world > 1:
+        idb = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idb = torch.tensor(list(pkg.Aloam.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idb, 0)
+        ctx.comm_init(rank, world, bytes(idb.cpu().tolist()))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def x0_of(k):
+        q, t = synth.pose(k)
+        return np.concatenate([q, t + np.array([0.05, -0.04, 0.02])])
+
+    def run(timed, profile=False):
+        ctx.profile_enable(profile)
+        for i in range(W):
+            ctx.map_upload(my_c, my_s); ctx.mapping_register(stacks[i][0], stacks[i][1], x0_of(stacks[i][2]))
+        barrier(); l0 = ctx.launch_count(); t0 = time.perf_counter(); err = 0.0
+        for i in range(W, W + timed):
+            ctx.map_upload(my_c, my_s)
+            x, st = ctx.mapping_register(stacks[i][0], stacks[i][1], x0_of(stacks[i][2]))
+            err = max(err, float(np.abs(x[4:] - synth.pose(stacks[i][2])[1]).max()))
+        torch.cuda.synchronize(); t1 = time.perf_counter(); barrier()
+        return t1 - t0, ctx.launch_count() - l0, err, st
+    sampler = ClockSampler(local_rank); sampler.start()
+    secs, launches, err, st = run(K)
+    clocks = sampler.stop()
+    run(K, profile=True)
+    prof = ctx.profile_read()
+    if world > 1:
+        tt = torch.tensor([secs], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); secs = float(tt[0])
+    if rank == 0:
+        per_kernel = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / K, "ms_per_step": v[0] / K} for k, v in prof.items()}
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        m_loc = len(my_c) + len(my_s)
+        grid_ms = per_kernel.get("k_map_grid", {}).get("ms_per_step", 0.0)
+        grid_bytes = 36 * m_loc    # 16 B read + 16 B cell-sorted copy + 4 B slot (SURVEY.md 8d "K0 index build")
+        line = {"metric": "scans/sec", "value": K / secs, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * secs / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+                "config": {"workload": "HDL-64 scan-to-map, %d-pt synthetic voxel map (%d corner + %d surf), %s, 2 outer x <=4 inner LM iterations; per step the"
+                                       " shard is uploaded from host and re-indexed (the reference rebuilds both kd-trees per frame)" %
+                                       (total_pts, len(cmap), len(smap), "1 GPU" if world == 1 else "x-slab shards + halo over %d GPUs, ncclAllReduce(32 f64) per evaluation" % world),
+                           "map_points_this_rank": m_loc, "stack_points": int(len(stacks[W][0]) + len(stacks[W][1])), "l2": "map shard %.0f MB re-uploaded each step" % (16 * m_loc / 1e6)},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": K / secs, "unit": "scans/s", "h2d_bytes_per_step": 16 * m_loc + 16 * int(len(stacks[W][0]) + len(stacks[W][1])), "d2h_bytes_per_step": 56 + 4 * 560},
+                "roofline": {"bound": "hbm", "kernel": "k_map_grid (K0: clear + insert + alloc + fill)", "achieved": (grid_bytes / (grid_ms * 1e-3) / 1e9) if grid_ms else 0.0,
+                             "peak": peak, "unit": "GB/s", "frac": (grid_bytes / (grid_ms * 1e-3) / 1e9 / peak) if grid_ms else 0.0, "traffic": None,
+                             "algorithmic_bytes_per_launch": grid_bytes, "per_kernel": per_kernel},
+                "pose_error_vs_truth_max_m": err, "last_stats": st}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,6 +257,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="odometry", choices=["odometry", "mapping"],
+                    help="odometry = BASELINE configs[1] (the contract line); mapping = configs[2] (1M-pt map) / configs[3] (8M-pt map sharded over --gpus)")
+    ap.add_argument("--map-points", type=int, default=0, help="mapping workload: total map points (default 1M per GPU)")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -155,6 +268,8 @@ def main():
     n_scans_needed = 1 + W + K
 
     synth = importlib.import_module("a-loam_b200.synth")
+    if args.workload == "mapping":
+        return bench_mapping(args, synth, rank, world, local_rank)
     config = {"workload": "HDL-64 synthetic 64x2000 scan-to-scan odometry (BASELINE.json configs[1]): feature extraction + "
                           "2 x (k-NN association + <=4-iter LM) + index build, consecutive scans of one trajectory",
               "sensor": SENSOR, "azimuth_steps": 2000, "beams": 64, "outer_iters": 2, "inner_iters": 4,

@@ -140,6 +140,20 @@ int aloam_solve(aloam_ctx* ctx, const double* blocks, int n_blocks, double x[7],
 /* last extract_features call: per-point curvature (scanRegistration.cpp:262), label (:303,309,355), ring start/end */
 int aloam_debug_features(aloam_ctx* ctx, float* curvature, int* label, int* scan_start, int* scan_end);
 
+/* association + fits of laserMapping.cpp:577-687 at pose x (tests): fits = (n_corner + n_surf) x 14 doubles
+ * [query, type (-1 rejected, 0 edge, 2 plane-norm), p0(3), p1(3), d, nn(5)], corner rows first */
+int aloam_mapping_associate(aloam_ctx* ctx, aloam_cloud_view corner_stack, aloam_cloud_view surf_stack,
+                            const double x[7], double* fits);
+
+/* ---- multi-GPU scan-to-map (one process per GPU).  Rank 0 creates the 128-byte id and ships it to the others;
+ * after aloam_comm_init each rank uploads only ITS shard of the submap (x-slabs of aloam_shard_slab_cells() cells of
+ * 1.00001 m, owner = slab mod world, plus one cell of halo) and aloam_mapping_register fits only the stack points
+ * whose cell the rank owns; the ranks meet in one ncclAllReduce of the 6x6 / 6x1 normal equations per evaluation and
+ * return the identical pose. */
+int aloam_comm_unique_id(char out128[128]);
+int aloam_comm_init(aloam_ctx* ctx, int rank, int world, const char id128[128]);
+int aloam_shard_slab_cells(void);
+
 /* ---- measurement hooks (bench.py): per-kernel CUDA-event timing on the ctx stream, and a launch counter */
 int aloam_profile_enable(aloam_ctx* ctx, int on);
 int aloam_profile_read(aloam_ctx* ctx, double* ms_sum, long long* count, const char** names, int capacity);

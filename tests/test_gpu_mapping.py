@@ -92,3 +92,21 @@ def test_thin_map_is_skipped(aloam, scene):
     x, st = c.mapping_register(cs, ss, x0)
     assert np.array_equal(x, x0) and st["flags"] & aloam.FLAG_MAP_TOO_THIN   # laserMapping.cpp:554,730-733
     c.close()
+
+
+@pytest.mark.parametrize("leaf", [0.2, 0.4, 0.8])
+def test_voxel_filter_matches_pcl_restatement(ctx, orc, synth, scans, leaf):
+    """aloam_voxel_filter == pcl::VoxelGrid restatement (canonical tie order), bit for bit (laserMapping.cpp:543-549)"""
+    ns, az, mr = synth.SENSORS["HDL-64"][:3]
+    f = orc.Features(scans("HDL-64", 1), ns, mr)
+    for cloud in (f.less_sharp, f.less_flat, f.full[:50000]):
+        ref = orc.voxel_grid(cloud, leaf, orc.SORT_CANONICAL)
+        got = ctx.voxel_filter(cloud, leaf)
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref)
+    assert ctx.voxel_filter(np.zeros((0, 4), np.float32), leaf).shape == (0, 4)
+
+
+def test_voxel_filter_overflow_returns_input(ctx):
+    cloud = np.array([[0, 0, 0, 1], [3000, 3000, 3000, 2], [1, 1, 1, 3]], np.float32)
+    assert np.array_equal(ctx.voxel_filter(cloud, 0.2), cloud)
