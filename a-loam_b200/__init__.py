@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "aloam_odometry_set_last", "aloam_odometry_register", "aloam_map_upload", "aloam_mapping_register",
     "aloam_voxel_filter", "aloam_scan_to_pose", "aloam_scan_to_pose_device", "aloam_reset_odometry", "aloam_knn",
     "aloam_odometry_associate", "aloam_normal_equations", "aloam_solve", "aloam_debug_features", "aloam_mapping_associate",
-    "aloam_comm_unique_id", "aloam_comm_init", "aloam_profile_enable", "aloam_profile_read", "aloam_launch_count",
+    "aloam_comm_unique_id", "aloam_comm_init", "aloam_scan_stream", "aloam_profile_enable", "aloam_profile_read", "aloam_launch_count",
 ]
 
 
@@ -82,6 +82,7 @@ def lib():
         L.aloam_scan_to_pose.argtypes = [C.c_void_p, cv, dp, dp, C.POINTER(Stats)]
         L.aloam_scan_to_pose_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp, dp, C.POINTER(Stats)]
         L.aloam_reset_odometry.argtypes = [C.c_void_p]
+        L.aloam_scan_stream.argtypes = [C.c_void_p, C.POINTER(cv), C.c_int, C.c_int, dp, C.POINTER(Stats)]
         L.aloam_knn.argtypes = [C.c_void_p, C.c_int, cv, C.c_int, ip, fp]
         L.aloam_odometry_associate.argtypes = [C.c_void_p, cv, cv, dp, dp, ip, ip]
         L.aloam_normal_equations.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp, dp]
@@ -257,6 +258,17 @@ class Aloam:
         st = Stats()
         _check(lib().aloam_scan_to_pose_device(self._h, C.c_void_p(dev_ptr), n, _dp(q), _dp(t), C.byref(st)))
         return q, t, st
+
+    def scan_stream(self, ptrs, counts, device_resident, stride=4):
+        """pipelined scan_to_pose over a sequence: ptrs = host (or device) addresses of the raw scans; returns (n, 7) poses"""
+        n = len(ptrs)
+        views = (CloudView * n)()
+        for i in range(n):
+            views[i] = CloudView(C.cast(C.c_void_p(int(ptrs[i])), C.POINTER(C.c_float)), int(counts[i]), stride)
+        poses = np.zeros((n, 7))
+        st = Stats()
+        _check(lib().aloam_scan_stream(self._h, views, n, int(device_resident), _dp(poses), C.byref(st)))
+        return poses, st
 
     def reset_odometry(self):
         _check(lib().aloam_reset_odometry(self._h))

@@ -51,6 +51,14 @@ int aloam_destroy(aloam_ctx* c) {
   if (!c) return ALOAM_OK;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->s_ext) { cudaStreamSynchronize(c->s_ext); cudaStreamDestroy(c->s_ext); }
+  if (c->s_h2d) { cudaStreamSynchronize(c->s_h2d); cudaStreamDestroy(c->s_h2d); }
+  for (cudaEvent_t e : c->ev_feat) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_odo) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_h2d) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_rawfree) if (e) cudaEventDestroy(e);
+  if (c->d_raw2) cudaFree(c->d_raw2);
+  if (c->h_poses) cudaFreeHost(c->h_poses);
   void* dev[] = {c->d_raw, c->d_ring, c->d_hist, c->d_offsets, c->d_ring_start, c->d_scan_start, c->d_scan_end, c->d_sc,
                  c->d_full, c->d_curv, c->d_label, c->st_sharp, c->st_less_sharp, c->st_flat, c->st_less_flat, c->st_counts,
                  c->d_blocks, c->d_corr, c->d_pose, c->d_world, c->d_out28, c->d_packed, c->d_summary, c->d_err, c->d_query,
@@ -110,7 +118,13 @@ int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
   TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   TRY(cudaEventCreate(&c->ev0)); TRY(cudaEventCreate(&c->ev1));
   for (cudaEvent_t& e : c->prof_ev) TRY(cudaEventCreate(&e));
-  TRY(dalloc(&c->d_raw, mp * 8));
+  TRY(dalloc(&c->d_raw, mp * 8)); TRY(dalloc(&c->d_raw2, mp * 8));
+  TRY(cudaStreamCreateWithFlags(&c->s_ext, cudaStreamNonBlocking)); TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  for (cudaEvent_t& e : c->ev_feat) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (cudaEvent_t& e : c->ev_odo) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (cudaEvent_t& e : c->ev_h2d) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (cudaEvent_t& e : c->ev_rawfree) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  TRY(halloc(&c->h_poses, (size_t)kMaxStreamScans * 7));
   TRY(dalloc(&c->d_ring, mp));
   TRY(dalloc(&c->d_hist, (size_t)c->nblocks_max * 64)); TRY(dalloc(&c->d_offsets, (size_t)c->nblocks_max * 64));
   TRY(dalloc(&c->d_ring_start, 72)); TRY(dalloc(&c->d_scan_start, 64)); TRY(dalloc(&c->d_scan_end, 64));
@@ -287,8 +301,8 @@ int aloam_odometry_associate(aloam_ctx* c, aloam_cloud_view sharp, aloam_cloud_v
 
 // ------------------------------------------------------------------------------------------------ fused pipeline
 static int scan_to_pose_impl(aloam_ctx* c, const float* d_raw, int n, int stride, double q_w[4], double t_w[3], aloam_stats* stats) {
-  FeatBuf& cur = c->feat[c->frame & 1];
-  FeatBuf& last = c->feat[(c->frame & 1) ^ 1];
+  FeatBuf& cur = c->feat[c->frame % 3];
+  FeatBuf& last = c->feat[(c->frame + 2) % 3];
   const int slot = c->parity;
   int rc = run_features(c, d_raw, n, stride, cur);
   if (rc) return rc;
@@ -318,7 +332,7 @@ static int scan_to_pose_impl(aloam_ctx* c, const float* d_raw, int n, int stride
   float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   if (c->frame == 0) { if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->flags = flags; stats->ms_total = ms; } }
   else fill_stats(c, stats, c->cfg.outer_iters, flags, ms);
-  c->cur = c->frame & 1;
+  c->cur = c->frame % 3;
   c->frame++;
   return ALOAM_OK;
 }
@@ -341,6 +355,74 @@ int aloam_scan_to_pose_device(aloam_ctx* c, const float* d_raw, int n, double q_
   CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
   CUDA_CHECK_RET(cudaEventRecord(c->ev0, c->stream));
   return scan_to_pose_impl(c, d_raw, n, 4, q_w, t_w, stats);
+}
+
+// Pipelined form of aloam_scan_to_pose for a sequence of scans: extraction + index build of scan k+1 (stream s_ext)
+// run concurrently with association + LM of scan k (main stream) and the host->device copy of scan k+2 (s_h2d) -- the
+// same three-stage overlap the reference gets from its three ROS processes.  Results are identical to calling
+// aloam_scan_to_pose once per scan.  poses: n x 7 doubles (q_w xyzw, t_w).
+int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, int device_resident, double* poses, aloam_stats* stats_last) {
+  if (!c || !raws || !poses || n_scans < 1 || n_scans > kMaxStreamScans) return ALOAM_ERR_INVALID_ARG;
+  for (int k = 0; k < n_scans; ++k) {
+    int rc = check_view(raws[k]); if (rc) return rc;
+    if (raws[k].n == 0) return ALOAM_ERR_EMPTY_CLOUD;
+    if (raws[k].n > c->max_points) return ALOAM_ERR_CAPACITY;
+    if (device_resident && raws[k].stride_floats != 4) return ALOAM_ERR_INVALID_ARG;
+  }
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  cudaStream_t s_main = c->stream;
+  float* rawbuf[2] = {c->d_raw, c->d_raw2};
+  CUDA_CHECK_RET(cudaEventRecord(c->ev0, s_main));
+  int first_slot = -1;
+  for (int k = 0; k < n_scans; ++k) {
+    const int f = c->frame;                 // global frame number of this scan
+    FeatBuf& cur = c->feat[f % 3];
+    FeatBuf& last = c->feat[(f + 2) % 3];
+    const float* d_raw;
+    if (device_resident) {
+      d_raw = raws[k].data;
+    } else {
+      const int b = k & 1;
+      if (k >= 2) CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_h2d, c->ev_rawfree[b], 0));   // extraction of scan k-2 has consumed the buffer
+      CUDA_CHECK_RET(cudaMemcpyAsync(rawbuf[b], raws[k].data, (size_t)raws[k].n * raws[k].stride_floats * 4, cudaMemcpyHostToDevice, c->s_h2d));
+      CUDA_CHECK_RET(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
+      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_h2d[b], 0));
+      d_raw = rawbuf[b];
+    }
+    // ---- extraction + index build on s_ext.  cur (= slot of frame f-3) was last read by the odometry of frame f-2 (as "last")
+    if (k >= 2) CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_odo[(f + 1) % 3], 0));  // (f-2) % 3
+    else CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev0, 0));                         // everything issued before this call
+    c->stream = c->s_ext;
+    const int slot = c->parity;
+    if (first_slot < 0) first_slot = slot;
+    int rc = run_features(c, d_raw, raws[k].n, device_resident ? 4 : raws[k].stride_floats, cur);
+    if (!device_resident) cudaEventRecord(c->ev_rawfree[k & 1], c->s_ext);
+    run_grid_build(c, cur, 64 * kMaxLessSharpPerRing, std::min(raws[k].n, c->max_points));
+    cudaEventRecord(c->ev_feat[f % 3], c->s_ext);
+    c->stream = s_main;
+    if (rc) return rc;
+    // ---- association + LM on the main stream
+    CUDA_CHECK_RET(cudaStreamWaitEvent(s_main, c->ev_feat[f % 3], 0));
+    if (f > 0) run_register(c, cur, last, kFusedSharpSlots, kFusedFlatSlots, true, nullptr);
+    CUDA_CHECK_RET(cudaMemcpyAsync(c->h_poses + (size_t)k * 7, c->d_world, 56, cudaMemcpyDeviceToHost, s_main));
+    CUDA_CHECK_RET(cudaEventRecord(c->ev_odo[f % 3], s_main));
+    c->cur = f % 3;
+    c->frame++;
+  }
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, s_main));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_sc, c->d_sc, 2 * sizeof(ScanScalars), cudaMemcpyDeviceToHost, s_main));
+  CUDA_CHECK_RET(cudaEventRecord(c->ev1, s_main));
+  CUDA_CHECK_RET(cudaStreamSynchronize(s_main));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->s_ext));
+  CUDA_CHECK_RET(cudaGetLastError());
+  prof_collect(c);
+  for (int b = 0; b < 2; ++b)
+    if (c->h_sc[b].error) { int e = c->h_sc[b].error; cudaMemset(&(c->d_sc + b)->error, 0, 4); return e; }
+  std::memcpy(poses, c->h_poses, (size_t)n_scans * 56);
+  float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  if (c->frame <= 1) { if (stats_last) { std::memset(stats_last, 0, sizeof(*stats_last)); stats_last->flags = ALOAM_FLAG_INITIALISED_ONLY; stats_last->ms_total = ms; } }
+  else fill_stats(c, stats_last, c->cfg.outer_iters, 0, ms);
+  return ALOAM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ fine-grained

@@ -16,7 +16,8 @@ namespace {
 constexpr int kMaxSharpPerRing = 12, kMaxLessSharpPerRing = 120, kMaxFlatPerRing = 24;
 constexpr int kFusedSharpSlots = 64 * kMaxSharpPerRing;  // 768
 constexpr int kFusedFlatSlots = 64 * kMaxFlatPerRing;    // 1536
-constexpr int kMaxQueries = 16384;                       // API-path capacity for sharp / flat query clouds
+constexpr int kMaxQueries = 16384;
+constexpr int kMaxStreamScans = 4096;                   // scans per aloam_scan_stream call                       // API-path capacity for sharp / flat query clouds
 
 struct FeatBuf {
   Pt4 *sharp = nullptr, *less_sharp = nullptr, *flat = nullptr, *less_flat = nullptr;
@@ -42,7 +43,7 @@ struct aloam_ctx {
   int8_t* d_label = nullptr;
   Pt4 *st_sharp = nullptr, *st_less_sharp = nullptr, *st_flat = nullptr, *st_less_flat = nullptr;
   int* st_counts = nullptr;
-  FeatBuf feat[2];
+  FeatBuf feat[3];   // triple-buffered feature sets (pipelined stream: extraction k+1 || odometry k needs k-1, k, k+1 alive)
   // odometry
   BlockRec* d_blocks = nullptr;
   int* d_corr = nullptr;
@@ -68,6 +69,12 @@ struct aloam_ctx {
   unsigned* d_vox_keys[2] = {nullptr, nullptr};
   int* d_vox_vals[2] = {nullptr, nullptr};
   int *d_vox_hist = nullptr, *d_vox_offs = nullptr, *d_vox_misc = nullptr;
+  // pipelined scan stream (aloam_scan_stream): extraction + index build on s_ext, association + LM on `stream`,
+  // host->device copies of the raw scans on s_h2d, all chained by events
+  cudaStream_t s_ext = nullptr, s_h2d = nullptr;
+  cudaEvent_t ev_feat[3] = {}, ev_odo[3] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {};
+  float* d_raw2 = nullptr;       // second raw-scan staging buffer
+  double* h_poses = nullptr;     // pinned [kMaxStreamScans][7]
   // pinned host mirrors
   Pt4* h_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int* h_ints = nullptr;        // scratch ints (counts etc.)

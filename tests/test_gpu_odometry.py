@@ -120,3 +120,23 @@ def test_fused_pipeline_poses(aloam, orc, synth, scans, sensor, frames):
         assert np.abs(gt - tw).max() < 1e-4 and rot_angle(gq, qw) < 1e-4, (k, gt, tw)
         assert np.abs(gt - tw).max() < 1e-7, (k, gt - tw)
     c.close()
+
+
+def test_scan_stream_equals_per_scan_calls(aloam, synth, scans):
+    """the 3-stream pipelined call returns exactly the poses of one aloam_scan_to_pose call per scan (host and device input)"""
+    import torch
+    raws = [scans("HDL-64", k) for k in range(7)]
+    a = aloam.Aloam(n_scans=64, max_points=140000)
+    ref = [np.concatenate(a.scan_to_pose(r)[:2]) for r in raws]
+    n = max(len(r) for r in raws)
+    host = torch.zeros((len(raws), n, 4), dtype=torch.float32).pin_memory()
+    for i, r in enumerate(raws):
+        host[i, :len(r)] = torch.from_numpy(r)
+    dev = host.cuda()
+    for buf, devres in [(host, False), (dev, True)]:
+        a.reset_odometry()
+        p1, _ = a.scan_stream([buf[i].data_ptr() for i in range(3)], [len(r) for r in raws[:3]], devres)     # split across two calls
+        p2, _ = a.scan_stream([buf[i].data_ptr() for i in range(3, 7)], [len(r) for r in raws[3:]], devres)
+        got = np.concatenate([p1, p2])
+        assert np.array_equal(got, np.array(ref))
+    a.close()
