@@ -243,14 +243,39 @@ def bench_mapping(args, synth, rank, world, local_rank):
                              "peak": peak, "unit": "GB/s", "frac": (grid_bytes / (grid_ms * 1e-3) / 1e9 / peak) if grid_ms else 0.0, "traffic": None,
                              "algorithmic_bytes_per_launch": grid_bytes, "per_kernel": per_kernel},
                 "pose_error_vs_truth_max_m": err, "last_stats": st}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+class _QuietStdout:
+    """Everything native libraries print on fd 1 while the benchmark runs (NCCL's version banner, ...) goes to stderr, so
+    that stdout carries exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+
+
 def main():
+    os.dup2(2, 1)   # from here on fd 1 is stderr; the JSON line is written to the saved descriptor by emit()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=64)
@@ -290,7 +315,7 @@ def main():
                                            "Ceres+PCL path, g++ -O3 no -march), extraction and odometry as two pipelined "
                                            "single-threaded stages like the reference's two ROS nodes" % (K, W)},
                 "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -437,7 +462,7 @@ def main():
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "pose_check": {"t_w_device_vs_host_path_maxabs": float(np.abs(pose_dev[1] - pose_e2e[1]).max()),
                                "t_w_stream_vs_sync_maxabs": float(np.abs(pose_dev[1] - pose_sync[1]).max())}}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
