@@ -443,21 +443,20 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
 
   if (tid < 7) s_x[tid] = x7[tid];
   __syncthreads();
-  cluster_evaluate(cluster, blocks, n, s_x, prm.huber_a, s_part, s_cta, s_tot, pass);
-
-  if (mode == 1) {
-    if (cluster.block_rank() == 0 && tid < 28) out28[tid] = s_tot[tid];
-    cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
-    return;
-  }
-  // thread 0 of EVERY CTA takes the same decision from the same totals (no broadcast needed)
-  if (tid == 0) tr_start(T, s_x, s_tot, prm, summary, writer);
-  __syncthreads();
-  while (T.go) {
-    cluster_evaluate(cluster, blocks, n, T.xc, prm.huber_a, s_part, s_cta, s_tot, pass);
-    if (tid == 0) tr_after_eval(T, s_tot, prm, summary, writer);
+  // one evaluation site (the evaluation body is large; duplicating it costs instruction-cache misses)
+  bool first = true;
+  do {
+    cluster_evaluate(cluster, blocks, n, first ? s_x : T.xc, prm.huber_a, s_part, s_cta, s_tot, pass);
+    if (first && mode == 1) {
+      if (cluster.block_rank() == 0 && tid < 28) out28[tid] = s_tot[tid];
+      cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
+      return;
+    }
+    // thread 0 of EVERY CTA takes the same decision from the same totals (no broadcast needed)
+    if (tid == 0) { if (first) tr_start(T, s_x, s_tot, prm, summary, writer); else tr_after_eval(T, s_tot, prm, summary, writer); }
+    first = false;
     __syncthreads();
-  }
+  } while (T.go);
   if (writer) {
     tr_finish(T, x7, summary);
     summary->cyc_total = clock64() - clk0;
