@@ -53,6 +53,11 @@ int aloam_destroy(aloam_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->s_ext) { cudaStreamSynchronize(c->s_ext); cudaStreamDestroy(c->s_ext); }
   if (c->s_h2d) { cudaStreamSynchronize(c->s_h2d); cudaStreamDestroy(c->s_h2d); }
+  if (c->s_exa) { cudaStreamSynchronize(c->s_exa); cudaStreamDestroy(c->s_exa); }
+  for (cudaEvent_t e : c->ev_a) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_b) if (e) cudaEventDestroy(e);
+  if (c->d_full2) cudaFree(c->d_full2);
+  if (c->d_ring_start2) cudaFree(c->d_ring_start2);
   for (cudaEvent_t e : c->ev_feat) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_odo) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_h2d) if (e) cudaEventDestroy(e);
@@ -120,6 +125,10 @@ int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
   for (cudaEvent_t& e : c->prof_ev) TRY(cudaEventCreate(&e));
   TRY(dalloc(&c->d_raw, mp * 8)); TRY(dalloc(&c->d_raw2, mp * 8));
   TRY(cudaStreamCreateWithFlags(&c->s_ext, cudaStreamNonBlocking)); TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  TRY(cudaStreamCreateWithFlags(&c->s_exa, cudaStreamNonBlocking));
+  for (cudaEvent_t& e : c->ev_a) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (cudaEvent_t& e : c->ev_b) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  TRY(dalloc(&c->d_full2, mp)); TRY(dalloc(&c->d_ring_start2, 72));
   for (cudaEvent_t& e : c->ev_feat) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (cudaEvent_t& e : c->ev_odo) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (cudaEvent_t& e : c->ev_h2d) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -128,7 +137,7 @@ int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
   TRY(dalloc(&c->d_ring, mp));
   TRY(dalloc(&c->d_hist, (size_t)c->nblocks_max * 64)); TRY(dalloc(&c->d_offsets, (size_t)c->nblocks_max * 64));
   TRY(dalloc(&c->d_ring_start, 72)); TRY(dalloc(&c->d_scan_start, 64)); TRY(dalloc(&c->d_scan_end, 64));
-  TRY(dalloc(&c->d_sc, 2));
+  TRY(dalloc(&c->d_sc, 3));
   TRY(dalloc(&c->d_full, mp)); TRY(dalloc(&c->d_curv, mp)); TRY(dalloc(&c->d_label, mp));
   TRY(dalloc(&c->st_sharp, 64 * kMaxSharpPerRing)); TRY(dalloc(&c->st_less_sharp, 64 * kMaxLessSharpPerRing));
   TRY(dalloc(&c->st_flat, 64 * kMaxFlatPerRing)); TRY(dalloc(&c->st_less_flat, (size_t)64 * ALOAM_MAX_RING));
@@ -150,8 +159,8 @@ int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
   TRY(dalloc(&c->d_summary, 4)); TRY(dalloc(&c->d_err, 4));
   TRY(dalloc(&c->d_query, mp)); TRY(dalloc(&c->d_knn_idx, mp)); TRY(dalloc(&c->d_knn_d, mp));
   for (int k = 0; k < 5; ++k) TRY(halloc(&c->h_out[k], k == 0 || k == 4 ? mp : (size_t)kMaxQueries));
-  TRY(halloc(&c->h_ints, 4096)); TRY(halloc(&c->h_dbl, 4096)); TRY(halloc(&c->h_summary, 4)); TRY(halloc(&c->h_sc, 2));
-  ScanScalars init[2];
+  TRY(halloc(&c->h_ints, 4096)); TRY(halloc(&c->h_dbl, 4096)); TRY(halloc(&c->h_summary, 4)); TRY(halloc(&c->h_sc, 3));
+  ScanScalars init[3];
   for (ScanScalars& s : init) { s.first_valid = INT32_MAX; s.last_valid = -1; s.half_idx = INT32_MAX; s.n_full = 0; s.start_ori = 0; s.end_ori = 0; s.error = 0; s.pad = 0; }
   TRY(cudaMemcpy(c->d_sc, init, sizeof(init), cudaMemcpyHostToDevice));
   TRY(cudaMemset(c->d_err, 0, 16));
@@ -373,32 +382,45 @@ int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, i
   cudaStream_t s_main = c->stream;
   float* rawbuf[2] = {c->d_raw, c->d_raw2};
   CUDA_CHECK_RET(cudaEventRecord(c->ev0, s_main));
-  int first_slot = -1;
+  // everything issued on the main stream before this call (reset, earlier calls) is ordered before the side streams.
+  // Waiting on an event that was never recorded, or whose work finished in an earlier call, is a no-op -- so the
+  // per-scan waits below need no "first iterations" special cases.
+  CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_h2d, c->ev0, 0));
+  CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_exa, c->ev0, 0));
+  CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev0, 0));
   for (int k = 0; k < n_scans; ++k) {
     const int f = c->frame;                 // global frame number of this scan
+    const int b = k & 1;                    // raw / ring-major double buffer
     FeatBuf& cur = c->feat[f % 3];
     FeatBuf& last = c->feat[(f + 2) % 3];
     const float* d_raw;
     if (device_resident) {
       d_raw = raws[k].data;
     } else {
-      const int b = k & 1;
-      if (k >= 2) CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_h2d, c->ev_rawfree[b], 0));   // extraction of scan k-2 has consumed the buffer
+      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_h2d, c->ev_rawfree[b], 0));   // stage A of scan k-2 has consumed the buffer
       CUDA_CHECK_RET(cudaMemcpyAsync(rawbuf[b], raws[k].data, (size_t)raws[k].n * raws[k].stride_floats * 4, cudaMemcpyHostToDevice, c->s_h2d));
       CUDA_CHECK_RET(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
-      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_h2d[b], 0));
+      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_exa, c->ev_h2d[b], 0));
       d_raw = rawbuf[b];
     }
-    // ---- extraction + index build on s_ext.  cur (= slot of frame f-3) was last read by the odometry of frame f-2 (as "last")
-    if (k >= 2) CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_odo[(f + 1) % 3], 0));  // (f-2) % 3
-    else CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev0, 0));                         // everything issued before this call
+    // ---- stage A (ring binning) on s_exa: needs full[b] free, i.e. stage B of scan k-2 done
+    CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_exa, c->ev_b[b], 0));
+    c->stream = c->s_exa;
+    int sc_slot = 0;
+    int rc = run_features_a(c, d_raw, raws[k].n, device_resident ? 4 : raws[k].stride_floats, b, &sc_slot);
+    if (!device_resident) cudaEventRecord(c->ev_rawfree[b], c->s_exa);
+    cudaEventRecord(c->ev_a[b], c->s_exa);
+    // ---- stage B (per-ring features + index build) on s_ext: needs stage A of this scan, and its output slot
+    //      feat[f % 3] free: that slot was last read by the odometry of frame f-2 (as its "last" clouds)
     c->stream = c->s_ext;
-    const int slot = c->parity;
-    if (first_slot < 0) first_slot = slot;
-    int rc = run_features(c, d_raw, raws[k].n, device_resident ? 4 : raws[k].stride_floats, cur);
-    if (!device_resident) cudaEventRecord(c->ev_rawfree[k & 1], c->s_ext);
-    run_grid_build(c, cur, 64 * kMaxLessSharpPerRing, std::min(raws[k].n, c->max_points));
-    cudaEventRecord(c->ev_feat[f % 3], c->s_ext);
+    if (!rc) {
+      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_a[b], 0));
+      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_odo[(f + 1) % 3], 0));
+      rc = run_features_b(c, b, sc_slot, cur);
+      cudaEventRecord(c->ev_b[b], c->s_ext);
+      run_grid_build(c, cur, 64 * kMaxLessSharpPerRing, std::min(raws[k].n, c->max_points));
+      cudaEventRecord(c->ev_feat[f % 3], c->s_ext);
+    }
     c->stream = s_main;
     if (rc) return rc;
     // ---- association + LM on the main stream
@@ -410,13 +432,15 @@ int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, i
     c->frame++;
   }
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, s_main));
-  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_sc, c->d_sc, 2 * sizeof(ScanScalars), cudaMemcpyDeviceToHost, s_main));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_sc, c->d_sc, 3 * sizeof(ScanScalars), cudaMemcpyDeviceToHost, s_main));
   CUDA_CHECK_RET(cudaEventRecord(c->ev1, s_main));
   CUDA_CHECK_RET(cudaStreamSynchronize(s_main));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->s_ext));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->s_exa));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->s_h2d));
   CUDA_CHECK_RET(cudaGetLastError());
   prof_collect(c);
-  for (int b = 0; b < 2; ++b)
+  for (int b = 0; b < 3; ++b)
     if (c->h_sc[b].error) { int e = c->h_sc[b].error; cudaMemset(&(c->d_sc + b)->error, 0, 4); return e; }
   std::memcpy(poses, c->h_poses, (size_t)n_scans * 56);
   float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);

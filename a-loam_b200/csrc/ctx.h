@@ -37,8 +37,9 @@ struct aloam_ctx {
   float* d_raw = nullptr;
   int8_t* d_ring = nullptr;
   int *d_hist = nullptr, *d_offsets = nullptr, *d_ring_start = nullptr, *d_scan_start = nullptr, *d_scan_end = nullptr;
-  ScanScalars* d_sc = nullptr;  // [2]
-  Pt4* d_full = nullptr;
+  ScanScalars* d_sc = nullptr;  // [3]: scan k uses slot k%3 and re-arms the next; B(k) may still read slot k while A(k+1) re-arms k+2
+  Pt4 *d_full = nullptr, *d_full2 = nullptr;   // ring-major cloud, double-buffered for the pipelined stream call
+  int* d_ring_start2 = nullptr;
   float* d_curv = nullptr;
   int8_t* d_label = nullptr;
   Pt4 *st_sharp = nullptr, *st_less_sharp = nullptr, *st_flat = nullptr, *st_less_flat = nullptr;
@@ -71,8 +72,8 @@ struct aloam_ctx {
   int *d_vox_hist = nullptr, *d_vox_offs = nullptr, *d_vox_misc = nullptr;
   // pipelined scan stream (aloam_scan_stream): extraction + index build on s_ext, association + LM on `stream`,
   // host->device copies of the raw scans on s_h2d, all chained by events
-  cudaStream_t s_ext = nullptr, s_h2d = nullptr;
-  cudaEvent_t ev_feat[3] = {}, ev_odo[3] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {};
+  cudaStream_t s_ext = nullptr, s_exa = nullptr, s_h2d = nullptr;
+  cudaEvent_t ev_feat[3] = {}, ev_odo[3] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {}, ev_a[2] = {}, ev_b[2] = {};
   float* d_raw2 = nullptr;       // second raw-scan staging buffer
   double* h_poses = nullptr;     // pinned [kMaxStreamScans][7]
   // pinned host mirrors
@@ -176,22 +177,41 @@ LastCloud last_corner(const FeatBuf& f) { return LastCloud{f.less_sharp, f.count
 LastCloud last_surf(const FeatBuf& f) { return LastCloud{f.less_flat, f.counts + 3, f.g_lf}; }
 
 // feature extraction kernels on a raw scan already in device memory
-int run_features(aloam_ctx* c, const float* d_raw, int n, int stride, FeatBuf& out) {
+// Feature extraction is issued in two halves so that the pipelined stream call can run them on different streams:
+//   A  ring binning   (k_classify, k_ring_scan, k_scatter)  raw scan -> ring-major cloud `full[buf]`, ring_start[buf]
+//   B  per-ring work  (k_ring_features, k_compact)          full[buf] -> the four feature clouds of `out`
+// `sc_slot` (returned by A, consumed by B) is the ScanScalars parity slot of this scan.
+int run_features_a(aloam_ctx* c, const float* d_raw, int n, int stride, int buf, int* sc_slot) {
   const int nb = (n + 1023) / 1024;
   const float thres = c->cfg.minimum_range;
   ScanScalars* sc = c->d_sc + c->parity;
-  ScanScalars* sc_next = c->d_sc + (c->parity ^ 1);
+  ScanScalars* sc_next = c->d_sc + (c->parity + 1) % 3;
+  Pt4* full = buf ? c->d_full2 : c->d_full;
+  int* rstart = buf ? c->d_ring_start2 : c->d_ring_start;
   LAUNCH(c, KID_CLASSIFY, k_classify, nb, 256, 0, d_raw, n, stride, c->cfg.n_scans, thres * thres, c->d_ring, c->d_hist, sc);
-  LAUNCH(c, KID_RING_SCAN, k_ring_scan, 1, 1024, 0, d_raw, stride, nb, c->cfg.n_scans, c->d_hist, c->d_offsets, c->d_ring_start,
+  LAUNCH(c, KID_RING_SCAN, k_ring_scan, 1, 1024, 0, d_raw, stride, nb, c->cfg.n_scans, c->d_hist, c->d_offsets, rstart,
          c->d_scan_start, c->d_scan_end, sc, sc_next);
-  LAUNCH(c, KID_SCATTER, k_scatter, nb, 256, 0, d_raw, n, stride, c->d_ring, c->d_offsets, sc, c->d_full);
-  LAUNCH(c, KID_RING_FEATURES, k_ring_features, c->cfg.n_scans, 256, ring_features_smem_bytes(), c->d_full, c->d_ring_start,
-         c->cfg.n_scans, 0.2f, c->st_sharp, c->st_less_sharp, c->st_flat, c->st_less_flat, c->st_counts, c->d_curv, c->d_label, sc);
-  LAUNCH(c, KID_COMPACT, k_compact, c->cfg.n_scans, 128, 0, c->cfg.n_scans, c->st_sharp, c->st_less_sharp, c->st_flat,
-         c->st_less_flat, c->st_counts, out.sharp, out.less_sharp, out.flat, out.less_flat, out.counts, out.rs_ls, out.rs_lf);
-  c->parity ^= 1;
+  LAUNCH(c, KID_SCATTER, k_scatter, nb, 256, 0, d_raw, n, stride, c->d_ring, c->d_offsets, sc, full);
+  *sc_slot = c->parity;
+  c->parity = (c->parity + 1) % 3;
   CUDA_CHECK_RET(cudaGetLastError());
   return ALOAM_OK;
+}
+int run_features_b(aloam_ctx* c, int buf, int sc_slot, FeatBuf& out) {
+  Pt4* full = buf ? c->d_full2 : c->d_full;
+  int* rstart = buf ? c->d_ring_start2 : c->d_ring_start;
+  LAUNCH(c, KID_RING_FEATURES, k_ring_features, c->cfg.n_scans, 256, ring_features_smem_bytes(), full, rstart,
+         c->cfg.n_scans, 0.2f, c->st_sharp, c->st_less_sharp, c->st_flat, c->st_less_flat, c->st_counts, c->d_curv, c->d_label, c->d_sc + sc_slot);
+  LAUNCH(c, KID_COMPACT, k_compact, c->cfg.n_scans, 128, 0, c->cfg.n_scans, c->st_sharp, c->st_less_sharp, c->st_flat,
+         c->st_less_flat, c->st_counts, out.sharp, out.less_sharp, out.flat, out.less_flat, out.counts, out.rs_ls, out.rs_lf);
+  CUDA_CHECK_RET(cudaGetLastError());
+  return ALOAM_OK;
+}
+int run_features(aloam_ctx* c, const float* d_raw, int n, int stride, FeatBuf& out) {
+  int slot = 0;
+  int rc = run_features_a(c, d_raw, n, stride, 0, &slot);
+  if (rc) return rc;
+  return run_features_b(c, 0, slot, out);
 }
 
 // index over the two "last" clouds: count -> scan -> fill (n_ls / n_lf = host upper bounds on the cloud sizes)
