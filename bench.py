@@ -428,8 +428,14 @@ def main():
         dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
         dom_ms = per_kernel[dom]["ms_per_launch"]
         achieved = alg_bytes.get(dom, 0) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or null
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic = tj["traffic"] if tj.get("kernel") == dom else tj.get("others", {}).get(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes.get(dom, 0),
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes.get(dom, 0),
                     "ms_per_launch": dom_ms, "per_kernel": per_kernel,
                     "note": "single ~2 MB scans are latency/occupancy bound, not HBM bound (SURVEY.md 8d): frac is expected << 1"}
 
