@@ -64,6 +64,7 @@ int aloam_destroy(aloam_ctx* c) {
   for (cudaEvent_t e : c->ev_rawfree) if (e) cudaEventDestroy(e);
   if (c->d_raw2) cudaFree(c->d_raw2);
   if (c->h_poses) cudaFreeHost(c->h_poses);
+  if (c->d_poses) cudaFree(c->d_poses);
   void* dev[] = {c->d_raw, c->d_ring, c->d_hist, c->d_offsets, c->d_ring_start, c->d_scan_start, c->d_scan_end, c->d_sc,
                  c->d_full, c->d_curv, c->d_label, c->st_sharp, c->st_less_sharp, c->st_flat, c->st_less_flat, c->st_counts,
                  c->d_blocks, c->d_corr, c->d_pose, c->d_world, c->d_out28, c->d_packed, c->d_summary, c->d_err, c->d_query,
@@ -133,7 +134,7 @@ int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
   for (cudaEvent_t& e : c->ev_odo) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (cudaEvent_t& e : c->ev_h2d) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (cudaEvent_t& e : c->ev_rawfree) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  TRY(halloc(&c->h_poses, (size_t)kMaxStreamScans * 7));
+  TRY(halloc(&c->h_poses, (size_t)kMaxStreamScans * 7)); TRY(dalloc(&c->d_poses, (size_t)kMaxStreamScans * 7));
   TRY(dalloc(&c->d_ring, mp));
   TRY(dalloc(&c->d_hist, (size_t)c->nblocks_max * 64)); TRY(dalloc(&c->d_offsets, (size_t)c->nblocks_max * 64));
   TRY(dalloc(&c->d_ring_start, 72)); TRY(dalloc(&c->d_scan_start, 64)); TRY(dalloc(&c->d_scan_end, 64));
@@ -425,12 +426,14 @@ int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, i
     if (rc) return rc;
     // ---- association + LM on the main stream
     CUDA_CHECK_RET(cudaStreamWaitEvent(s_main, c->ev_feat[f % 3], 0));
-    if (f > 0) run_register(c, cur, last, kFusedSharpSlots, kFusedFlatSlots, true, nullptr);
-    CUDA_CHECK_RET(cudaMemcpyAsync(c->h_poses + (size_t)k * 7, c->d_world, 56, cudaMemcpyDeviceToHost, s_main));
+    // the last solve of the scan writes the integrated world pose into its slot of d_poses (no copy on the critical chain)
+    if (f > 0) run_register(c, cur, last, kFusedSharpSlots, kFusedFlatSlots, true, nullptr, c->d_poses + (size_t)k * 7);
+    else CUDA_CHECK_RET(cudaMemcpyAsync(c->d_poses + (size_t)k * 7, c->d_world, 56, cudaMemcpyDeviceToDevice, s_main));
     CUDA_CHECK_RET(cudaEventRecord(c->ev_odo[f % 3], s_main));
     c->cur = f % 3;
     c->frame++;
   }
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_poses, c->d_poses, (size_t)n_scans * 56, cudaMemcpyDeviceToHost, s_main));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, s_main));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_sc, c->d_sc, 3 * sizeof(ScanScalars), cudaMemcpyDeviceToHost, s_main));
   CUDA_CHECK_RET(cudaEventRecord(c->ev1, s_main));
@@ -480,7 +483,7 @@ static int run_lm_api(aloam_ctx* c, const double* blocks, int n_blocks, const do
   }
   for (int k = 0; k < 7; ++k) c->h_dbl[k] = x[k];
   CUDA_CHECK_RET(cudaMemcpyAsync(c->d_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
-  launch_lm(c, (const BlockRec*)c->d_blocks, (const int*)nullptr, n_blocks, c->d_pose, lm_params(c->cfg), c->d_summary, mode,
+  launch_lm(c, false, (const BlockRec*)c->d_blocks, (const int*)nullptr, n_blocks, c->d_pose, lm_params(c->cfg), c->d_summary, mode,
             c->d_out28, (double*)nullptr, 0);
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 8, c->d_pose, 56, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 32, c->d_out28, 28 * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -28,6 +28,14 @@ struct FeatureCounts {
   int n_sharp, n_less_sharp, n_flat, n_less_flat;
 };
 
+// programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident before its predecessor in the stream has finished. pdl_wait() blocks until the predecessor grid has completed
+// and its memory is visible (a no-op for a normal launch); pdl_launch_dependents() lets the successor start launching.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 #define CUDA_CHECK_RET(expr)                                                                   \
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \

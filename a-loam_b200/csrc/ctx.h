@@ -76,6 +76,7 @@ struct aloam_ctx {
   cudaEvent_t ev_feat[3] = {}, ev_odo[3] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {}, ev_a[2] = {}, ev_b[2] = {};
   float* d_raw2 = nullptr;       // second raw-scan staging buffer
   double* h_poses = nullptr;     // pinned [kMaxStreamScans][7]
+  double* d_poses = nullptr;     // device [kMaxStreamScans][7]: per-scan world poses of a stream call (one D2H at the end)
   // pinned host mirrors
   Pt4* h_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int* h_ints = nullptr;        // scratch ints (counts etc.)
@@ -124,19 +125,27 @@ inline void prof_collect(aloam_ctx* c) {
 #define LAUNCH(c, kid, kernel, grid, block, smem, ...) \
   do { prof_begin(c, kid); kernel<<<grid, block, smem, (c)->stream>>>(__VA_ARGS__); prof_end(c); } while (0)
 
+// launch with an optional programmatic dependency on the previous kernel of the stream (PDL): the grid may become resident
+// while its predecessor is still running and blocks in pdl_wait() (common.cuh) until the predecessor has completed and flushed.
+template <typename K, typename... Args>
+void launch_ex(aloam_ctx* c, int kid, K kernel, dim3 grid, dim3 block, size_t smem, int cluster, bool pdl, Args... args) {
+  prof_begin(c, kid);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (cluster > 1) { at[na].id = cudaLaunchAttributeClusterDimension; at[na].val.clusterDim.x = cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1; ++na; }
+  if (pdl && !c->prof_on) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+  cfg.attrs = at; cfg.numAttrs = na;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+  prof_end(c);
+}
+
 // the LM kernel runs as one thread-block cluster (distributed-shared-memory reduction, see lm.cu)
 constexpr int kLmCluster = 8;
 template <typename... Args>
-void launch_lm(aloam_ctx* c, Args... args) {
-  prof_begin(c, KID_LM_SOLVE);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(kLmCluster); cfg.blockDim = dim3(ALOAM_LM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = kLmCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, k_lm_solve, args...);
-  prof_end(c);
+void launch_lm(aloam_ctx* c, bool pdl, Args... args) {
+  launch_ex(c, KID_LM_SOLVE, k_lm_solve, dim3(kLmCluster), dim3(ALOAM_LM_THREADS), 0, kLmCluster, pdl, args...);
 }
 
 // sharded LM (comm.cu): per evaluation one kernel for the local blocks, one ncclAllReduce of 28 doubles, one step kernel
@@ -144,7 +153,7 @@ void launch_lm(aloam_ctx* c, Args... args) {
 void launch_lm_sharded(aloam_ctx* c, const aloam::BlockRec* blocks, int n, double* pose, const aloam::LmParams& lp, aloam::LmSummary* summary);
 namespace {
 inline void launch_lm_step(aloam_ctx* c, const BlockRec* blocks, int n, double* pose, const LmParams& lp, LmSummary* summary) {
-  if (c->shard_count <= 1) launch_lm(c, blocks, (const int*)nullptr, n, pose, lp, summary, 0, (double*)nullptr, (double*)nullptr, 0);
+  if (c->shard_count <= 1) launch_lm(c, false, blocks, (const int*)nullptr, n, pose, lp, summary, 0, (double*)nullptr, (double*)nullptr, 0);
   else launch_lm_sharded(c, blocks, n, pose, lp, summary);
 }
 
@@ -223,18 +232,20 @@ void run_grid_build(aloam_ctx* c, FeatBuf& f, int n_ls, int n_lf) {
 }
 
 // outer_iters x (association + LM) ; `cur` supplies sharp/flat, `last` the targets ; pose in c->d_pose
+// `pose_slot` (device, 7 doubles, may be null): the integrated world pose is also written there by the last solve
 void run_register(aloam_ctx* c, const FeatBuf& cur, const FeatBuf& last, int sharp_slots, int flat_slots, bool integrate,
-                  int* d_corr) {
+                  int* d_corr, double* pose_slot = nullptr) {
   OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan};
   const LmParams lp = lm_params(c->cfg);
   const int slots = sharp_slots + flat_slots;
   for (int it = 0; it < c->cfg.outer_iters; ++it) {
+    // within one call the chain association -> LM -> association -> LM is launched with programmatic dependencies
     if (slots > 0)
-      LAUNCH(c, KID_ODOM_ASSOC, k_odom_assoc, (slots + 7) / 8, 256, 0, cur.sharp, cur.flat, cur.counts, last_corner(last),
-             last_surf(last), c->d_pose, op, c->d_blocks, d_corr, sharp_slots);
+      launch_ex(c, KID_ODOM_ASSOC, k_odom_assoc, dim3((slots + 7) / 8), dim3(256), 0, 1, it > 0, (const Pt4*)cur.sharp, (const Pt4*)cur.flat,
+                (const int*)cur.counts, last_corner(last), last_surf(last), (const double*)c->d_pose, op, c->d_blocks, d_corr, sharp_slots);
     const bool last_it = it == c->cfg.outer_iters - 1;
-    launch_lm(c, (const BlockRec*)c->d_blocks, (const int*)nullptr, slots, c->d_pose, lp, c->d_summary + (it & 3), 0,
-              (double*)nullptr, c->d_world, (integrate && last_it) ? 1 : 0);
+    launch_lm(c, slots > 0, (const BlockRec*)c->d_blocks, (const int*)nullptr, slots, c->d_pose, lp, c->d_summary + (it & 3), 0,
+              (integrate && last_it) ? pose_slot : (double*)nullptr, c->d_world, (integrate && last_it) ? 1 : 0);
   }
 }
 

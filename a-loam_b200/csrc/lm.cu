@@ -436,6 +436,8 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
   __shared__ double s_x[7];
   __shared__ TrState T;
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();   // blocks / x7 are produced by the preceding kernel of the stream
   const int n = n_blocks_ptr ? *n_blocks_ptr : n_blocks_host;
   const bool writer = cluster.block_rank() == 0 && tid == 0;
   int pass = 0;
@@ -445,8 +447,12 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
   __syncthreads();
   // one evaluation site (the evaluation body is large; duplicating it costs instruction-cache misses)
   bool first = true;
+  long long cyc_eval = 0, cyc_tr = 0;
   do {
+    const long long c0 = clock64();
     cluster_evaluate(cluster, blocks, n, first ? s_x : T.xc, prm.huber_a, s_part, s_cta, s_tot, pass);
+    const long long c1 = clock64();
+    cyc_eval += c1 - c0;
     if (first && mode == 1) {
       if (cluster.block_rank() == 0 && tid < 28) out28[tid] = s_tot[tid];
       cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
@@ -456,10 +462,14 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
     if (tid == 0) { if (first) tr_start(T, s_x, s_tot, prm, summary, writer); else tr_after_eval(T, s_tot, prm, summary, writer); }
     first = false;
     __syncthreads();
+    cyc_tr += clock64() - c1;
   } while (T.go);
   if (writer) {
     tr_finish(T, x7, summary);
     summary->cyc_total = clock64() - clk0;
+    summary->cyc_eval = cyc_eval;
+    summary->cyc_chol = cyc_tr;
+    summary->cyc_plus = pass;
     if (integrate && world7) {
       // laserOdometry.cpp:504-505  t_w += q_w * t_last_curr ; q_w = q_w * q_last_curr
       const V3 u{world7[0], world7[1], world7[2]};
@@ -477,6 +487,10 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
       world7[0] = aw * bx + ax * bw + ay * bz - az * by;
       world7[1] = aw * by + ay * bw + az * bx - ax * bz;
       world7[2] = aw * bz + az * bw + ax * by - ay * bx;
+      if (out28) {   // mode 0: `out28` doubles as the per-scan pose slot of a stream call
+#pragma unroll
+        for (int k = 0; k < 7; ++k) out28[k] = world7[k];
+      }
     }
   }
   cluster.sync();  // no CTA may exit while another can still read its shared memory

@@ -197,6 +197,8 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
                                                     const int* __restrict__ feat_counts, LastCloud corner,
                                                     LastCloud surf, const double* __restrict__ pose7, OdomParams prm,
                                                     BlockRec* __restrict__ blocks, int* __restrict__ corr, int max_sharp) {
+  pdl_launch_dependents();   // the LM solve that follows may become resident now; it blocks in its own pdl_wait()
+  pdl_wait();                // the preceding LM solve (pose7 producer, blocks consumer) has completed
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = lane_id();
   const bool is_corner = wid < max_sharp;
