@@ -166,6 +166,8 @@ int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
   TRY(cudaMemcpy(c->d_sc, init, sizeof(init), cudaMemcpyHostToDevice));
   TRY(cudaMemset(c->d_err, 0, 16));
   TRY(cudaFuncSetAttribute(k_ring_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_features_smem_bytes()));
+  TRY(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dynamic_smem_bytes()));
+  TRY(cudaFuncSetAttribute(k_lm_eval_shard, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dynamic_smem_bytes()));
 #undef TRY
   int rc = aloam_reset_odometry(c);
   if (rc != ALOAM_OK) { aloam_destroy(c); return rc; }

@@ -45,7 +45,7 @@ void launch_lm_sharded(aloam_ctx* c, const BlockRec* blocks, int n, double* pose
     const int first = e == 0, last = e == evals - 1;
     prof_begin(c, KID_LM_SOLVE);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kLmCluster); cfg.blockDim = dim3(ALOAM_LM_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cfg.gridDim = dim3(kLmCluster); cfg.blockDim = dim3(ALOAM_LM_THREADS); cfg.dynamicSmemBytes = lm_dynamic_smem_bytes(); cfg.stream = c->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = kLmCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

@@ -145,7 +145,7 @@ void launch_ex(aloam_ctx* c, int kid, K kernel, dim3 grid, dim3 block, size_t sm
 constexpr int kLmCluster = 8;
 template <typename... Args>
 void launch_lm(aloam_ctx* c, bool pdl, Args... args) {
-  launch_ex(c, KID_LM_SOLVE, k_lm_solve, dim3(kLmCluster), dim3(ALOAM_LM_THREADS), 0, kLmCluster, pdl, args...);
+  launch_ex(c, KID_LM_SOLVE, k_lm_solve, dim3(kLmCluster), dim3(ALOAM_LM_THREADS), lm_dynamic_smem_bytes(), kLmCluster, pdl, args...);
 }
 
 // sharded LM (comm.cu): per evaluation one kernel for the local blocks, one ncclAllReduce of 28 doubles, one step kernel

@@ -113,6 +113,7 @@ __global__ void k_lm_solve(const BlockRec* blocks, const int* n_blocks_ptr, int 
                            LmParams prm, LmSummary* summary, int mode, double* out28, double* world7, int integrate);
 // sharded solve: per-evaluation kernels around an ncclAllReduce (see lm.cu, comm.cu)
 size_t lm_state_bytes();
+size_t lm_dynamic_smem_bytes();   // dynamic shared memory of k_lm_solve / k_lm_eval_shard (opt-in > 48 KB)
 __global__ void k_lm_eval_shard(const BlockRec* blocks, int n, const double* x7, void* state, int first, double huber_a, double* local32);
 __global__ void k_lm_tr_shard(void* state, const double* tot32, double* x7, int first, int last, LmParams prm, LmSummary* summary);
 // packs API-side residual blocks (11 doubles) into BlockRec

@@ -361,50 +361,79 @@ __device__ void tr_finish(const TrState& T, double* x7, LmSummary* summary) {
   summary->trace_rows = T.trace_rows;
 }
 
-// every thread of the cluster evaluates its share of the blocks at x ; afterwards s_tot[0..31] holds the cluster-wide
-// totals in every CTA (slots 28 / 29 = edge / plane block counts)
+// every thread of the cluster evaluates its share of the blocks at x ; afterwards s_tot[0..29] (written and read by warp 0
+// only) holds the cluster-wide totals in every CTA (slots 28 / 29 = edge / plane block counts).
+//   thread -> warp : the 30 accumulators are transposed through shared memory (15 STS.128 per thread, then lane L adds
+//                    column L of its warp's 32 rows in a fixed order) -- 80 instructions instead of the 217 of a
+//                    select + shuffle butterfly in double precision
+//   warp -> CTA    : warp 0 adds the NW partial vectors
+//   CTA -> cluster : warp 0 PUSHES its vector into every CTA's shared memory (DSMEM stores), one cluster barrier, then
+//                    every CTA adds the 8 vectors it received in rank order => bit-identical totals everywhere.
+// `rb0` is this thread's first block, kept in registers across the passes of a solve.
+constexpr int RS = 30;   // doubles per thread row of the transpose scratch (240 B: 16-byte aligned, bank-conflict free)
 template <typename Cluster>
-__device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRec* __restrict__ blocks, int n, const double* xs,
-                                                 double huber_a, double (*s_part)[32], double (*s_cta)[32], double* s_tot, int& pass) {
+__device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRec* __restrict__ blocks, int n, const BlockRec& rb0,
+                                                 const double* xs, double huber_a, double* s_red, double (*s_part)[32],
+                                                 double (*s_in)[8][32], double* s_tot, int& pass) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
   const int gtid = (int)crank * NT + tid, gstride = (int)csize * NT;
   double x[7];
 #pragma unroll
   for (int k = 0; k < 7; ++k) x[k] = xs[k];
-  double acc[32];
+  double acc[RS];
 #pragma unroll
-  for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-  for (int b = gtid; b < n; b += gstride) {
-    const BlockRec rb = blocks[b];
-    if (rb.type >= 0) {
-      eval_block(rb, x, huber_a, acc);
-      acc[28] += (rb.type == 0) ? 1.0 : 0.0;
-      acc[29] += (rb.type > 0) ? 1.0 : 0.0;
+  for (int k = 0; k < RS; ++k) acc[k] = 0.0;
+  if (gtid < n) {
+    BlockRec rb = rb0;
+    for (int b = gtid;;) {
+      if (rb.type >= 0) {
+        eval_block(rb, x, huber_a, acc);
+        acc[28] += (rb.type == 0) ? 1.0 : 0.0;
+        acc[29] += (rb.type > 0) ? 1.0 : 0.0;
+      }
+      b += gstride;
+      if (b >= n) break;
+      rb = blocks[b];
     }
   }
-  const double mine = warp_transpose_reduce(acc);
+  double2* row = reinterpret_cast<double2*>(s_red + (size_t)tid * RS);
+#pragma unroll
+  for (int k = 0; k < RS / 2; ++k) row[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+  __syncwarp();
+  double mine = 0.0;
+  if (lane < RS) {
+    const double* col = s_red + (size_t)(warp * 32) * RS + lane;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 32; r += 2) { s0 += col[r * RS]; s1 += col[(r + 1) * RS]; }
+    mine = s0 + s1;
+  }
   s_part[warp][lane] = mine;
   __syncthreads();
-  if (tid < 32) {
+  if (warp == 0) {
     double v = 0.0;
 #pragma unroll
-    for (int w2 = 0; w2 < NW; ++w2) v += s_part[w2][tid];
-    s_cta[pass & 1][tid] = v;
+    for (int w2 = 0; w2 < NW; ++w2) v += s_part[w2][lane];
+    double* slot = &s_in[pass & 1][crank][lane];
+    for (unsigned r = 0; r < csize; ++r) *cluster.map_shared_rank(slot, r) = v;
   }
-  cluster.sync();
-  if (tid < 32 * (int)csize && tid < NT) {   // one remote read per thread, all CTAs' partials in flight at once
-    const double* remote = cluster.map_shared_rank(&s_cta[pass & 1][0], (unsigned)(tid >> 5));
-    s_part[tid >> 5][tid & 31] = remote[tid & 31];
-  }
-  __syncthreads();
-  if (tid < 32) {
-    double v = 0.0;
-    for (unsigned r = 0; r < csize; ++r) v += s_part[r][tid];   // rank order => identical totals in every CTA
-    s_tot[tid] = v;
+  cluster.sync();   // release / acquire: every CTA's pushes of this pass are visible
+  if (warp == 0) {
+    double t = 0.0;
+    for (unsigned r = 0; r < csize; ++r) t += s_in[pass & 1][r][lane];   // rank order => identical totals in every CTA
+    s_tot[lane] = t;
+    __syncwarp();
   }
   ++pass;
-  __syncthreads();
+}
+
+__device__ __forceinline__ BlockRec load_first_block(const BlockRec* __restrict__ blocks, int n, unsigned crank) {
+  BlockRec rb;
+  rb.type = -1;
+  const int gtid = (int)crank * NT + (int)threadIdx.x;
+  if (gtid < n) rb = blocks[gtid];
+  return rb;
 }
 
 }  // namespace
@@ -430,8 +459,9 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
                                                     LmSummary* __restrict__ summary, int mode, double* __restrict__ out28,
                                                     double* __restrict__ world7, int integrate) {
   cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) double s_red[];   // [NT][RS] transpose scratch
   __shared__ double s_part[NW][32];
-  __shared__ double s_cta[2][32];   // this CTA's partial totals, double-buffered by pass parity (read by the whole cluster)
+  __shared__ double s_in[2][8][32];   // partial totals pushed by the 8 CTAs of the cluster, double-buffered by pass parity
   __shared__ double s_tot[32];
   __shared__ double s_x[7];
   __shared__ TrState T;
@@ -442,6 +472,7 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
   const bool writer = cluster.block_rank() == 0 && tid == 0;
   int pass = 0;
   const long long clk0 = clock64();
+  const BlockRec rb0 = load_first_block(blocks, n, cluster.block_rank());
 
   if (tid < 7) s_x[tid] = x7[tid];
   __syncthreads();
@@ -450,13 +481,12 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
   long long cyc_eval = 0, cyc_tr = 0;
   do {
     const long long c0 = clock64();
-    cluster_evaluate(cluster, blocks, n, first ? s_x : T.xc, prm.huber_a, s_part, s_cta, s_tot, pass);
+    cluster_evaluate(cluster, blocks, n, rb0, first ? s_x : T.xc, prm.huber_a, s_red, s_part, s_in, s_tot, pass);
     const long long c1 = clock64();
     cyc_eval += c1 - c0;
     if (first && mode == 1) {
       if (cluster.block_rank() == 0 && tid < 28) out28[tid] = s_tot[tid];
-      cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
-      return;
+      return;   // all remote stores into this CTA preceded the cluster barrier inside cluster_evaluate
     }
     // thread 0 of EVERY CTA takes the same decision from the same totals (no broadcast needed)
     if (tid == 0) { if (first) tr_start(T, s_x, s_tot, prm, summary, writer); else tr_after_eval(T, s_tot, prm, summary, writer); }
@@ -493,8 +523,10 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
       }
     }
   }
-  cluster.sync();  // no CTA may exit while another can still read its shared memory
+  // no trailing cluster barrier: the only remote accesses are the pushes that precede each pass's barrier
 }
+
+size_t lm_dynamic_smem_bytes() { return (size_t)NT * RS * sizeof(double); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Sharded solve (map split over GPUs): the same trust-region logic, but every evaluation is
@@ -506,8 +538,9 @@ size_t lm_state_bytes() { return sizeof(TrState); }
 __global__ void __launch_bounds__(NT, 1) k_lm_eval_shard(const BlockRec* __restrict__ blocks, int n, const double* __restrict__ x7,
                                                          void* state, int first, double huber_a, double* __restrict__ local32) {
   cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) double s_red[];
   __shared__ double s_part[NW][32];
-  __shared__ double s_cta[2][32];
+  __shared__ double s_in[2][8][32];
   __shared__ double s_tot[32];
   __shared__ double s_x[7];
   const TrState* T = reinterpret_cast<const TrState*>(state);
@@ -517,12 +550,12 @@ __global__ void __launch_bounds__(NT, 1) k_lm_eval_shard(const BlockRec* __restr
   __syncthreads();
   int pass = 0;
   if (active) {
-    cluster_evaluate(cluster, blocks, n, s_x, huber_a, s_part, s_cta, s_tot, pass);
-    if (cluster.block_rank() == 0 && tid < 32) local32[tid] = s_tot[tid];
+    const BlockRec rb0 = load_first_block(blocks, n, cluster.block_rank());
+    cluster_evaluate(cluster, blocks, n, rb0, s_x, huber_a, s_red, s_part, s_in, s_tot, pass);
+    if (cluster.block_rank() == 0 && tid < 32) local32[tid] = tid < RS ? s_tot[tid] : 0.0;
   } else if (cluster.block_rank() == 0 && tid < 32) {
     local32[tid] = 0.0;
   }
-  cluster.sync();
 }
 
 __global__ void k_lm_tr_shard(void* state, const double* __restrict__ tot32, double* __restrict__ x7, int first, int last,
