@@ -126,12 +126,40 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&v)[32]) {
   return v[0];
 }
 
+// sin(n)/n and cos(n).  LM steps are small rotations: below 0.25 rad both are evaluated as Taylor polynomials in n^2
+// (truncation < 1e-17 relative, i.e. the same <= 1 ulp class as libm's sin / cos) -- 16 FMAs instead of two libm calls
+// and a division on the serial trust-region path; larger angles take the libm route.
+__device__ __forceinline__ void sinc_cos(double n, double& sinc, double& c) {
+  if (n < 0.25) {
+    const double t = n * n;
+    double p = -1.0 / 6227020800.0;                 // sin(n)/n = 1 - t/3! + t^2/5! - ... - t^6/13!
+    p = fma(p, t, 1.0 / 39916800.0);
+    p = fma(p, t, -1.0 / 362880.0);
+    p = fma(p, t, 1.0 / 5040.0);
+    p = fma(p, t, -1.0 / 120.0);
+    p = fma(p, t, 1.0 / 6.0);
+    sinc = fma(-p, t, 1.0);
+    double q = 1.0 / 87178291200.0;                 // cos(n) = 1 - t/2! + t^2/4! - ... + t^7/14!
+    q = fma(q, t, -1.0 / 479001600.0);
+    q = fma(q, t, 1.0 / 3628800.0);
+    q = fma(q, t, -1.0 / 40320.0);
+    q = fma(q, t, 1.0 / 720.0);
+    q = fma(q, t, -1.0 / 24.0);
+    q = fma(q, t, 0.5);
+    c = fma(-q, t, 1.0);
+  } else {
+    sinc = sin(n) / n;
+    c = cos(n);
+  }
+}
+
 // ceres::EigenQuaternionParameterization::Plus + plain addition on t
 __device__ __forceinline__ void plus7(const double* x, const double* d, double* o) {
   const double n = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
   if (n > 0.0) {
-    const double s = sin(n) / n;
-    const double ax = s * d[0], ay = s * d[1], az = s * d[2], aw = cos(n);
+    double s, aw;
+    sinc_cos(n, s, aw);
+    const double ax = s * d[0], ay = s * d[1], az = s * d[2];
     const double bx = x[0], by = x[1], bz = x[2], bw = x[3];
     o[3] = aw * bw - ax * bx - ay * by - az * bz;
     o[0] = aw * bx + ax * bw + ay * bz - az * by;
@@ -144,11 +172,15 @@ __device__ __forceinline__ void plus7(const double* x, const double* d, double* 
 }
 
 // trust-region state of one solve (thread 0 only).  Shared memory in k_lm_solve, global memory in the sharded path.
+// The accepted point's reduced totals (packed: 21 upper-triangle J^T J, 6 J^T r, cost) are NOT copied into the state on
+// the cluster path: the kernel double-buffers its totals and `acc_buf` says which buffer belongs to the accepted point;
+// the sharded path keeps them in `acc`.
 struct TrState {
-  double x[7], xc[7], H[6][6], g[6], scale[6], diag[6];
+  double x[7], xc[7], acc[28], scale[6], diag[6];
   double cost, radius, decrease_factor, mcc, gmax, x_norm;
   int reuse_diag, last_successful, iteration, num_invalid, num_successful, num_evals, termination, trace_rows;
   int go;       // 1: xc holds a candidate that must be evaluated next ; 0: the solve is over
+  int acc_buf;  // cluster path: index of the totals buffer of the accepted point
   int n_res;
 };
 
@@ -167,18 +199,23 @@ __device__ double gradient_max(const double* x, const double* g, double tol) {
   return m;
 }
 
-// (Hs + diag/radius) y = b by Cholesky ; returns false on breakdown
-__device__ bool chol_solve6(const double Hs[6][6], const double* dg, double radius, const double* b, double* y) {
-  // L holds the strict lower triangle, inv[j] = 1 / L[j][j]  (one rsqrt per column, no divisions)
-  double L[6][6], inv[6];
-  const double ir = 1.0 / radius;
+// packed index of J^T J entry (a, c), a <= c
+__device__ __forceinline__ constexpr int pk(int a, int c) { return a * 6 - (a * (a - 1)) / 2 + (c - a); }
+
+// (Hs + diag/radius) y = b by Cholesky ; only the lower triangle Hs[i][j], i >= j, is read ; returns false on breakdown
+__device__ __forceinline__ bool chol_solve6(const double (&Hs)[6][6], const double* dr, const double* b, double* y) {
+  // L holds the strict lower triangle, inv[j] = 1 / L[j][j]  (one rsqrt per column, no divisions).  Every dot product
+  // ends with its most recently produced operand, so the dependent chain per column is one FMA + rsqrt + one multiply.
+  double L[6][6], inv[6], z[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double d = Hs[j][j] + dg[j] * ir;
+    double d = Hs[j][j] + dr[j];
+    double zj = b[j];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) if (k < j) d -= L[j][k] * L[j][k];
+    for (int k = 0; k < 6; ++k) if (k < j) { d -= L[j][k] * L[j][k]; zj -= L[j][k] * z[k]; }
     if (!(d > 0.0)) return false;
     inv[j] = rsqrt(d);
+    z[j] = zj * inv[j];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       if (i > j) {
@@ -189,19 +226,11 @@ __device__ bool chol_solve6(const double Hs[6][6], const double* dg, double radi
       }
     }
   }
-  double z[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    double s = b[i];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) if (k < i) s -= L[i][k] * z[k];
-    z[i] = s * inv[i];
-  }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = z[i];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) if (k > i) s -= L[k][i] * y[k];
+    for (int k = 5; k >= 0; --k) if (k > i) s -= L[k][i] * y[k];   // descending: y[i + 1], the newest, comes last
     y[i] = s * inv[i];
   }
   bool ok = true;
@@ -221,20 +250,11 @@ __device__ __forceinline__ void tr_trace(TrState& T, LmSummary* summary, bool wr
   }
 }
 
-// totals (28 numbers) -> T.H (full symmetric), T.g
-__device__ __forceinline__ void tr_load_totals(TrState& T, const double* tot) {
-  int k = 0;
+// produce the next candidate (-> T.xc, T.go = 1) or stop (T.go = 0).  A = packed totals of the accepted point.
+__device__ void tr_next_candidate(TrState& T, const double* A, const LmParams& prm, LmSummary* summary, bool writer) {
+  double sc[6];
 #pragma unroll
-  for (int a = 0; a < 6; ++a) {
-#pragma unroll
-    for (int c = a; c < 6; ++c) { T.H[a][c] = tot[k]; T.H[c][a] = tot[k]; ++k; }
-  }
-#pragma unroll
-  for (int a = 0; a < 6; ++a) T.g[a] = tot[21 + a];
-}
-
-// produce the next candidate (-> T.xc, T.go = 1) or stop (T.go = 0)
-__device__ void tr_next_candidate(TrState& T, const LmParams& prm, LmSummary* summary, bool writer) {
+  for (int j = 0; j < 6; ++j) sc[j] = T.scale[j];
   for (;;) {
     if (T.iteration >= prm.max_iters) { T.termination = 0; T.go = 0; return; }
     if (T.last_successful && T.gmax <= prm.gradient_tolerance) { T.termination = 1; T.go = 0; return; }
@@ -243,31 +263,28 @@ __device__ void tr_next_candidate(TrState& T, const LmParams& prm, LmSummary* su
     T.last_successful = 0;
     if (!T.reuse_diag) {
 #pragma unroll
-      for (int j = 0; j < 6; ++j) T.diag[j] = fmin(fmax(T.scale[j] * T.scale[j] * T.H[j][j], prm.min_lm_diagonal), prm.max_lm_diagonal);
+      for (int j = 0; j < 6; ++j) T.diag[j] = fmin(fmax(sc[j] * sc[j] * A[pk(j, j)], prm.min_lm_diagonal), prm.max_lm_diagonal);
     }
-    double Hs[6][6], b[6], y[6], dg[6];
+    double Hs[6][6], b[6], y[6], dr[6];
+    const double ir = 1.0 / T.radius;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) Hs[a][c] = T.scale[a] * T.H[a][c] * T.scale[c];
-      b[a] = T.scale[a] * T.g[a];
-      dg[a] = T.diag[a];
+      for (int c = 0; c < 6; ++c) if (c <= a) Hs[a][c] = sc[c] * A[pk(c, a)] * sc[a];
+      b[a] = sc[a] * A[21 + a];
+      dr[a] = T.diag[a] * ir;
     }
-    const bool ok = chol_solve6(Hs, dg, T.radius, b, y);
+    const bool ok = chol_solve6(Hs, dr, b, y);
     T.reuse_diag = 1;
     double mcc = 0;
     if (ok) {
-      // model_cost_change = -(Js step)^T (r + Js step / 2) = -step^T Js^T r - 1/2 step^T Js^T Js step,  step = -y
-      double sb = 0, shs = 0;
+      // model_cost_change = -(Js step)^T (r + Js step / 2) = y^T b - 1/2 y^T Hs y  with step = -y.  Since
+      // (Hs + D/radius) y = b :  y^T Hs y = y^T b - sum (D/radius)_a y_a^2 , hence
+      // model_cost_change = 1/2 (y^T b + sum (D/radius)_a y_a^2)  -- 12 FMAs instead of a 6x6 matrix-vector product
+      double yb = 0, ydy = 0;
 #pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        sb -= y[a] * b[a];
-        double t = 0;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) t -= Hs[a][c] * y[c];
-        shs -= y[a] * t;
-      }
-      mcc = -sb - 0.5 * shs;
+      for (int a = 0; a < 6; ++a) { yb += y[a] * b[a]; ydy += dr[a] * y[a] * y[a]; }
+      mcc = 0.5 * (yb + ydy);
     }
     T.mcc = mcc;
     if (!(ok && mcc > 0.0)) {  // invalid step
@@ -279,7 +296,7 @@ __device__ void tr_next_candidate(TrState& T, const LmParams& prm, LmSummary* su
     T.num_invalid = 0;
     double delta[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) delta[k] = -y[k] * T.scale[k];
+    for (int k = 0; k < 6; ++k) delta[k] = -y[k] * sc[k];
     plus7(T.x, delta, T.xc);
     T.go = 1;
     return;
@@ -291,27 +308,27 @@ __device__ void tr_start(TrState& T, const double* x, const double* tot, const L
   const int ne = (int)(tot[28] + 0.5), np = (int)(tot[29] + 0.5);
 #pragma unroll
   for (int k = 0; k < 7; ++k) { T.x[k] = x[k]; T.xc[k] = x[k]; }
-  tr_load_totals(T, tot);
   T.cost = tot[27];
   T.radius = prm.initial_radius; T.decrease_factor = 2.0; T.mcc = 0; T.gmax = 0;
   T.reuse_diag = 0; T.last_successful = 0; T.iteration = 0; T.num_invalid = 0; T.num_successful = 0; T.num_evals = 1;
-  T.termination = 0; T.trace_rows = 0; T.n_res = ne + np; T.go = 0;
+  T.termination = 0; T.trace_rows = 0; T.n_res = ne + np; T.go = 0; T.acc_buf = 0;
   if (writer) { summary->initial_cost = T.cost; summary->n_edge = ne; summary->n_plane = np; }
   if (ne + np == 0) { T.termination = 4; return; }  // Ceres: nothing to optimise, parameters untouched
 #pragma unroll
-  for (int j = 0; j < 6; ++j) T.scale[j] = 1.0 / (1.0 + sqrt(T.H[j][j]));
-  T.gmax = gradient_max(T.x, T.g, prm.gradient_tolerance);
+  for (int j = 0; j < 6; ++j) T.scale[j] = 1.0 / (1.0 + sqrt(tot[pk(j, j)]));
+  T.gmax = gradient_max(T.x, tot + 21, prm.gradient_tolerance);
   double xn = 0;
 #pragma unroll
   for (int k = 0; k < 7; ++k) xn += T.x[k] * T.x[k];
   T.x_norm = sqrt(xn);
   tr_trace(T, summary, writer, T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0);
   if (T.gmax <= prm.gradient_tolerance) { T.termination = 1; return; }
-  tr_next_candidate(T, prm, summary, writer);
+  tr_next_candidate(T, tot, prm, summary, writer);
 }
 
-// after the evaluation of candidate T.xc: tolerance tests, accept / reject, next candidate
-__device__ void tr_after_eval(TrState& T, const double* tot, const LmParams& prm, LmSummary* summary, bool writer) {
+// after the evaluation of candidate T.xc (totals `tot`; `A` = totals of the currently accepted point): tolerance tests,
+// accept / reject, next candidate.  Returns true when the candidate was accepted (its totals are the accepted ones now).
+__device__ bool tr_after_eval(TrState& T, const double* tot, const double* A, const LmParams& prm, LmSummary* summary, bool writer) {
   ++T.num_evals;
   const double cand_cost = tot[27];
   double sn = 0;
@@ -320,20 +337,20 @@ __device__ void tr_after_eval(TrState& T, const double* tot, const LmParams& prm
   sn = sqrt(sn);
   const double cost_change = T.cost - cand_cost;
   if (sn <= prm.parameter_tolerance * (T.x_norm + prm.parameter_tolerance)) {
-    tr_trace(T, summary, writer, T.cost, 0, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 2; T.go = 0; return;
+    tr_trace(T, summary, writer, T.cost, 0, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 2; T.go = 0; return false;
   }
   if (fabs(cost_change) <= prm.function_tolerance * T.cost) {
-    tr_trace(T, summary, writer, T.cost, cost_change, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 3; T.go = 0; return;
+    tr_trace(T, summary, writer, T.cost, cost_change, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 3; T.go = 0; return false;
   }
   const double rho = cost_change / T.mcc;
-  if (rho > prm.min_relative_decrease) {
+  const bool accept = rho > prm.min_relative_decrease;
+  if (accept) {
     double xn = 0;
 #pragma unroll
     for (int k = 0; k < 7; ++k) { T.x[k] = T.xc[k]; xn += T.xc[k] * T.xc[k]; }
     T.x_norm = sqrt(xn);
-    tr_load_totals(T, tot);
     T.cost = cand_cost;
-    T.gmax = gradient_max(T.x, T.g, prm.gradient_tolerance);
+    T.gmax = gradient_max(T.x, tot + 21, prm.gradient_tolerance);
     T.last_successful = 1;
     ++T.num_successful;
     const double tq = 2.0 * rho - 1.0;
@@ -347,7 +364,8 @@ __device__ void tr_after_eval(TrState& T, const double* tot, const LmParams& prm
     T.reuse_diag = 1;
     tr_trace(T, summary, writer, T.cost, cost_change, T.gmax, sn, rho, T.radius, 1, 0);
   }
-  tr_next_candidate(T, prm, summary, writer);
+  tr_next_candidate(T, accept ? tot : A, prm, summary, writer);
+  return accept;
 }
 
 __device__ void tr_finish(const TrState& T, double* x7, LmSummary* summary) {
@@ -370,6 +388,14 @@ __device__ void tr_finish(const TrState& T, double* x7, LmSummary* summary) {
 //   CTA -> cluster : warp 0 PUSHES its vector into every CTA's shared memory (DSMEM stores), one cluster barrier, then
 //                    every CTA adds the 8 vectors it received in rank order => bit-identical totals everywhere.
 // `rb0` is this thread's first block, kept in registers across the passes of a solve.
+// Block b of a pass is evaluated by the thread with first_block_index == b mod (cluster threads).  Consecutive 32-block
+// chunks go round-robin over the CTAs (chunk c -> CTA c mod 8, warp c / 8): the association kernels write all edge
+// blocks first (3 residual rows each, ~2x the work of a plane block) and leave the unused slots at the end of each
+// section, so a CTA-major assignment would give three CTAs all the edges and the last CTAs nothing.
+__device__ __forceinline__ int first_block_index(unsigned crank, unsigned csize) {
+  return (int)(((threadIdx.x >> 5) * csize + crank) * 32u + (threadIdx.x & 31u));
+}
+
 constexpr int RS = 30;   // doubles per thread row of the transpose scratch (240 B: 16-byte aligned, bank-conflict free)
 template <typename Cluster>
 __device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRec* __restrict__ blocks, int n, const BlockRec& rb0,
@@ -377,7 +403,7 @@ __device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRe
                                                  double (*s_in)[8][32], double* s_tot, int& pass) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
-  const int gtid = (int)crank * NT + tid, gstride = (int)csize * NT;
+  const int gtid = first_block_index(crank, csize), gstride = (int)csize * NT;
   double x[7];
 #pragma unroll
   for (int k = 0; k < 7; ++k) x[k] = xs[k];
@@ -404,25 +430,29 @@ __device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRe
   double mine = 0.0;
   if (lane < RS) {
     const double* col = s_red + (size_t)(warp * 32) * RS + lane;
-    double s0 = 0.0, s1 = 0.0;
+    double s4[4] = {0.0, 0.0, 0.0, 0.0};   // four interleaved chains, then a fixed tree
 #pragma unroll
-    for (int r = 0; r < 32; r += 2) { s0 += col[r * RS]; s1 += col[(r + 1) * RS]; }
-    mine = s0 + s1;
+    for (int r = 0; r < 32; r += 4) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s4[q] += col[(r + q) * RS];
+    }
+    mine = (s4[0] + s4[1]) + (s4[2] + s4[3]);
   }
   s_part[warp][lane] = mine;
   __syncthreads();
   if (warp == 0) {
-    double v = 0.0;
-#pragma unroll
-    for (int w2 = 0; w2 < NW; ++w2) v += s_part[w2][lane];
+    static_assert(NW == 9, "fixed summation tree below is written for 9 warps");
+    const double v = ((s_part[0][lane] + s_part[1][lane]) + (s_part[2][lane] + s_part[3][lane])) +
+                     ((s_part[4][lane] + s_part[5][lane]) + (s_part[6][lane] + s_part[7][lane])) + s_part[8][lane];
     double* slot = &s_in[pass & 1][crank][lane];
     for (unsigned r = 0; r < csize; ++r) *cluster.map_shared_rank(slot, r) = v;
   }
   cluster.sync();   // release / acquire: every CTA's pushes of this pass are visible
   if (warp == 0) {
-    double t = 0.0;
-    for (unsigned r = 0; r < csize; ++r) t += s_in[pass & 1][r][lane];   // rank order => identical totals in every CTA
-    s_tot[lane] = t;
+    // rank order, fixed tree => identical totals in every CTA (the cluster size is 8 in every launch; ranks that do
+    // not exist would read zeros written at kernel start)
+    const double (*in)[32] = s_in[pass & 1];
+    s_tot[lane] = ((in[0][lane] + in[1][lane]) + (in[2][lane] + in[3][lane])) + ((in[4][lane] + in[5][lane]) + (in[6][lane] + in[7][lane]));
     __syncwarp();
   }
   ++pass;
@@ -431,7 +461,7 @@ __device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRe
 __device__ __forceinline__ BlockRec load_first_block(const BlockRec* __restrict__ blocks, int n, unsigned crank) {
   BlockRec rb;
   rb.type = -1;
-  const int gtid = (int)crank * NT + (int)threadIdx.x;
+  const int gtid = first_block_index(crank, 8);
   if (gtid < n) rb = blocks[gtid];
   return rb;
 }
@@ -462,7 +492,7 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
   extern __shared__ __align__(16) double s_red[];   // [NT][RS] transpose scratch
   __shared__ double s_part[NW][32];
   __shared__ double s_in[2][8][32];   // partial totals pushed by the 8 CTAs of the cluster, double-buffered by pass parity
-  __shared__ double s_tot[32];
+  __shared__ double s_tot[2][32];   // totals of the accepted point (T.acc_buf) and of the candidate being evaluated
   __shared__ double s_x[7];
   __shared__ TrState T;
   const int tid = threadIdx.x;
@@ -481,15 +511,19 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
   long long cyc_eval = 0, cyc_tr = 0;
   do {
     const long long c0 = clock64();
-    cluster_evaluate(cluster, blocks, n, rb0, first ? s_x : T.xc, prm.huber_a, s_red, s_part, s_in, s_tot, pass);
+    double* tot = s_tot[first ? 0 : 1 - T.acc_buf];
+    cluster_evaluate(cluster, blocks, n, rb0, first ? s_x : T.xc, prm.huber_a, s_red, s_part, s_in, tot, pass);
     const long long c1 = clock64();
     cyc_eval += c1 - c0;
     if (first && mode == 1) {
-      if (cluster.block_rank() == 0 && tid < 28) out28[tid] = s_tot[tid];
+      if (cluster.block_rank() == 0 && tid < 28) out28[tid] = tot[tid];
       return;   // all remote stores into this CTA preceded the cluster barrier inside cluster_evaluate
     }
     // thread 0 of EVERY CTA takes the same decision from the same totals (no broadcast needed)
-    if (tid == 0) { if (first) tr_start(T, s_x, s_tot, prm, summary, writer); else tr_after_eval(T, s_tot, prm, summary, writer); }
+    if (tid == 0) {
+      if (first) tr_start(T, s_x, tot, prm, summary, writer);
+      else if (tr_after_eval(T, tot, s_tot[T.acc_buf], prm, summary, writer)) T.acc_buf ^= 1;
+    }
     first = false;
     __syncthreads();
     cyc_tr += clock64() - c1;
@@ -562,8 +596,10 @@ __global__ void k_lm_tr_shard(void* state, const double* __restrict__ tot32, dou
                               LmParams prm, LmSummary* __restrict__ summary) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   TrState& T = *reinterpret_cast<TrState*>(state);
-  if (first) tr_start(T, x7, tot32, prm, summary, true);
-  else if (T.go) tr_after_eval(T, tot32, prm, summary, true);
+  bool keep = false;
+  if (first) { tr_start(T, x7, tot32, prm, summary, true); keep = true; }
+  else if (T.go) keep = tr_after_eval(T, tot32, T.acc, prm, summary, true);
+  if (keep) { for (int k = 0; k < 28; ++k) T.acc[k] = tot32[k]; }
   if (last || !T.go) {
     if (last && T.go) { T.go = 0; }   // cannot happen: the schedule covers max_iters evaluations
     tr_finish(T, x7, summary);
