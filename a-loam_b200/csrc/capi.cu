@@ -54,6 +54,8 @@ int aloam_destroy(aloam_ctx* c) {
   if (c->s_ext) { cudaStreamSynchronize(c->s_ext); cudaStreamDestroy(c->s_ext); }
   if (c->s_h2d) { cudaStreamSynchronize(c->s_h2d); cudaStreamDestroy(c->s_h2d); }
   if (c->s_exa) { cudaStreamSynchronize(c->s_exa); cudaStreamDestroy(c->s_exa); }
+  if (c->s_idx) { cudaStreamSynchronize(c->s_idx); cudaStreamDestroy(c->s_idx); }
+  for (cudaEvent_t e : c->ev_idx) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_a) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_b) if (e) cudaEventDestroy(e);
   if (c->d_full2) cudaFree(c->d_full2);
@@ -126,7 +128,8 @@ int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
   for (cudaEvent_t& e : c->prof_ev) TRY(cudaEventCreate(&e));
   TRY(dalloc(&c->d_raw, mp * 8)); TRY(dalloc(&c->d_raw2, mp * 8));
   TRY(cudaStreamCreateWithFlags(&c->s_ext, cudaStreamNonBlocking)); TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
-  TRY(cudaStreamCreateWithFlags(&c->s_exa, cudaStreamNonBlocking));
+  TRY(cudaStreamCreateWithFlags(&c->s_exa, cudaStreamNonBlocking)); TRY(cudaStreamCreateWithFlags(&c->s_idx, cudaStreamNonBlocking));
+  for (cudaEvent_t& e : c->ev_idx) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (cudaEvent_t& e : c->ev_a) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (cudaEvent_t& e : c->ev_b) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   TRY(dalloc(&c->d_full2, mp)); TRY(dalloc(&c->d_ring_start2, 72));
@@ -391,6 +394,7 @@ int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, i
   CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_h2d, c->ev0, 0));
   CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_exa, c->ev0, 0));
   CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev0, 0));
+  CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_idx, c->ev0, 0));
   for (int k = 0; k < n_scans; ++k) {
     const int f = c->frame;                 // global frame number of this scan
     const int b = k & 1;                    // raw / ring-major double buffer
@@ -413,21 +417,26 @@ int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, i
     int rc = run_features_a(c, d_raw, raws[k].n, device_resident ? 4 : raws[k].stride_floats, b, &sc_slot);
     if (!device_resident) cudaEventRecord(c->ev_rawfree[b], c->s_exa);
     cudaEventRecord(c->ev_a[b], c->s_exa);
-    // ---- stage B (per-ring features + index build) on s_ext: needs stage A of this scan, and its output slot
-    //      feat[f % 3] free: that slot was last read by the odometry of frame f-2 (as its "last" clouds)
+    // ---- stage B (per-ring features) on s_ext: needs stage A of this scan, and its output slot feat[f % 3] free: that
+    //      slot was last read by the odometry of frame f-2 (as its "last" clouds)
     c->stream = c->s_ext;
     if (!rc) {
       CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_a[b], 0));
       CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_odo[(f + 1) % 3], 0));
       rc = run_features_b(c, b, sc_slot, cur);
       cudaEventRecord(c->ev_b[b], c->s_ext);
-      run_grid_build(c, cur, 64 * kMaxLessSharpPerRing, std::min(raws[k].n, c->max_points));
       cudaEventRecord(c->ev_feat[f % 3], c->s_ext);
+      // ---- stage C (search index over the less-sharp / less-flat clouds) on s_idx: only the NEXT scan's odometry needs it
+      c->stream = c->s_idx;
+      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_idx, c->ev_feat[f % 3], 0));
+      run_grid_build(c, cur, 64 * kMaxLessSharpPerRing, std::min(raws[k].n, c->max_points));
+      cudaEventRecord(c->ev_idx[f % 3], c->s_idx);
     }
     c->stream = s_main;
     if (rc) return rc;
-    // ---- association + LM on the main stream
+    // ---- association + LM on the main stream: this scan's sharp / flat points, the previous scan's clouds + index
     CUDA_CHECK_RET(cudaStreamWaitEvent(s_main, c->ev_feat[f % 3], 0));
+    CUDA_CHECK_RET(cudaStreamWaitEvent(s_main, c->ev_idx[(f + 2) % 3], 0));
     // the last solve of the scan writes the integrated world pose into its slot of d_poses (no copy on the critical chain)
     if (f > 0) run_register(c, cur, last, kFusedSharpSlots, kFusedFlatSlots, true, nullptr, c->d_poses + (size_t)k * 7);
     else CUDA_CHECK_RET(cudaMemcpyAsync(c->d_poses + (size_t)k * 7, c->d_world, 56, cudaMemcpyDeviceToDevice, s_main));
@@ -442,6 +451,7 @@ int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, i
   CUDA_CHECK_RET(cudaStreamSynchronize(s_main));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->s_ext));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->s_exa));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->s_idx));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->s_h2d));
   CUDA_CHECK_RET(cudaGetLastError());
   prof_collect(c);

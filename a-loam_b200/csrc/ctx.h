@@ -72,8 +72,8 @@ struct aloam_ctx {
   int *d_vox_hist = nullptr, *d_vox_offs = nullptr, *d_vox_misc = nullptr;
   // pipelined scan stream (aloam_scan_stream): extraction + index build on s_ext, association + LM on `stream`,
   // host->device copies of the raw scans on s_h2d, all chained by events
-  cudaStream_t s_ext = nullptr, s_exa = nullptr, s_h2d = nullptr;
-  cudaEvent_t ev_feat[3] = {}, ev_odo[3] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {}, ev_a[2] = {}, ev_b[2] = {};
+  cudaStream_t s_ext = nullptr, s_exa = nullptr, s_idx = nullptr, s_h2d = nullptr;
+  cudaEvent_t ev_feat[3] = {}, ev_idx[3] = {}, ev_odo[3] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {}, ev_a[2] = {}, ev_b[2] = {};
   float* d_raw2 = nullptr;       // second raw-scan staging buffer
   double* h_poses = nullptr;     // pinned [kMaxStreamScans][7]
   double* d_poses = nullptr;     // device [kMaxStreamScans][7]: per-scan world poses of a stream call (one D2H at the end)
@@ -141,6 +141,8 @@ void launch_ex(aloam_ctx* c, int kid, K kernel, dim3 grid, dim3 block, size_t sm
   prof_end(c);
 }
 
+#define LAUNCH_PDL(c, kid, kernel, grid, block, smem, ...) launch_ex(c, kid, kernel, dim3(grid), dim3(block), smem, 1, true, __VA_ARGS__)
+
 // the LM kernel runs as one thread-block cluster (distributed-shared-memory reduction, see lm.cu)
 constexpr int kLmCluster = 8;
 template <typename... Args>
@@ -198,9 +200,9 @@ int run_features_a(aloam_ctx* c, const float* d_raw, int n, int stride, int buf,
   Pt4* full = buf ? c->d_full2 : c->d_full;
   int* rstart = buf ? c->d_ring_start2 : c->d_ring_start;
   LAUNCH(c, KID_CLASSIFY, k_classify, nb, 256, 0, d_raw, n, stride, c->cfg.n_scans, thres * thres, c->d_ring, c->d_hist, sc);
-  LAUNCH(c, KID_RING_SCAN, k_ring_scan, 1, 1024, 0, d_raw, stride, nb, c->cfg.n_scans, c->d_hist, c->d_offsets, rstart,
+  LAUNCH_PDL(c, KID_RING_SCAN, k_ring_scan, 1, 1024, 0, d_raw, stride, nb, c->cfg.n_scans, c->d_hist, c->d_offsets, rstart,
          c->d_scan_start, c->d_scan_end, sc, sc_next);
-  LAUNCH(c, KID_SCATTER, k_scatter, nb, 256, 0, d_raw, n, stride, c->d_ring, c->d_offsets, sc, full);
+  LAUNCH_PDL(c, KID_SCATTER, k_scatter, nb, 256, 0, d_raw, n, stride, c->d_ring, c->d_offsets, sc, full);
   *sc_slot = c->parity;
   c->parity = (c->parity + 1) % 3;
   CUDA_CHECK_RET(cudaGetLastError());
@@ -211,7 +213,7 @@ int run_features_b(aloam_ctx* c, int buf, int sc_slot, FeatBuf& out) {
   int* rstart = buf ? c->d_ring_start2 : c->d_ring_start;
   LAUNCH(c, KID_RING_FEATURES, k_ring_features, c->cfg.n_scans, 256, ring_features_smem_bytes(), full, rstart,
          c->cfg.n_scans, 0.2f, c->st_sharp, c->st_less_sharp, c->st_flat, c->st_less_flat, c->st_counts, c->d_curv, c->d_label, c->d_sc + sc_slot);
-  LAUNCH(c, KID_COMPACT, k_compact, c->cfg.n_scans, 128, 0, c->cfg.n_scans, c->st_sharp, c->st_less_sharp, c->st_flat,
+  LAUNCH_PDL(c, KID_COMPACT, k_compact, c->cfg.n_scans, 128, 0, c->cfg.n_scans, c->st_sharp, c->st_less_sharp, c->st_flat,
          c->st_less_flat, c->st_counts, out.sharp, out.less_sharp, out.flat, out.less_flat, out.counts, out.rs_ls, out.rs_lf);
   CUDA_CHECK_RET(cudaGetLastError());
   return ALOAM_OK;
@@ -227,8 +229,8 @@ int run_features(aloam_ctx* c, const float* d_raw, int n, int stride, FeatBuf& o
 void run_grid_build(aloam_ctx* c, FeatBuf& f, int n_ls, int n_lf) {
   const int pb = (std::max(std::max(n_ls, n_lf), 1) + 255) / 256;
   LAUNCH(c, KID_GRID_BUILD, k_rab_count, dim3(pb, 2), 256, 0, f.g_ls, f.less_sharp, f.counts + 1, f.g_lf, f.less_flat, f.counts + 3);
-  LAUNCH(c, KID_GRID_BUILD, k_rab_scan, 2, 1024, 0, f.g_ls, f.g_lf);
-  LAUNCH(c, KID_GRID_BUILD, k_rab_fill, dim3(pb, 2), 256, 0, f.g_ls, f.less_sharp, f.counts + 1, f.g_lf, f.less_flat, f.counts + 3);
+  LAUNCH_PDL(c, KID_GRID_BUILD, k_rab_scan, 2, 1024, 0, f.g_ls, f.g_lf);
+  LAUNCH_PDL(c, KID_GRID_BUILD, k_rab_fill, dim3(pb, 2), 256, 0, f.g_ls, f.less_sharp, f.counts + 1, f.g_lf, f.less_flat, f.counts + 3);
 }
 
 // outer_iters x (association + LM) ; `cur` supplies sharp/flat, `last` the targets ; pose in c->d_pose

@@ -75,6 +75,7 @@ __device__ __forceinline__ float ori_first_half(float x, float y, float start_or
 __global__ void __launch_bounds__(CT) k_classify(const float* __restrict__ raw, int n, int stride, int n_scans,
                                                  float thres2, int8_t* __restrict__ ring_out,
                                                  int* __restrict__ hist, ScanScalars* __restrict__ sc) {
+  pdl_launch_dependents();   // the next kernel of the stream may become resident (it blocks in pdl_wait())
   __shared__ int s_hist[64];
   __shared__ int s_first, s_last, s_half;
   const int tid = threadIdx.x;
@@ -135,6 +136,8 @@ __global__ void __launch_bounds__(1024) k_ring_scan(const float* __restrict__ ra
                                                     int* __restrict__ offsets, int* __restrict__ ring_start,
                                                     int* __restrict__ scan_start, int* __restrict__ scan_end,
                                                     ScanScalars* __restrict__ sc, ScanScalars* __restrict__ sc_next) {
+  pdl_launch_dependents();
+  pdl_wait();   // launched with a programmatic dependency on the previous kernel of the stream
   __shared__ int s_tot[64];
   __shared__ int s_start[65];
   const int t = threadIdx.x, r = t >> 4, s = t & 15;
@@ -195,6 +198,8 @@ __global__ void __launch_bounds__(1024) k_ring_scan(const float* __restrict__ ra
 __global__ void __launch_bounds__(CT) k_scatter(const float* __restrict__ raw, int n, int stride,
                                                 const int8_t* __restrict__ ring_in, const int* __restrict__ offsets,
                                                 const ScanScalars* __restrict__ sc, Pt4* __restrict__ full) {
+  pdl_launch_dependents();
+  pdl_wait();   // launched with a programmatic dependency on the previous kernel of the stream
   __shared__ int s_cnt[ITERS * (CT / 32)][64];  // [slot = it*8 + warp][ring], then exclusive prefix over slots
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   for (int k = tid; k < ITERS * (CT / 32) * 64; k += CT) (&s_cnt[0][0])[k] = 0;
@@ -435,6 +440,7 @@ __global__ void __launch_bounds__(256) k_ring_features(const Pt4* __restrict__ f
                                                        Pt4* __restrict__ st_less_flat, int* __restrict__ st_counts,
                                                        float* __restrict__ dbg_curv, int8_t* __restrict__ dbg_label,
                                                        ScanScalars* __restrict__ sc) {
+  pdl_launch_dependents();   // the next kernel of the stream may become resident (it blocks in pdl_wait())
   extern __shared__ __align__(16) unsigned char smem[];
   Pt4* pts = reinterpret_cast<Pt4*>(smem);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + (size_t)MAXR * 16);
@@ -677,6 +683,8 @@ __global__ void __launch_bounds__(128) k_compact(int n_scans, const Pt4* __restr
                                                  Pt4* __restrict__ flat, Pt4* __restrict__ less_flat,
                                                  int* __restrict__ counts, int* __restrict__ rs_less_sharp,
                                                  int* __restrict__ rs_less_flat) {
+  pdl_launch_dependents();
+  pdl_wait();   // launched with a programmatic dependency on the previous kernel of the stream
   __shared__ int s_off[4];
   const int ring = blockIdx.x, tid = threadIdx.x;
   if (tid < 4) {

@@ -55,6 +55,7 @@ __device__ __forceinline__ int bucket_of(float x, float y) {
 // blockIdx.y selects the cloud (0 = a, 1 = b)
 __global__ void k_rab_count(RabIndex a, const Pt4* __restrict__ pa, const int* __restrict__ na, RabIndex b,
                             const Pt4* __restrict__ pb, const int* __restrict__ nb) {
+  pdl_launch_dependents();   // the next kernel of the stream may become resident (it blocks in pdl_wait())
   const RabIndex& g = blockIdx.y == 0 ? a : b;
   const Pt4* __restrict__ pts = blockIdx.y == 0 ? pa : pb;
   const int n = blockIdx.y == 0 ? *na : *nb;
@@ -69,6 +70,8 @@ __global__ void k_rab_count(RabIndex a, const Pt4* __restrict__ pa, const int* _
 
 // one CTA per cloud: exclusive scan of the ALOAM_NB*64 cell counts -> start[], and reset the counts for the next build
 __global__ void __launch_bounds__(1024) k_rab_scan(RabIndex a, RabIndex b) {
+  pdl_launch_dependents();
+  pdl_wait();   // launched with a programmatic dependency on the previous kernel of the stream
   const RabIndex& g = blockIdx.x == 0 ? a : b;
   constexpr int NC = ALOAM_NB * 64, PER = NC / 1024;
   __shared__ int s_w[32];
@@ -96,6 +99,8 @@ __global__ void __launch_bounds__(1024) k_rab_scan(RabIndex a, RabIndex b) {
 
 __global__ void k_rab_fill(RabIndex a, const Pt4* __restrict__ pa, const int* __restrict__ na, RabIndex b,
                            const Pt4* __restrict__ pb, const int* __restrict__ nb) {
+  pdl_launch_dependents();
+  pdl_wait();   // launched with a programmatic dependency on the previous kernel of the stream
   const RabIndex& g = blockIdx.y == 0 ? a : b;
   const Pt4* __restrict__ pts = blockIdx.y == 0 ? pa : pb;
   const int n = blockIdx.y == 0 ? *na : *nb;
