@@ -7,11 +7,14 @@
 //   The order of points inside a cell depends on atomic timing, but every search below compares candidates on
 //   (distance, original index / visiting rank), so results are a pure function of the input.
 // Search = ONE WARP PER QUERY, exact.  The clouds live in the sensor frame of the last scan, so a point whose
-//   azimuth differs from the query's by at least a has distance >= rho_q * sin(a) from it.  The warp streams the
-//   query's own bucket, then buckets +-1, +-2, ... with coalesced float4 loads (4 in flight per lane) and REDUX
-//   arg-min; after +-k buckets a best distance below rho_q*sin(k*w) is final.  The sweep stops at the latest when
-//   that bound exceeds the reference's own threshold (DISTANCE_SQ_THRESHOLD = 25 m^2), beyond which the reference
-//   discards the match anyway, or when the whole circle has been read.
+//   azimuth differs from the query's by at least a has distance >= rho_q * sin(a) from it.  After buckets bq-k..bq+k
+//   have been read a best distance below rho_q*sin(k*w) is final.  The kernel is bound by DEPENDENT L2 round trips
+//   (cell table -> points -> decision), not by bytes, so the first sweep reads the whole interval bq-k0..bq+k0 at
+//   once -- it is one contiguous slice of the bucket-major array: one round for its two delimiters, then 12 coalesced
+//   float4 loads in flight per lane -- with k0 = 1 (3 for rho < 6.5 m, where a bucket is narrower than the point
+//   spacing); 98 % of the queries end there.  The rest grow the interval bucket by bucket.  The sweep stops at the
+//   latest when the bound exceeds the reference's own threshold (DISTANCE_SQ_THRESHOLD = 25 m^2), beyond which the
+//   reference discards the match anyway, or when the whole circle has been read.
 // The 2nd / 3rd correspondence points of :312-361 / :402-455 use the same sweep restricted to the ring slice
 // rc-2..rc+2, with candidates ranked by the reference's visiting order (forward ascending first, then backward
 // descending, strict '<'), so ties resolve exactly as the sequential loops do.
@@ -140,6 +143,79 @@ __device__ __forceinline__ void visit_ring_step(const RabIndex& g, int bq, int k
   if (b1 != b0) visit_cells(g, b1 * 64 + r_lo, b1 * 64 + r_hi, f);
 }
 
+// f over gpts[e0, e1) with kBatch loads in flight per lane.  Out-of-range slots are clamped to the last element, so
+// a point may be visited more than once: every visitor in this file is idempotent (strict minimum on (d2, key)).
+constexpr int kBatch = 12;
+template <typename F>
+__device__ __forceinline__ void visit_span(const float4* __restrict__ gpts, int e0, int e1, F&& f) {
+  if (e0 >= e1) return;
+  const int lane = (int)lane_id(), last = e1 - 1;
+  int base = e0;
+  while (e1 - base > 128) {
+    float4 p[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) p[i] = __ldg(gpts + min(base + lane + 32 * i, last));
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) f(p[i].x, p[i].y, p[i].z, __float_as_int(p[i].w));
+    base += 32 * kBatch;
+    if (base >= e1) return;
+  }
+  float4 p[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __ldg(gpts + min(base + lane + 32 * i, last));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f(p[i].x, p[i].y, p[i].z, __float_as_int(p[i].w));
+}
+
+// All rings of the azimuth buckets lo..hi (lo <= hi, indices may run past either end of the circle) are at most two
+// contiguous slices of gpts: [a0, a1) and [b0, b1).  Their four delimiters are fetched in ONE round.
+struct Spans2 { int a0, a1, b0, b1; };
+__device__ __forceinline__ Spans2 bucket_interval(const RabIndex& g, int lo, int hi) {
+  int c0, c1, c2 = 0, c3 = 0;
+  if (hi - lo + 1 >= ALOAM_NB) { c0 = 0; c1 = ALOAM_NB * 64; }
+  else if (lo < 0) { c0 = (lo + ALOAM_NB) * 64; c1 = ALOAM_NB * 64; c3 = (hi + 1) * 64; }
+  else if (hi >= ALOAM_NB) { c0 = lo * 64; c1 = ALOAM_NB * 64; c3 = (hi - ALOAM_NB + 1) * 64; }
+  else { c0 = lo * 64; c1 = (hi + 1) * 64; }
+  const int lane = (int)lane_id();
+  const int v = g.start[lane == 0 ? c0 : lane == 1 ? c1 : lane == 2 ? c2 : c3];
+  Spans2 s;
+  s.a0 = __shfl_sync(0xffffffffu, v, 0); s.a1 = __shfl_sync(0xffffffffu, v, 1);
+  s.b0 = __shfl_sync(0xffffffffu, v, 2); s.b1 = __shfl_sync(0xffffffffu, v, 3);
+  return s;
+}
+
+// Ring slice [r_lo, r_hi] of each of the buckets bq-k..bq+k (k <= kMaxK0): 2k+1 short slices.  One round for all the
+// delimiters, one round for the first 32 points of every slice, then whatever is left of slices longer than 32.
+constexpr int kMaxK0 = 3;
+template <typename F>
+__device__ __forceinline__ void visit_ring_slices(const RabIndex& g, int bq, int k, int r_lo, int r_hi, F&& f) {
+  const int lane = (int)lane_id();
+  const int nb = 2 * k + 1;
+  int v = 0;
+  if (lane < 2 * nb) {
+    const int b = (bq - k + (lane >> 1) + ALOAM_NB) % ALOAM_NB;
+    v = g.start[b * 64 + ((lane & 1) ? r_hi + 1 : r_lo)];
+  }
+  int e0[2 * kMaxK0 + 1], e1[2 * kMaxK0 + 1];
+  float4 p[2 * kMaxK0 + 1];
+#pragma unroll
+  for (int j = 0; j < 2 * kMaxK0 + 1; ++j) {
+    e0[j] = __shfl_sync(0xffffffffu, v, 2 * j);
+    e1[j] = __shfl_sync(0xffffffffu, v, 2 * j + 1);
+    if (j >= nb) e1[j] = e0[j];   // lanes past 2*nb hold 0 => empty anyway; explicit for clarity
+    if (e0[j] < e1[j]) p[j] = __ldg(g.gpts + min(e0[j] + lane, e1[j] - 1));
+  }
+#pragma unroll
+  for (int j = 0; j < 2 * kMaxK0 + 1; ++j) {
+    if (e0[j] < e1[j]) {
+      f(p[j].x, p[j].y, p[j].z, __float_as_int(p[j].w));
+      if (e1[j] - e0[j] > 32) visit_span(g.gpts, e0[j] + 32, e1[j], f);
+    }
+  }
+}
+
+__device__ __forceinline__ int first_halfwidth(float rho) { return rho < 6.5f ? kMaxK0 : 1; }
+
 // After buckets bq-k .. bq+k have been seen, every unseen point is at azimuth distance >= k*w from q, hence at
 // distance >= rho_q * sin(k*w) (k*w < pi/2).  1e-4 rad absorbs atan2f / bucket rounding.  Returns the squared safe radius.
 __device__ __forceinline__ float safe_radius_sq(float rho_q, int k) {
@@ -172,26 +248,31 @@ __device__ __forceinline__ void store_none(BlockRec* b, int* corr) {
 
 constexpr int kBig = 1 << 25;       // separates forward ranks [0, 2^24) from backward ranks
 
-// exact nearest neighbour of q with d2 < limit (strict); returns index or -1, d2 in out_d.  Ties -> smaller index.
-__device__ __forceinline__ int rab_nearest(const RabIndex& g, float qx, float qy, float qz, float limit, float& out_d) {
+// exact nearest neighbour of q with d2 < limit (strict); returns its packed word (ring << 24 | index) or -1, d2 in out_d,
+// the half-width of the bucket interval it had to read in k_out.  Ties -> smaller index (the cloud is ring-major, so
+// packed order == index order).
+__device__ __forceinline__ int rab_nearest(const RabIndex& g, float qx, float qy, float qz, float limit, float& out_d, int& k_out) {
   const int bq = bucket_of(qx, qy);
   const float rho = sqrtf(qx * qx + qy * qy);
   float best_d = limit; int best_i = INT_MAX;
   float wd = FLT_MAX; int wi = INT_MAX;
   auto f = [&](float x, float y, float z, int packed) {
     const float d2 = sqdist3(x, y, z, qx, qy, qz);
-    const int idx = packed & 0xffffff;
-    if (d2 < best_d || (d2 == best_d && best_i != INT_MAX && idx < best_i)) { best_d = d2; best_i = idx; }
+    if (d2 < best_d || (d2 == best_d && best_i != INT_MAX && packed < best_i)) { best_d = d2; best_i = packed; }
   };
-  visit_ring_step(g, bq, 0, 0, 63, f);
-  for (int k = 1; 2 * k <= ALOAM_NB; ++k) {
-    visit_ring_step(g, bq, k, 0, 63, f);
+  int k = first_halfwidth(rho);
+  const Spans2 sp = bucket_interval(g, bq - k, bq + k);
+  visit_span(g.gpts, sp.a0, sp.a1, f);
+  visit_span(g.gpts, sp.b0, sp.b1, f);
+  for (;;) {
     wd = best_i == INT_MAX ? FLT_MAX : best_d; wi = best_i;
     warp_argmin(wd, wi);
     const float safe2 = safe_radius_sq(rho, k);
-    if ((wi != INT_MAX && wd < safe2) || safe2 >= limit) break;
+    if ((wi != INT_MAX && wd < safe2) || safe2 >= limit || 2 * (k + 1) > ALOAM_NB) break;
+    ++k;
+    visit_ring_step(g, bq, k, 0, 63, f);
   }
-  if (wi == INT_MAX) { wd = best_i == INT_MAX ? FLT_MAX : best_d; wi = best_i; warp_argmin(wd, wi); }
+  k_out = k;
   out_d = wd;
   return (wi == INT_MAX || wd == FLT_MAX) ? -1 : wi;
 }
@@ -224,9 +305,11 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
 
   // nearest neighbour (kdtree*Last->nearestKSearch(pointSel, 1, ...), :302,390) then `< DISTANCE_SQ_THRESHOLD`
   float d1;
-  const int closest = rab_nearest(g, qx, qy, qz, thr, d1);
-  if (closest < 0 || !((double)d1 < prm.dist_sq_thresh)) { if (lane == 0) store_none(out, co); return; }
-  const int rc = (int)L.pts[closest].i;  // closestPointScanID
+  int k_nn;
+  const int packed1 = rab_nearest(g, qx, qy, qz, thr, d1, k_nn);
+  if (packed1 < 0 || !((double)d1 < prm.dist_sq_thresh)) { if (lane == 0) store_none(out, co); return; }
+  const int closest = packed1 & 0xffffff;
+  const int rc = packed1 >> 24;  // closestPointScanID = int(intensity) of the closest point (k_rab_fill packs it)
   // rings rc-up .. rc+up survive the `> rc + NEARBY_SCAN` / `< rc - NEARBY_SCAN` break tests (:319,345,405,433)
   int up = 0; while ((double)(rc + up + 1) <= (double)rc + prm.nearby_scan) ++up;
 
@@ -254,9 +337,9 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
         else { if (d2 < b3 || (d2 == b3 && r3 != INT_MAX && rank < r3)) { b3 = d2; r3 = rank; } }
       }
     };
-    visit_ring_step(g, bq, 0, r_lo, r_hi, f);
-    for (int k = 1; 2 * k <= ALOAM_NB; ++k) {
-      visit_ring_step(g, bq, k, r_lo, r_hi, f);
+    int k = min(k_nn, kMaxK0);
+    visit_ring_slices(g, bq, k, r_lo, r_hi, f);
+    for (;;) {
       w2 = r2 == INT_MAX ? FLT_MAX : b2; k2 = r2; warp_argmin(w2, k2);
       const float safe2 = safe_radius_sq(rho, k);
       bool done = k2 != INT_MAX && w2 < safe2;
@@ -264,10 +347,10 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
         w3 = r3 == INT_MAX ? FLT_MAX : b3; k3 = r3; warp_argmin(w3, k3);
         done = done && k3 != INT_MAX && w3 < safe2;
       }
-      if (done || safe2 >= thr) break;
+      if (done || safe2 >= thr || 2 * (k + 1) > ALOAM_NB) break;
+      ++k;
+      visit_ring_step(g, bq, k, r_lo, r_hi, f);
     }
-    if (k2 == INT_MAX) { w2 = r2 == INT_MAX ? FLT_MAX : b2; k2 = r2; warp_argmin(w2, k2); }
-    if (!is_corner && k3 == INT_MAX) { w3 = r3 == INT_MAX ? FLT_MAX : b3; k3 = r3; warp_argmin(w3, k3); }
   }
   // rank -> index
   int j2 = -1, j3 = -1;
@@ -316,7 +399,9 @@ __global__ void __launch_bounds__(256) k_knn_last(LastCloud cloud, const Pt4* __
   if (wid >= nq) return;
   const Pt4 q = queries[wid];
   float d;
-  const int j = rab_nearest(cloud.index, q.x, q.y, q.z, FLT_MAX, d);
+  int k_used;
+  const int packed = rab_nearest(cloud.index, q.x, q.y, q.z, FLT_MAX, d, k_used);
+  const int j = packed < 0 ? -1 : (packed & 0xffffff);
   if (lane_id() == 0) { idx[wid] = j; sqd[wid] = j < 0 ? __int_as_float(0x7f800000) : d; }
 }
 
