@@ -16,7 +16,7 @@ namespace {
 constexpr int kMaxSharpPerRing = 12, kMaxLessSharpPerRing = 120, kMaxFlatPerRing = 24;
 constexpr int kFusedSharpSlots = 64 * kMaxSharpPerRing;  // 768
 constexpr int kFusedFlatSlots = 64 * kMaxFlatPerRing;    // 1536
-constexpr int kMaxQueries = 16384;
+constexpr int kMaxQueries = ALOAM_MAX_QUERIES;
 constexpr int kMaxStreamScans = 4096;                   // scans per aloam_scan_stream call                       // API-path capacity for sharp / flat query clouds
 
 struct FeatBuf {

@@ -57,6 +57,7 @@ struct __align__(8) BlockRec {
   int type;      // 0 edge, 1 plane, 2 plane-norm, -1 = no residual (query without correspondence)
   int pad;
 };
+#define ALOAM_MAX_QUERIES 16384   // capacity of the sharp / flat query buffers (ctx.h kMaxQueries)
 struct OdomParams { double dist_sq_thresh; double nearby_scan; };
 __global__ void k_odom_assoc(const Pt4* sharp, const Pt4* flat, const int* feat_counts /*[4]*/, LastCloud corner,
                              LastCloud surf, const double* pose7, OdomParams prm, BlockRec* blocks,

@@ -118,53 +118,39 @@ __global__ void k_rab_fill(RabIndex a, const Pt4* __restrict__ pa, const int* __
 // search
 namespace {
 
-// f(x, y, z, packed) for every point of cells [cell_lo, cell_hi] (a contiguous slice of gpts); coalesced, 4 loads in flight
-template <typename F>
-__device__ __forceinline__ void visit_cells(const RabIndex& g, int cell_lo, int cell_hi, F&& f) {
-  const int lane = (int)lane_id();
-  const int e0 = g.start[cell_lo], e1 = g.start[cell_hi + 1];
-  int e = e0 + lane;
-  for (; e + 96 < e1; e += 128) {
-    const float4 p0 = __ldg(g.gpts + e), p1 = __ldg(g.gpts + e + 32), p2 = __ldg(g.gpts + e + 64), p3 = __ldg(g.gpts + e + 96);
-    f(p0.x, p0.y, p0.z, __float_as_int(p0.w)); f(p1.x, p1.y, p1.z, __float_as_int(p1.w));
-    f(p2.x, p2.y, p2.z, __float_as_int(p2.w)); f(p3.x, p3.y, p3.z, __float_as_int(p3.w));
-  }
-  for (; e < e1; e += 32) {
-    const float4 p = __ldg(g.gpts + e);
-    f(p.x, p.y, p.z, __float_as_int(p.w));
-  }
-}
-
-// Visit ring slice [r_lo, r_hi] of azimuth buckets bq-k and bq+k (k == 0: bucket bq only; the two coincide when 2k == NB)
-template <typename F>
-__device__ __forceinline__ void visit_ring_step(const RabIndex& g, int bq, int k, int r_lo, int r_hi, F&& f) {
-  const int b0 = (bq - k + ALOAM_NB) % ALOAM_NB, b1 = (bq + k) % ALOAM_NB;
-  visit_cells(g, b0 * 64 + r_lo, b0 * 64 + r_hi, f);
-  if (b1 != b0) visit_cells(g, b1 * 64 + r_lo, b1 * 64 + r_hi, f);
-}
-
-// f over gpts[e0, e1) with kBatch loads in flight per lane.  Out-of-range slots are clamped to the last element, so
-// a point may be visited more than once: every visitor in this file is idempotent (strict minimum on (d2, key)).
-constexpr int kBatch = 12;
-template <typename F>
+// The visitors below are written for CODE SIZE as much as for loads in flight: every call site of the visitor lambda is
+// inlined, the kernel runs for ~10 us on a cold instruction cache, and an earlier version with ~120 inlined copies of
+// the lambda (13 k SASS instructions) spent more time fetching instructions than data.  Each helper has exactly one
+// batch of B inlined copies inside a loop that is not unrolled.
+//
+// f(x, y, z, packed) over gpts[e0, e1) with B coalesced float4 loads in flight per lane.  Out-of-range slots are clamped
+// to the last element, so a point may be visited more than once: every visitor in this file is idempotent (strict
+// minimum on (d2, key)).
+template <int B, typename F>
 __device__ __forceinline__ void visit_span(const float4* __restrict__ gpts, int e0, int e1, F&& f) {
   if (e0 >= e1) return;
   const int lane = (int)lane_id(), last = e1 - 1;
-  int base = e0;
-  while (e1 - base > 128) {
-    float4 p[kBatch];
+#pragma unroll 1
+  for (int base = e0; base < e1; base += 32 * B) {
+    float4 p[B];
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i) p[i] = __ldg(gpts + min(base + lane + 32 * i, last));
+    for (int i = 0; i < B; ++i) p[i] = __ldg(gpts + min(base + lane + 32 * i, last));
 #pragma unroll
-    for (int i = 0; i < kBatch; ++i) f(p[i].x, p[i].y, p[i].z, __float_as_int(p[i].w));
-    base += 32 * kBatch;
-    if (base >= e1) return;
+    for (int i = 0; i < B; ++i) f(p[i].x, p[i].y, p[i].z, __float_as_int(p[i].w));
   }
-  float4 p[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p[i] = __ldg(gpts + min(base + lane + 32 * i, last));
-#pragma unroll
-  for (int i = 0; i < 4; ++i) f(p[i].x, p[i].y, p[i].z, __float_as_int(p[i].w));
+}
+
+// Ring slice [r_lo, r_hi] of azimuth buckets bq-k and bq+k (the two coincide when 2k == NB): the growth step of a sweep
+// whose first interval was not enough (2 % of the queries)
+template <typename F>
+__device__ __forceinline__ void visit_ring_step(const RabIndex& g, int bq, int k, int r_lo, int r_hi, F&& f) {
+  const int b0 = (bq - k + ALOAM_NB) % ALOAM_NB, b1 = (bq + k) % ALOAM_NB;
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    if (side && b1 == b0) break;
+    const int b = side ? b1 : b0;
+    visit_span<4>(g.gpts, g.start[b * 64 + r_lo], g.start[b * 64 + r_hi + 1], f);
+  }
 }
 
 // All rings of the azimuth buckets lo..hi (lo <= hi, indices may run past either end of the circle) are at most two
@@ -196,21 +182,21 @@ __device__ __forceinline__ void visit_ring_slices(const RabIndex& g, int bq, int
     const int b = (bq - k + (lane >> 1) + ALOAM_NB) % ALOAM_NB;
     v = g.start[b * 64 + ((lane & 1) ? r_hi + 1 : r_lo)];
   }
-  int e0[2 * kMaxK0 + 1], e1[2 * kMaxK0 + 1];
   float4 p[2 * kMaxK0 + 1];
+  unsigned valid = 0, longer = 0;
 #pragma unroll
   for (int j = 0; j < 2 * kMaxK0 + 1; ++j) {
-    e0[j] = __shfl_sync(0xffffffffu, v, 2 * j);
-    e1[j] = __shfl_sync(0xffffffffu, v, 2 * j + 1);
-    if (j >= nb) e1[j] = e0[j];   // lanes past 2*nb hold 0 => empty anyway; explicit for clarity
-    if (e0[j] < e1[j]) p[j] = __ldg(g.gpts + min(e0[j] + lane, e1[j] - 1));
+    const int e0 = __shfl_sync(0xffffffffu, v, 2 * j), e1 = __shfl_sync(0xffffffffu, v, 2 * j + 1);   // 0, 0 past nb
+    if (e0 < e1) { p[j] = __ldg(g.gpts + min(e0 + lane, e1 - 1)); valid |= 1u << j; if (e1 - e0 > 32) longer |= 1u << j; }
   }
 #pragma unroll
-  for (int j = 0; j < 2 * kMaxK0 + 1; ++j) {
-    if (e0[j] < e1[j]) {
-      f(p[j].x, p[j].y, p[j].z, __float_as_int(p[j].w));
-      if (e1[j] - e0[j] > 32) visit_span(g.gpts, e0[j] + 32, e1[j], f);
-    }
+  for (int j = 0; j < 2 * kMaxK0 + 1; ++j)
+    if (valid & (1u << j)) f(p[j].x, p[j].y, p[j].z, __float_as_int(p[j].w));
+#pragma unroll 1
+  while (longer) {
+    const int j = __ffs(longer) - 1;
+    longer &= longer - 1;
+    visit_span<2>(g.gpts, __shfl_sync(0xffffffffu, v, 2 * j) + 32, __shfl_sync(0xffffffffu, v, 2 * j + 1), f);
   }
 }
 
@@ -219,8 +205,10 @@ __device__ __forceinline__ int first_halfwidth(float rho) { return rho < 6.5f ? 
 // After buckets bq-k .. bq+k have been seen, every unseen point is at azimuth distance >= k*w from q, hence at
 // distance >= rho_q * sin(k*w) (k*w < pi/2).  1e-4 rad absorbs atan2f / bucket rounding.  Returns the squared safe radius.
 __device__ __forceinline__ float safe_radius_sq(float rho_q, int k) {
-  const float ang = (float)k * kBucketW - 1e-4f;
-  const float s = ang >= 0.5f * kPiF ? 1.0f : sinf(fmaxf(ang, 0.f));
+  // sin(a) >= a - a^3/6 for a >= 0: a LOWER bound is all the argument needs (and no libm call, whose large-argument slow
+  // path costs a stack frame and ~1 k instructions of code); past 1.4 rad the polynomial's maximum 0.94 is used.
+  const float a = fmaxf((float)k * kBucketW - 1e-4f, 0.f);
+  const float s = a >= 1.4f ? 0.94f : a * (1.f - a * a * (1.f / 6.f));
   const float r = rho_q * s;
   return r * r * 0.9999f;
 }
@@ -262,8 +250,9 @@ __device__ __forceinline__ int rab_nearest(const RabIndex& g, float qx, float qy
   };
   int k = first_halfwidth(rho);
   const Spans2 sp = bucket_interval(g, bq - k, bq + k);
-  visit_span(g.gpts, sp.a0, sp.a1, f);
-  visit_span(g.gpts, sp.b0, sp.b1, f);
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) visit_span<12>(g.gpts, side ? sp.b0 : sp.a0, side ? sp.b1 : sp.a1, f);
+#pragma unroll 1
   for (;;) {
     wd = best_i == INT_MAX ? FLT_MAX : best_d; wi = best_i;
     warp_argmin(wd, wi);
@@ -289,16 +278,18 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
   const unsigned lane = lane_id();
   const bool is_corner = wid < max_sharp;
   const int qi = is_corner ? wid : wid - max_sharp;
+  // one round for everything the setup needs: the query point is fetched before its slot is known to be in use (the
+  // query buffers hold ALOAM_MAX_QUERIES points, every slot index is a valid address)
   const int nq = is_corner ? feat_counts[0] : feat_counts[2];
+  const Pt4 cur = (is_corner ? sharp : flat)[min(qi, ALOAM_MAX_QUERIES - 1)];
+  double pose[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) pose[k] = pose7[k];
   BlockRec* out = blocks + wid;
   int* co = corr ? corr + 4 * wid : nullptr;
   if (qi >= nq) { if (lane == 0) store_none(out, co); return; }
   const LastCloud& L = is_corner ? corner : surf;
   const RabIndex& g = L.index;
-  const Pt4 cur = is_corner ? sharp[qi] : flat[qi];
-  double pose[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) pose[k] = pose7[k];
   float qx, qy, qz;
   transform_to_start(pose, cur.x, cur.y, cur.z, qx, qy, qz);
   const float thr = (float)prm.dist_sq_thresh;
@@ -309,6 +300,7 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
   const int packed1 = rab_nearest(g, qx, qy, qz, thr, d1, k_nn);
   if (packed1 < 0 || !((double)d1 < prm.dist_sq_thresh)) { if (lane == 0) store_none(out, co); return; }
   const int closest = packed1 & 0xffffff;
+  const Pt4 pc = L.pts[closest];   // issued now, consumed after the second search
   const int rc = packed1 >> 24;  // closestPointScanID = int(intensity) of the closest point (k_rab_fill packs it)
   // rings rc-up .. rc+up survive the `> rc + NEARBY_SCAN` / `< rc - NEARBY_SCAN` break tests (:319,345,405,433)
   int up = 0; while ((double)(rc + up + 1) <= (double)rc + prm.nearby_scan) ++up;
@@ -339,6 +331,7 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
     };
     int k = min(k_nn, kMaxK0);
     visit_ring_slices(g, bq, k, r_lo, r_hi, f);
+#pragma unroll 1
     for (;;) {
       w2 = r2 == INT_MAX ? FLT_MAX : b2; k2 = r2; warp_argmin(w2, k2);
       const float safe2 = safe_radius_sq(rho, k);
@@ -363,7 +356,7 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
   if (is_corner) {
     if (j2 < 0) { if (lane == 0) store_none(out, co); return; }
     if (lane == 0) {
-      const Pt4 a = L.pts[closest], b = L.pts[j2];
+      const Pt4 a = pc, b = L.pts[j2];
       out->cp[0] = cur.x; out->cp[1] = cur.y; out->cp[2] = cur.z;
       out->a[0] = a.x; out->a[1] = a.y; out->a[2] = a.z;
       out->b[0] = b.x; out->b[1] = b.y; out->b[2] = b.z;
@@ -375,7 +368,7 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
   } else {
     if (j2 < 0 || j3 < 0) { if (lane == 0) store_none(out, co); return; }
     if (lane == 0) {
-      const Pt4 pj = L.pts[closest], pl = L.pts[j2], pm = L.pts[j3];
+      const Pt4 pj = pc, pl = L.pts[j2], pm = L.pts[j3];
       out->cp[0] = cur.x; out->cp[1] = cur.y; out->cp[2] = cur.z;
       out->a[0] = pj.x; out->a[1] = pj.y; out->a[2] = pj.z;
       // ljm_norm = (j - l) x (j - m), normalised (lidarFactor.hpp:64-65)
