@@ -316,8 +316,8 @@ int aloam_odometry_associate(aloam_ctx* c, aloam_cloud_view sharp, aloam_cloud_v
 
 // ------------------------------------------------------------------------------------------------ fused pipeline
 static int scan_to_pose_impl(aloam_ctx* c, const float* d_raw, int n, int stride, double q_w[4], double t_w[3], aloam_stats* stats) {
-  FeatBuf& cur = c->feat[c->frame % 3];
-  FeatBuf& last = c->feat[(c->frame + 2) % 3];
+  FeatBuf& cur = c->feat[c->frame % kFeatSlots];
+  FeatBuf& last = c->feat[(c->frame + kFeatSlots - 1) % kFeatSlots];
   const int slot = c->parity;
   int rc = run_features(c, d_raw, n, stride, cur);
   if (rc) return rc;
@@ -347,7 +347,7 @@ static int scan_to_pose_impl(aloam_ctx* c, const float* d_raw, int n, int stride
   float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   if (c->frame == 0) { if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->flags = flags; stats->ms_total = ms; } }
   else fill_stats(c, stats, c->cfg.outer_iters, flags, ms);
-  c->cur = c->frame % 3;
+  c->cur = c->frame % kFeatSlots;
   c->frame++;
   return ALOAM_OK;
 }
@@ -398,8 +398,8 @@ int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, i
   for (int k = 0; k < n_scans; ++k) {
     const int f = c->frame;                 // global frame number of this scan
     const int b = k & 1;                    // raw / ring-major double buffer
-    FeatBuf& cur = c->feat[f % 3];
-    FeatBuf& last = c->feat[(f + 2) % 3];
+    FeatBuf& cur = c->feat[f % kFeatSlots];
+    FeatBuf& last = c->feat[(f + kFeatSlots - 1) % kFeatSlots];
     const float* d_raw;
     if (device_resident) {
       d_raw = raws[k].data;
@@ -417,31 +417,31 @@ int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, i
     int rc = run_features_a(c, d_raw, raws[k].n, device_resident ? 4 : raws[k].stride_floats, b, &sc_slot);
     if (!device_resident) cudaEventRecord(c->ev_rawfree[b], c->s_exa);
     cudaEventRecord(c->ev_a[b], c->s_exa);
-    // ---- stage B (per-ring features) on s_ext: needs stage A of this scan, and its output slot feat[f % 3] free: that
-    //      slot was last read by the odometry of frame f-2 (as its "last" clouds)
+    // ---- stage B (per-ring features) on s_ext: needs stage A of this scan, and its output slot feat[f % kFeatSlots]
+    //      free: that slot was last read by the odometry of frame f - (kFeatSlots - 1) (as its "last" clouds)
     c->stream = c->s_ext;
     if (!rc) {
       CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_a[b], 0));
-      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_odo[(f + 1) % 3], 0));
+      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_odo[(f + 1) % kFeatSlots], 0));
       rc = run_features_b(c, b, sc_slot, cur);
       cudaEventRecord(c->ev_b[b], c->s_ext);
-      cudaEventRecord(c->ev_feat[f % 3], c->s_ext);
+      cudaEventRecord(c->ev_feat[f % kFeatSlots], c->s_ext);
       // ---- stage C (search index over the less-sharp / less-flat clouds) on s_idx: only the NEXT scan's odometry needs it
       c->stream = c->s_idx;
-      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_idx, c->ev_feat[f % 3], 0));
+      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_idx, c->ev_feat[f % kFeatSlots], 0));
       run_grid_build(c, cur, 64 * kMaxLessSharpPerRing, std::min(raws[k].n, c->max_points));
-      cudaEventRecord(c->ev_idx[f % 3], c->s_idx);
+      cudaEventRecord(c->ev_idx[f % kFeatSlots], c->s_idx);
     }
     c->stream = s_main;
     if (rc) return rc;
     // ---- association + LM on the main stream: this scan's sharp / flat points, the previous scan's clouds + index
-    CUDA_CHECK_RET(cudaStreamWaitEvent(s_main, c->ev_feat[f % 3], 0));
-    CUDA_CHECK_RET(cudaStreamWaitEvent(s_main, c->ev_idx[(f + 2) % 3], 0));
+    CUDA_CHECK_RET(cudaStreamWaitEvent(s_main, c->ev_feat[f % kFeatSlots], 0));
+    CUDA_CHECK_RET(cudaStreamWaitEvent(s_main, c->ev_idx[(f + kFeatSlots - 1) % kFeatSlots], 0));
     // the last solve of the scan writes the integrated world pose into its slot of d_poses (no copy on the critical chain)
     if (f > 0) run_register(c, cur, last, kFusedSharpSlots, kFusedFlatSlots, true, nullptr, c->d_poses + (size_t)k * 7);
     else CUDA_CHECK_RET(cudaMemcpyAsync(c->d_poses + (size_t)k * 7, c->d_world, 56, cudaMemcpyDeviceToDevice, s_main));
-    CUDA_CHECK_RET(cudaEventRecord(c->ev_odo[f % 3], s_main));
-    c->cur = f % 3;
+    CUDA_CHECK_RET(cudaEventRecord(c->ev_odo[f % kFeatSlots], s_main));
+    c->cur = f % kFeatSlots;
     c->frame++;
   }
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_poses, c->d_poses, (size_t)n_scans * 56, cudaMemcpyDeviceToHost, s_main));

@@ -17,6 +17,7 @@ constexpr int kMaxSharpPerRing = 12, kMaxLessSharpPerRing = 120, kMaxFlatPerRing
 constexpr int kFusedSharpSlots = 64 * kMaxSharpPerRing;  // 768
 constexpr int kFusedFlatSlots = 64 * kMaxFlatPerRing;    // 1536
 constexpr int kMaxQueries = ALOAM_MAX_QUERIES;
+constexpr int kFeatSlots = 4;                          // feature-set ring of the fused / stream paths
 constexpr int kMaxStreamScans = 4096;                   // scans per aloam_scan_stream call                       // API-path capacity for sharp / flat query clouds
 
 struct FeatBuf {
@@ -44,7 +45,7 @@ struct aloam_ctx {
   int8_t* d_label = nullptr;
   Pt4 *st_sharp = nullptr, *st_less_sharp = nullptr, *st_flat = nullptr, *st_less_flat = nullptr;
   int* st_counts = nullptr;
-  FeatBuf feat[3];   // triple-buffered feature sets (pipelined stream: extraction k+1 || odometry k needs k-1, k, k+1 alive)
+  FeatBuf feat[kFeatSlots];   // ring of feature sets: odometry k reads sets k-1 and k while extraction runs up to kFeatSlots-2 scans ahead
   // odometry
   BlockRec* d_blocks = nullptr;
   int* d_corr = nullptr;
@@ -73,7 +74,7 @@ struct aloam_ctx {
   // pipelined scan stream (aloam_scan_stream): extraction + index build on s_ext, association + LM on `stream`,
   // host->device copies of the raw scans on s_h2d, all chained by events
   cudaStream_t s_ext = nullptr, s_exa = nullptr, s_idx = nullptr, s_h2d = nullptr;
-  cudaEvent_t ev_feat[3] = {}, ev_idx[3] = {}, ev_odo[3] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {}, ev_a[2] = {}, ev_b[2] = {};
+  cudaEvent_t ev_feat[kFeatSlots] = {}, ev_idx[kFeatSlots] = {}, ev_odo[kFeatSlots] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {}, ev_a[2] = {}, ev_b[2] = {};
   float* d_raw2 = nullptr;       // second raw-scan staging buffer
   double* h_poses = nullptr;     // pinned [kMaxStreamScans][7]
   double* d_poses = nullptr;     // device [kMaxStreamScans][7]: per-scan world poses of a stream call (one D2H at the end)
