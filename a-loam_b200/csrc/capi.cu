@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -59,6 +60,9 @@ int aloam_destroy(aloam_ctx* c) {
   for (cudaEvent_t e : c->ev_a) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_b) if (e) cudaEventDestroy(e);
   if (c->d_full2) cudaFree(c->d_full2);
+  { void* extra[] = {c->st_sharp2, c->st_less_sharp2, c->st_flat2, c->st_less_flat2, c->st_counts2};
+    for (void* q : extra) if (q) cudaFree(q); }
+  for (cudaEvent_t e : c->ev_cmp) if (e) cudaEventDestroy(e);
   if (c->d_ring_start2) cudaFree(c->d_ring_start2);
   for (cudaEvent_t e : c->ev_feat) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_odo) if (e) cudaEventDestroy(e);
@@ -146,6 +150,10 @@ int aloam_create(const aloam_config* cfg, aloam_ctx** out) {
   TRY(dalloc(&c->st_sharp, 64 * kMaxSharpPerRing)); TRY(dalloc(&c->st_less_sharp, 64 * kMaxLessSharpPerRing));
   TRY(dalloc(&c->st_flat, 64 * kMaxFlatPerRing)); TRY(dalloc(&c->st_less_flat, (size_t)64 * ALOAM_MAX_RING));
   TRY(dalloc(&c->st_counts, 64 * 4));
+  TRY(dalloc(&c->st_sharp2, 64 * kMaxSharpPerRing)); TRY(dalloc(&c->st_less_sharp2, 64 * kMaxLessSharpPerRing));
+  TRY(dalloc(&c->st_flat2, 64 * kMaxFlatPerRing)); TRY(dalloc(&c->st_less_flat2, (size_t)64 * ALOAM_MAX_RING));
+  TRY(dalloc(&c->st_counts2, 64 * 4));
+  for (cudaEvent_t& e : c->ev_cmp) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (FeatBuf& f : c->feat) {
     TRY(dalloc(&f.sharp, kMaxQueries)); TRY(dalloc(&f.flat, kMaxQueries));
     TRY(dalloc(&f.less_sharp, mp)); TRY(dalloc(&f.less_flat, mp));
@@ -387,6 +395,7 @@ int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, i
   CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
   cudaStream_t s_main = c->stream;
   float* rawbuf[2] = {c->d_raw, c->d_raw2};
+  const auto host_t0 = std::chrono::steady_clock::now();
   CUDA_CHECK_RET(cudaEventRecord(c->ev0, s_main));
   // everything issued on the main stream before this call (reset, earlier calls) is ordered before the side streams.
   // Waiting on an event that was never recorded, or whose work finished in an earlier call, is a no-op -- so the
@@ -417,18 +426,23 @@ int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, i
     int rc = run_features_a(c, d_raw, raws[k].n, device_resident ? 4 : raws[k].stride_floats, b, &sc_slot);
     if (!device_resident) cudaEventRecord(c->ev_rawfree[b], c->s_exa);
     cudaEventRecord(c->ev_a[b], c->s_exa);
-    // ---- stage B (per-ring features) on s_ext: needs stage A of this scan, and its output slot feat[f % kFeatSlots]
-    //      free: that slot was last read by the odometry of frame f - (kFeatSlots - 1) (as its "last" clouds)
+    // ---- stage B (k_ring_features, the longest kernel) on s_ext: needs stage A of this scan and the staging set b free
+    //      (its previous content was consumed by the compaction of scan k-2)
     c->stream = c->s_ext;
     if (!rc) {
       CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_a[b], 0));
-      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_odo[(f + 1) % kFeatSlots], 0));
-      rc = run_features_b(c, b, sc_slot, cur);
+      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_ext, c->ev_cmp[b], 0));
+      rc = run_features_b1(c, b, sc_slot);
       cudaEventRecord(c->ev_b[b], c->s_ext);
-      cudaEventRecord(c->ev_feat[f % kFeatSlots], c->s_ext);
-      // ---- stage C (search index over the less-sharp / less-flat clouds) on s_idx: only the NEXT scan's odometry needs it
+      // ---- stage C on s_idx: ring-ordered compaction into feat[f % kFeatSlots] -- that slot was last read by the odometry
+      //      of frame f - (kFeatSlots - 1) as its "last" clouds -- then the search index over its less-sharp / less-flat
+      //      clouds, which only the NEXT scan's odometry needs
       c->stream = c->s_idx;
-      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_idx, c->ev_feat[f % kFeatSlots], 0));
+      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_idx, c->ev_b[b], 0));
+      CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_idx, c->ev_odo[(f + 1) % kFeatSlots], 0));
+      if (!rc) rc = run_features_b2(c, b, cur, false);
+      cudaEventRecord(c->ev_cmp[b], c->s_idx);
+      cudaEventRecord(c->ev_feat[f % kFeatSlots], c->s_idx);
       run_grid_build(c, cur, 64 * kMaxLessSharpPerRing, std::min(raws[k].n, c->max_points));
       cudaEventRecord(c->ev_idx[f % kFeatSlots], c->s_idx);
     }
@@ -444,6 +458,9 @@ int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, i
     c->cur = f % kFeatSlots;
     c->frame++;
   }
+  if (getenv("ALOAM_DEBUG_TIMING")) fprintf(stderr, "[aloam_b200] scan_stream: host issued %d scans in %.1f us (%.1f us / scan)\n", n_scans,
+      std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count(),
+      std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count() / n_scans);
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_poses, c->d_poses, (size_t)n_scans * 56, cudaMemcpyDeviceToHost, s_main));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, s_main));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_sc, c->d_sc, 3 * sizeof(ScanScalars), cudaMemcpyDeviceToHost, s_main));

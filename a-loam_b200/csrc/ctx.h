@@ -45,6 +45,10 @@ struct aloam_ctx {
   int8_t* d_label = nullptr;
   Pt4 *st_sharp = nullptr, *st_less_sharp = nullptr, *st_flat = nullptr, *st_less_flat = nullptr;
   int* st_counts = nullptr;
+  // second set of per-ring staging buffers: in the stream call k_compact(k) runs on the index stream while
+  // k_ring_features(k+1) is already filling the other set
+  Pt4 *st_sharp2 = nullptr, *st_less_sharp2 = nullptr, *st_flat2 = nullptr, *st_less_flat2 = nullptr;
+  int* st_counts2 = nullptr;
   FeatBuf feat[kFeatSlots];   // ring of feature sets: odometry k reads sets k-1 and k while extraction runs up to kFeatSlots-2 scans ahead
   // odometry
   BlockRec* d_blocks = nullptr;
@@ -74,7 +78,7 @@ struct aloam_ctx {
   // pipelined scan stream (aloam_scan_stream): extraction + index build on s_ext, association + LM on `stream`,
   // host->device copies of the raw scans on s_h2d, all chained by events
   cudaStream_t s_ext = nullptr, s_exa = nullptr, s_idx = nullptr, s_h2d = nullptr;
-  cudaEvent_t ev_feat[kFeatSlots] = {}, ev_idx[kFeatSlots] = {}, ev_odo[kFeatSlots] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {}, ev_a[2] = {}, ev_b[2] = {};
+  cudaEvent_t ev_feat[kFeatSlots] = {}, ev_idx[kFeatSlots] = {}, ev_odo[kFeatSlots] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {}, ev_a[2] = {}, ev_b[2] = {}, ev_cmp[2] = {};
   float* d_raw2 = nullptr;       // second raw-scan staging buffer
   double* h_poses = nullptr;     // pinned [kMaxStreamScans][7]
   double* d_poses = nullptr;     // device [kMaxStreamScans][7]: per-scan world poses of a stream call (one D2H at the end)
@@ -209,15 +213,29 @@ int run_features_a(aloam_ctx* c, const float* d_raw, int n, int stride, int buf,
   CUDA_CHECK_RET(cudaGetLastError());
   return ALOAM_OK;
 }
-int run_features_b(aloam_ctx* c, int buf, int sc_slot, FeatBuf& out) {
+// B1: per-ring kernel -> staging set `buf` ; B2: ring-ordered concatenation of the staging set into `out`
+int run_features_b1(aloam_ctx* c, int buf, int sc_slot) {
   Pt4* full = buf ? c->d_full2 : c->d_full;
   int* rstart = buf ? c->d_ring_start2 : c->d_ring_start;
   LAUNCH(c, KID_RING_FEATURES, k_ring_features, c->cfg.n_scans, 256, ring_features_smem_bytes(), full, rstart,
-         c->cfg.n_scans, 0.2f, c->st_sharp, c->st_less_sharp, c->st_flat, c->st_less_flat, c->st_counts, c->d_curv, c->d_label, c->d_sc + sc_slot);
-  LAUNCH_PDL(c, KID_COMPACT, k_compact, c->cfg.n_scans, 128, 0, c->cfg.n_scans, c->st_sharp, c->st_less_sharp, c->st_flat,
-         c->st_less_flat, c->st_counts, out.sharp, out.less_sharp, out.flat, out.less_flat, out.counts, out.rs_ls, out.rs_lf);
+         c->cfg.n_scans, 0.2f, buf ? c->st_sharp2 : c->st_sharp, buf ? c->st_less_sharp2 : c->st_less_sharp,
+         buf ? c->st_flat2 : c->st_flat, buf ? c->st_less_flat2 : c->st_less_flat, buf ? c->st_counts2 : c->st_counts,
+         c->d_curv, c->d_label, c->d_sc + sc_slot);
   CUDA_CHECK_RET(cudaGetLastError());
   return ALOAM_OK;
+}
+int run_features_b2(aloam_ctx* c, int buf, FeatBuf& out, bool pdl) {
+  launch_ex(c, KID_COMPACT, k_compact, dim3(c->cfg.n_scans), dim3(128), 0, 1, pdl, c->cfg.n_scans,
+            (const Pt4*)(buf ? c->st_sharp2 : c->st_sharp), (const Pt4*)(buf ? c->st_less_sharp2 : c->st_less_sharp),
+            (const Pt4*)(buf ? c->st_flat2 : c->st_flat), (const Pt4*)(buf ? c->st_less_flat2 : c->st_less_flat),
+            (const int*)(buf ? c->st_counts2 : c->st_counts), out.sharp, out.less_sharp, out.flat, out.less_flat, out.counts, out.rs_ls, out.rs_lf);
+  CUDA_CHECK_RET(cudaGetLastError());
+  return ALOAM_OK;
+}
+int run_features_b(aloam_ctx* c, int buf, int sc_slot, FeatBuf& out) {
+  int rc = run_features_b1(c, buf, sc_slot);
+  if (rc) return rc;
+  return run_features_b2(c, buf, out, true);
 }
 int run_features(aloam_ctx* c, const float* d_raw, int n, int stride, FeatBuf& out) {
   int slot = 0;
