@@ -202,6 +202,12 @@ class Aloam:
         b, kb = _view(surf_map)
         _check(lib().aloam_map_upload(self._h, a, b))
 
+    def map_upload_ptr(self, corner_ptr, n_corner, surf_ptr, n_surf, stride=4):
+        """aloam_map_upload on raw addresses (pinned host memory or device memory; the library infers the copy kind)"""
+        a = CloudView(C.cast(C.c_void_p(int(corner_ptr)), C.POINTER(C.c_float)), int(n_corner), stride)
+        b = CloudView(C.cast(C.c_void_p(int(surf_ptr)), C.POINTER(C.c_float)), int(n_surf), stride)
+        _check(lib().aloam_map_upload(self._h, a, b))
+
     def mapping_register(self, corner_stack, surf_stack, x):
         a, ka = _view(corner_stack)
         b, kb = _view(surf_stack)

@@ -182,9 +182,9 @@ int upload_cloud(aloam_ctx* c, aloam_cloud_view v, Pt4* dst, int capacity) {
   if (v.n > capacity) return ALOAM_ERR_CAPACITY;
   if (v.n == 0) return ALOAM_OK;
   if (v.stride_floats == 4) {
-    CUDA_CHECK_RET(cudaMemcpyAsync(dst, v.data, (size_t)v.n * 16, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK_RET(cudaMemcpyAsync(dst, v.data, (size_t)v.n * 16, cudaMemcpyDefault, c->stream));   // host or device source
   } else {
-    CUDA_CHECK_RET(cudaMemcpy2DAsync(dst, 16, v.data, (size_t)v.stride_floats * 4, 16, v.n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK_RET(cudaMemcpy2DAsync(dst, 16, v.data, (size_t)v.stride_floats * 4, 16, v.n, cudaMemcpyDefault, c->stream));
   }
   return ALOAM_OK;
 }

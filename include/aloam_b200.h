@@ -103,7 +103,9 @@ int aloam_odometry_register(aloam_ctx* ctx, aloam_cloud_view sharp, aloam_cloud_
 /* ---- scan-to-map refinement.
  * aloam_map_upload replaces laserMapping.cpp:531-539 + :558-559 (the gathered 5x5x3-cube submap and the two
  * kd-tree builds).  aloam_mapping_register replaces :554-729; the stacks are the voxel-filtered current
- * corner / surf clouds of :542-550 (use aloam_voxel_filter for those), q_t_w_curr = parameters[7]. */
+ * corner / surf clouds of :542-550 (use aloam_voxel_filter for those), q_t_w_curr = parameters[7].
+ * Input views of aloam_map_upload / aloam_odometry_* / aloam_mapping_* may point to host memory (pageable or pinned)
+ * or to device memory: the copy kind is inferred from the address (unified virtual addressing). */
 int aloam_map_upload(aloam_ctx* ctx, aloam_cloud_view corner_map, aloam_cloud_view surf_map);
 int aloam_mapping_register(aloam_ctx* ctx, aloam_cloud_view corner_stack, aloam_cloud_view surf_stack,
                            double q_t_w_curr[7], aloam_stats* stats);
