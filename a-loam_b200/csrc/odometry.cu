@@ -140,67 +140,68 @@ __device__ __forceinline__ void visit_span(const float4* __restrict__ gpts, int 
   }
 }
 
-// All rings of two runs of azimuth buckets, bq+offA .. bq+offA+cntA-1 and bq+offB .. bq+offB+cntB-1 (either may be empty;
-// indices wrap around the circle, cnt <= ALOAM_NB): at most four contiguous slices of gpts, whose eight delimiters are
-// fetched in ONE round.
-// Lane i < 8 returns delimiter i (slice j = [value of lane 2j, value of lane 2j+1)); the caller broadcasts with shuffles.
-__device__ __forceinline__ void run_cells(int bq, int off, int cnt, int& c0, int& c1, int& c2, int& c3) {
-  c0 = c1 = c2 = c3 = 0;
-  if (cnt <= 0) return;
-  if (cnt >= ALOAM_NB) { c1 = ALOAM_NB * 64; return; }
-  const int lo = ((bq + off) % ALOAM_NB + ALOAM_NB) % ALOAM_NB, hi = lo + cnt - 1;
-  if (hi < ALOAM_NB) { c0 = lo * 64; c1 = (hi + 1) * 64; }
-  else { c0 = lo * 64; c1 = ALOAM_NB * 64; c3 = (hi - ALOAM_NB + 1) * 64; }
-}
-__device__ __forceinline__ int bucket_runs(const RabIndex& g, int bq, int offA, int cntA, int offB, int cntB) {
-  int c[8];
-  run_cells(bq, offA, cntA, c[0], c[1], c[2], c[3]);
-  run_cells(bq, offB, cntB, c[4], c[5], c[6], c[7]);
-  const int lane = (int)lane_id();
-  int mine = c[7];
-#pragma unroll
-  for (int i = 0; i < 7; ++i) if (lane == i) mine = c[i];
-  return g.start[mine];
-}
-
-// Ring slice [r_lo, r_hi] of `cnt` consecutive buckets starting at bq+off (wrapping), eight buckets at a time: one round
-// for the sixteen delimiters, one round for the first 32 points of every slice, then whatever is left of slices longer
-// than 32 points.
+// Ring slice [r_lo, r_hi] of azimuth buckets bq-k and bq+k (the two coincide when 2k == NB): the growth step of a sweep
+// whose first interval was not enough (2 % of the queries).  (A variant that doubles the interval per step -- one
+// delimiter round per step instead of two per bucket -- was measured: it shortens the rare far sweeps but its extra
+// bookkeeping on the common path cost 2 us per launch on average (14.5 -> 16.6 us); bucket-by-bucket growth stays.)
 template <typename F>
-__device__ __forceinline__ void visit_ring_buckets(const RabIndex& g, int bq, int off, int cnt, int r_lo, int r_hi, F&& f) {
-  const int lane = (int)lane_id();
+__device__ __forceinline__ void visit_ring_step(const RabIndex& g, int bq, int k, int r_lo, int r_hi, F&& f) {
+  const int b0 = (bq - k + ALOAM_NB) % ALOAM_NB, b1 = (bq + k) % ALOAM_NB;
 #pragma unroll 1
-  for (int base = 0; base < cnt; base += 8) {
-    int v = 0;
-    if (lane < 16 && base + (lane >> 1) < cnt) {
-      const int b = ((bq + off + base + (lane >> 1)) % ALOAM_NB + ALOAM_NB) % ALOAM_NB;
-      v = g.start[b * 64 + ((lane & 1) ? r_hi + 1 : r_lo)];
-    }
-    float4 p[8];
-    unsigned valid = 0, longer = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int e0 = __shfl_sync(0xffffffffu, v, 2 * j), e1 = __shfl_sync(0xffffffffu, v, 2 * j + 1);   // 0, 0 past cnt
-      if (e0 < e1) { p[j] = __ldg(g.gpts + min(e0 + lane, e1 - 1)); valid |= 1u << j; if (e1 - e0 > 32) longer |= 1u << j; }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (valid & (1u << j)) f(p[j].x, p[j].y, p[j].z, __float_as_int(p[j].w));
-#pragma unroll 1
-    while (longer) {
-      const int j = __ffs(longer) - 1;
-      longer &= longer - 1;
-      visit_span<2>(g.gpts, __shfl_sync(0xffffffffu, v, 2 * j) + 32, __shfl_sync(0xffffffffu, v, 2 * j + 1), f);
-    }
+  for (int side = 0; side < 2; ++side) {
+    if (side && b1 == b0) break;
+    const int b = side ? b1 : b0;
+    visit_span<4>(g.gpts, g.start[b * 64 + r_lo], g.start[b * 64 + r_hi + 1], f);
   }
 }
 
-// A sweep that is not finished after buckets bq-k..bq+k continues with bq-k'..bq+k', k' = 2k+1 (capped at half the
-// circle): the new buckets are one run on each side.  Queries without any neighbour inside the reference's 25 m^2
-// threshold must read azimuth until rho*sin(k*w) passes 5 m -- a third of the circle at rho = 6 m; growing bucket by
-// bucket cost them ~4 dependent rounds per step and made the slowest warp of the grid 3x slower than the median.
+// All rings of the azimuth buckets lo..hi (lo <= hi, indices may run past either end of the circle) are at most two
+// contiguous slices of gpts: [a0, a1) and [b0, b1).  Their four delimiters are fetched in ONE round.
+struct Spans2 { int a0, a1, b0, b1; };
+__device__ __forceinline__ Spans2 bucket_interval(const RabIndex& g, int lo, int hi) {
+  int c0, c1, c2 = 0, c3 = 0;
+  if (hi - lo + 1 >= ALOAM_NB) { c0 = 0; c1 = ALOAM_NB * 64; }
+  else if (lo < 0) { c0 = (lo + ALOAM_NB) * 64; c1 = ALOAM_NB * 64; c3 = (hi + 1) * 64; }
+  else if (hi >= ALOAM_NB) { c0 = lo * 64; c1 = ALOAM_NB * 64; c3 = (hi - ALOAM_NB + 1) * 64; }
+  else { c0 = lo * 64; c1 = (hi + 1) * 64; }
+  const int lane = (int)lane_id();
+  const int v = g.start[lane == 0 ? c0 : lane == 1 ? c1 : lane == 2 ? c2 : c3];
+  Spans2 s;
+  s.a0 = __shfl_sync(0xffffffffu, v, 0); s.a1 = __shfl_sync(0xffffffffu, v, 1);
+  s.b0 = __shfl_sync(0xffffffffu, v, 2); s.b1 = __shfl_sync(0xffffffffu, v, 3);
+  return s;
+}
+
+// Ring slice [r_lo, r_hi] of each of the buckets bq-k..bq+k (k <= kMaxK0): 2k+1 short slices.  One round for all the
+// delimiters, one round for the first 32 points of every slice, then whatever is left of slices longer than 32.
 constexpr int kMaxK0 = 3;
-__device__ __forceinline__ int next_halfwidth(int k) { return min(2 * k + 1, ALOAM_NB / 2); }
+template <typename F>
+__device__ __forceinline__ void visit_ring_slices(const RabIndex& g, int bq, int k, int r_lo, int r_hi, F&& f) {
+  const int lane = (int)lane_id();
+  const int nb = 2 * k + 1;
+  int v = 0;
+  if (lane < 2 * nb) {
+    const int b = (bq - k + (lane >> 1) + ALOAM_NB) % ALOAM_NB;
+    v = g.start[b * 64 + ((lane & 1) ? r_hi + 1 : r_lo)];
+  }
+  float4 p[2 * kMaxK0 + 1];
+  unsigned valid = 0, longer = 0;
+#pragma unroll
+  for (int j = 0; j < 2 * kMaxK0 + 1; ++j) {
+    const int e0 = __shfl_sync(0xffffffffu, v, 2 * j), e1 = __shfl_sync(0xffffffffu, v, 2 * j + 1);   // 0, 0 past nb
+    if (e0 < e1) { p[j] = __ldg(g.gpts + min(e0 + lane, e1 - 1)); valid |= 1u << j; if (e1 - e0 > 32) longer |= 1u << j; }
+  }
+#pragma unroll
+  for (int j = 0; j < 2 * kMaxK0 + 1; ++j)
+    if (valid & (1u << j)) f(p[j].x, p[j].y, p[j].z, __float_as_int(p[j].w));
+#pragma unroll 1
+  while (longer) {
+    const int j = __ffs(longer) - 1;
+    longer &= longer - 1;
+    visit_span<2>(g.gpts, __shfl_sync(0xffffffffu, v, 2 * j) + 32, __shfl_sync(0xffffffffu, v, 2 * j + 1), f);
+  }
+}
+
 __device__ __forceinline__ int first_halfwidth(float rho) { return rho < 6.5f ? kMaxK0 : 1; }
 
 // After buckets bq-k .. bq+k have been seen, every unseen point is at azimuth distance >= k*w from q, hence at
@@ -250,20 +251,17 @@ __device__ __forceinline__ int rab_nearest(const RabIndex& g, float qx, float qy
     if (d2 < best_d || (d2 == best_d && best_i != INT_MAX && packed < best_i)) { best_d = d2; best_i = packed; }
   };
   int k = first_halfwidth(rho);
-  int offA = -k, cntA = 2 * k + 1, offB = 0, cntB = 0;
+  const Spans2 sp = bucket_interval(g, bq - k, bq + k);
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) visit_span<12>(g.gpts, side ? sp.b0 : sp.a0, side ? sp.b1 : sp.a1, f);
 #pragma unroll 1
   for (;;) {
-    const int delim = bucket_runs(g, bq, offA, cntA, offB, cntB);
-#pragma unroll 1
-    for (int i = 0; i < 4; ++i)
-      visit_span<12>(g.gpts, __shfl_sync(0xffffffffu, delim, 2 * i), __shfl_sync(0xffffffffu, delim, 2 * i + 1), f);
     wd = best_i == INT_MAX ? FLT_MAX : best_d; wi = best_i;
     warp_argmin(wd, wi);
     const float safe2 = safe_radius_sq(rho, k);
-    if ((wi != INT_MAX && wd < safe2) || safe2 >= limit || 2 * k >= ALOAM_NB) break;
-    const int kn = next_halfwidth(k);
-    offA = -kn; cntA = kn - k; offB = k + 1; cntB = kn - k;
-    k = kn;
+    if ((wi != INT_MAX && wd < safe2) || safe2 >= limit || 2 * (k + 1) > ALOAM_NB) break;
+    ++k;
+    visit_ring_step(g, bq, k, 0, 63, f);
   }
   k_out = k;
   out_d = wd;
@@ -333,12 +331,10 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
         else { if (d2 < b3 || (d2 == b3 && r3 != INT_MAX && rank < r3)) { b3 = d2; r3 = rank; } }
       }
     };
-    int k = k_nn;
-    int offA = -k, cntA = min(2 * k + 1, ALOAM_NB), offB = 0, cntB = 0;
+    int k = min(k_nn, kMaxK0);
+    visit_ring_slices(g, bq, k, r_lo, r_hi, f);
 #pragma unroll 1
     for (;;) {
-#pragma unroll 1
-      for (int side = 0; side < 2; ++side) visit_ring_buckets(g, bq, side ? offB : offA, side ? cntB : cntA, r_lo, r_hi, f);
       w2 = r2 == INT_MAX ? FLT_MAX : b2; k2 = r2; warp_argmin(w2, k2);
       const float safe2 = safe_radius_sq(rho, k);
       bool done = k2 != INT_MAX && w2 < safe2;
@@ -346,10 +342,9 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ shar
         w3 = r3 == INT_MAX ? FLT_MAX : b3; k3 = r3; warp_argmin(w3, k3);
         done = done && k3 != INT_MAX && w3 < safe2;
       }
-      if (done || safe2 >= thr || 2 * k >= ALOAM_NB) break;
-      const int kn = next_halfwidth(k);
-      offA = -kn; cntA = kn - k; offB = k + 1; cntB = kn - k;
-      k = kn;
+      if (done || safe2 >= thr || 2 * (k + 1) > ALOAM_NB) break;
+      ++k;
+      visit_ring_step(g, bq, k, r_lo, r_hi, f);
     }
   }
   // rank -> index

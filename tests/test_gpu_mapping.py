@@ -110,3 +110,17 @@ def test_voxel_filter_matches_pcl_restatement(ctx, orc, synth, scans, leaf):
 def test_voxel_filter_overflow_returns_input(ctx):
     cloud = np.array([[0, 0, 0, 1], [3000, 3000, 3000, 2], [1, 1, 1, 3]], np.float32)
     assert np.array_equal(ctx.voxel_filter(cloud, 0.2), cloud)
+
+
+def test_map_upload_accepts_device_memory(aloam, scene):
+    """aloam_map_upload infers the copy kind: a map resident in device memory gives the same pose as the host upload"""
+    import torch
+    cmap, smap, cs, ss, x0, _ = scene
+    c = aloam.Aloam(n_scans=64, max_points=200000, max_map_points=len(cmap) + len(smap) + 1024)
+    c.map_upload(cmap, smap)
+    x_host, _ = c.mapping_register(cs, ss, x0)
+    dc, ds = torch.from_numpy(np.ascontiguousarray(cmap)).cuda(), torch.from_numpy(np.ascontiguousarray(smap)).cuda()
+    c.map_upload_ptr(dc.data_ptr(), dc.shape[0], ds.data_ptr(), ds.shape[0])
+    x_dev, _ = c.mapping_register(cs, ss, x0)
+    assert np.array_equal(x_host, x_dev)
+    c.close()

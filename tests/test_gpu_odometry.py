@@ -123,7 +123,7 @@ def test_fused_pipeline_poses(aloam, orc, synth, scans, sensor, frames):
 
 
 def test_scan_stream_equals_per_scan_calls(aloam, synth, scans):
-    """the 3-stream pipelined call returns exactly the poses of one aloam_scan_to_pose call per scan (host and device input)"""
+    """the multi-stream pipelined call returns exactly the poses of one aloam_scan_to_pose call per scan (host and device input)"""
     import torch
     raws = [scans("HDL-64", k) for k in range(7)]
     a = aloam.Aloam(n_scans=64, max_points=140000)
@@ -139,4 +139,29 @@ def test_scan_stream_equals_per_scan_calls(aloam, synth, scans):
         p2, _ = a.scan_stream([buf[i].data_ptr() for i in range(3, 7)], [len(r) for r in raws[3:]], devres)
         got = np.concatenate([p1, p2])
         assert np.array_equal(got, np.array(ref))
+    a.close()
+
+
+def test_scan_stream_mixes_with_per_scan_calls(aloam, synth, scans):
+    """stream calls and synchronous calls share one trajectory state: any interleaving gives the per-scan poses, and a
+    long stream (several turns of the feature-set ring, programmatic launches across scans) stays bit-identical"""
+    import torch
+    raws = [scans("VLP-16", k, n_az=900) for k in range(14)]
+    a = aloam.Aloam(n_scans=16, max_points=20000)
+    ref = np.array([np.concatenate(a.scan_to_pose(r)[:2]) for r in raws])
+    n = max(len(r) for r in raws)
+    dev = torch.zeros((len(raws), n, 4), dtype=torch.float32)
+    for i, r in enumerate(raws):
+        dev[i, :len(r)] = torch.from_numpy(r)
+    dev = dev.cuda()
+    cnt = [len(r) for r in raws]
+    a.reset_odometry()
+    got = [np.concatenate(a.scan_to_pose(raws[0])[:2])]
+    p, _ = a.scan_stream([dev[i].data_ptr() for i in range(1, 6)], cnt[1:6], True); got += list(p)
+    got.append(np.concatenate(a.scan_to_pose(raws[6])[:2]))
+    p, _ = a.scan_stream([dev[i].data_ptr() for i in range(7, 14)], cnt[7:14], True); got += list(p)
+    assert np.array_equal(np.array(got), ref)
+    a.reset_odometry()
+    p, _ = a.scan_stream([dev[i].data_ptr() for i in range(14)], cnt, True)
+    assert np.array_equal(p, ref)
     a.close()
