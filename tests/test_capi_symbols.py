@@ -1,4 +1,4 @@
-"""CPU: the C-ABI shared library loads without a GPU and exports every entry point include/aloam_b200.h declares."""
+"""CPU: the C-ABI shared library loads without a GPU and exports every entry point the headers under include/ declare."""
 import ctypes
 import os
 import re
@@ -9,9 +9,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    src = open(os.path.join(ROOT, "include", "aloam_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(aloam_[a-z_0-9]+)\s*\(", src)))
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for h in sorted(os.listdir(inc)):
+        if h.endswith(".h"):
+            src = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, h)).read(), flags=re.S)
+            names |= set(re.findall(r"\b(aloam_[a-z_0-9]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_symbols_exported(aloam):

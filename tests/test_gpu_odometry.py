@@ -165,3 +165,24 @@ def test_scan_stream_mixes_with_per_scan_calls(aloam, synth, scans):
     p, _ = a.scan_stream([dev[i].data_ptr() for i in range(14)], cnt, True)
     assert np.array_equal(p, ref)
     a.close()
+
+
+def test_replay_of_kitti_files_equals_direct_calls(aloam, synth, scans, tmp_path):
+    """tools/replay_kitti.py: scans written as KITTI .bin files and replayed through aloam_scan_stream give the poses of
+    direct aloam_scan_to_pose calls; the written KITTI pose lines parse back to the same lidar-frame poses"""
+    import importlib, os, sys
+    io = importlib.import_module("a-loam_b200.io")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import replay_kitti
+    raws = [scans("VLP-16", k, n_az=900) for k in range(6)]
+    paths = []
+    for k, r in enumerate(raws):
+        p = str(tmp_path / ("%06d.bin" % k)); io.write_kitti_bin(p, r); paths.append(p)
+    got = replay_kitti.replay(paths, n_scans=16, chunk=4)
+    a = aloam.Aloam(n_scans=16, max_points=20000)
+    ref = np.array([np.concatenate(a.scan_to_pose(r)[:2]) for r in raws])
+    a.close()
+    assert np.array_equal(got, ref)
+    T = io.lidar_pose_to_kitti(got[-1][:4], got[-1][4:])
+    q, t = io.kitti_pose_to_lidar(T)
+    assert np.abs(t - got[-1][4:]).max() < 1e-12 and rot_angle(q, got[-1][:4]) < 1e-7
