@@ -497,6 +497,11 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__
   __shared__ TrState T;
   const int tid = threadIdx.x;
   pdl_launch_dependents();
+  // Every CTA of the cluster must have started before its shared memory is written remotely (the first push happens
+  // before the first barrier of a pass).  Placed before pdl_wait(): when the kernel was launched with a programmatic
+  // dependency this barrier runs while the predecessor is still finishing.  (compute-sanitizer racecheck flags the
+  // kernel without it: "block that might not have entered yet".)
+  cluster.sync();
   pdl_wait();   // blocks / x7 are produced by the preceding kernel of the stream
   const int n = n_blocks_ptr ? *n_blocks_ptr : n_blocks_host;
   const bool writer = cluster.block_rank() == 0 && tid == 0;
@@ -579,6 +584,7 @@ __global__ void __launch_bounds__(NT, 1) k_lm_eval_shard(const BlockRec* __restr
   __shared__ double s_x[7];
   const TrState* T = reinterpret_cast<const TrState*>(state);
   const int tid = threadIdx.x;
+  cluster.sync();   // all CTAs of the cluster have started before the first remote shared-memory store
   const bool active = first || T->go;   // uniform over the grid and over all ranks
   if (tid < 7) s_x[tid] = first ? x7[tid] : T->xc[tid];
   __syncthreads();
