@@ -536,7 +536,9 @@ __global__ void __launch_bounds__(256) k_ring_features(const Pt4* __restrict__ f
         bool hit = false;
         if (lane < nl) { const int k = (int)s_less[w][lane] - sp; hit = k < 5 && ((in >> k) & 1u); }
         if (lane >= 24 && lane - 24 < nf) { const int k = (int)s_flat[w][lane - 24] - sp; hit = hit || (k < 5 && ((in >> k) & 1u)); }
-        if (__any_sync(0xffffffffu, hit)) run_segment(w, in);
+        const bool rerun = __any_sync(0xffffffffu, hit);
+        __syncwarp();   // the reads of s_less / s_flat above are ordered before the re-run's writes (votes do not order memory)
+        if (rerun) run_segment(w, in);
       }
     }
     __syncthreads();
