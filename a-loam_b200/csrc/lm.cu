@@ -3,14 +3,15 @@
 // :106-138 plane-norm) and everything Ceres drives around them (AutoDiff Jacobians, HuberLoss(0.1) + Corrector,
 // EigenQuaternionParameterization, trust-region loop, DENSE_QR step).
 //
-// B200 shape: the whole solve is ONE launch of ONE thread-block cluster (8 CTAs x 512 threads, co-scheduled on one
+// B200 shape: the whole solve is ONE launch of ONE thread-block cluster (8 CTAs x 288 threads, co-scheduled on one
 // GPC) and never returns to the host.  Each pass evaluates every residual block with the closed-form tangent
 // Jacobian (SURVEY.md 8a "Residual math") and reduces the 28 numbers the 6-dof problem boils down to -- upper
-// triangle of J^T J (21), J^T r (6), cost (1):
-//     thread  -> warp   : transposed butterfly (31 shuffles instead of 28 x 5), lane L ends up owning number L
-//     warp    -> CTA    : shared memory, fixed order
-//     CTA     -> cluster: every CTA reads all 8 partial vectors through DISTRIBUTED SHARED MEMORY in rank order,
-//                         so all CTAs hold bit-identical totals after one cluster barrier (double-buffered).
+// triangle of J^T J (21), J^T r (6), cost (1) -- plus the two block counts:
+//     thread  -> warp   : transpose through shared memory, lane L adds column L in a fixed tree
+//     warp    -> CTA    : warp 0 adds the 9 partial vectors in a fixed tree
+//     CTA     -> cluster: every CTA PUSHES its vector into the shared memory of all 8 CTAs (distributed shared memory
+//                         stores), one cluster barrier, then adds the 8 vectors in rank order, so all CTAs hold
+//                         bit-identical totals (double-buffered by pass parity).
 // No float atomics anywhere => run-to-run deterministic.  Thread 0 of every CTA then takes the SAME trust-region
 // decision redundantly (no broadcast step), exactly as Ceres' TrustRegionMinimizer / LevenbergMarquardtStrategy:
 //   Jacobi scaling 1/(1+||J_j||) fixed at iteration 0, D^2 = clamp(diag(Js^T Js), 1e-6, 1e32) (re-used after a

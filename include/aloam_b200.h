@@ -121,9 +121,9 @@ int aloam_scan_to_pose(aloam_ctx* ctx, aloam_cloud_view raw, double q_w_curr[4],
 /* same, raw scan already in device memory (4-float packed points); used for HBM-resident measurements */
 int aloam_scan_to_pose_device(aloam_ctx* ctx, const float* d_raw_xyzi, int n, double q_w_curr[4],
                               double t_w_curr[3], aloam_stats* stats);
-/* pipelined form for a sequence of scans: extraction of scan k+1, odometry of scan k and the upload of scan k+2 overlap on
- * three CUDA streams (the overlap the reference gets from its three ROS processes); results identical to calling
- * aloam_scan_to_pose once per scan.  device_resident != 0: raws[k].data are device pointers (stride 4).
+/* pipelined form for a sequence of scans: upload, ring binning, per-ring feature extraction, compaction + index build
+ * and association + LM of consecutive scans overlap on five CUDA streams (the overlap the reference gets from its three
+ * ROS processes); results identical to calling aloam_scan_to_pose once per scan, in any interleaving with it.  device_resident != 0: raws[k].data are device pointers (stride 4).
  * poses: n_scans x 7 doubles (q_w xyzw, t_w). */
 int aloam_scan_stream(aloam_ctx* ctx, const aloam_cloud_view* raws, int n_scans, int device_resident, double* poses,
                       aloam_stats* stats_last);
