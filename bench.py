@@ -444,14 +444,22 @@ def main():
             c.scan_stream(ptrs[:1 + W], counts[:1 + W], True)
         torch.cuda.synchronize()
         res = [None] * n_streams
+        reps = 4    # each trajectory goes over the timed scans `reps` times (one pipelined call each): a longer region than
+                    # thread start-up jitter; the trajectory simply continues, every stream sees the same sequence
+        go = threading.Event()
         def work(j):
-            res[j] = ctxs[j].scan_stream(ptrs[1 + W:1 + W + timed_steps], counts[1 + W:1 + W + timed_steps], True)[0]
+            go.wait()
+            for _ in range(reps):
+                res[j] = ctxs[j].scan_stream(ptrs[1 + W:1 + W + timed_steps], counts[1 + W:1 + W + timed_steps], True)[0]
         th = [threading.Thread(target=work, args=(j,)) for j in range(n_streams)]
-        t0 = time.perf_counter()
         for t_ in th: t_.start()
+        time.sleep(0.05)
+        t0 = time.perf_counter()
+        go.set()
         for t_ in th: t_.join()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        t1 = t0 + (t1 - t0) / reps   # per pass over the timed scans
         same = all(np.array_equal(res[0], r) for r in res[1:])
         for c in ctxs: c.close()
         return t1 - t0, same
@@ -467,8 +475,8 @@ def main():
     if world == 1 and args.streams > 1:
         secs_multi, same = run_multi(args.streams, K)
         multi = {"streams": args.streams, "value": args.streams * K / secs_multi, "unit": "scans/s", "identical_poses_across_streams": bool(same),
-                 "note": "%d independent trajectories, one context + one host thread each, on the same GPU (HBM-resident scans); "
-                         "the headline value is ONE trajectory" % args.streams}
+                 "note": "%d independent trajectories, one context + one host thread each, on the same GPU (HBM-resident scans), "
+                         "each going 4 times over the timed scans; the headline value is ONE trajectory" % args.streams}
     _, _, _, _ = run("device", K, profile=True)
     prof = ctx.profile_read()
     ctx.profile_enable(False)
