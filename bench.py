@@ -44,88 +44,109 @@ def gen_scans(synth, count, seed):
     return scans
 
 
+_POLLER = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+bus = sys.argv[1]
+try:
+    h = nv.nvmlDeviceGetHandleByPciBusId(bus.encode()) if bus != '-' else nv.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))
+except Exception:
+    h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))
+mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+out = sys.stdout
+while True:
+    try:
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        out.write('%.6f %d %d %d\n' % (time.time(), sm, mx, r)); out.flush()
+    except Exception:
+        pass
+    time.sleep(0.001)
+"""
+
+
 class ClockSampler:
-    """SM clock and clock-event (throttle) reasons sampled WHILE the timed region runs: NVML polled every ~2 ms from a
-    thread (the timed regions here last tens of milliseconds); falls back to `nvidia-smi -lms 200` without NVML."""
-    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event (throttle) reasons sampled WHILE the timed region runs.  The timed regions here last tens
+    of milliseconds, so the samples come from a separate process that polls NVML every millisecond (a thread of this
+    process is starved by the launch loop); it is spawned early, `start()` / `stop()` only mark the window.  One
+    synchronous sample is added at each end of the window, so the result is never empty."""
+    BITS = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []          # (sm_mhz, max_mhz, [reason names])
         self.proc = None
-        self.th = None
-        self.stop_flag = False
-        self.mode = None
-
-    def _nvml_handle(self):
-        import pynvml
-        pynvml.nvmlInit()
+        self.lines = []
+        self.t0 = None
+        self.edge = []
+        self.nv = None
+        self.h = None
+        bus = "-"
         try:
             import torch
-            pr = torch.cuda.get_device_properties(self.gpu)
+            pr = torch.cuda.get_device_properties(gpu_index)
             bus = "%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
         except Exception:
-            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
-
-    def _poll_nvml(self, nv, h):
-        bits = [("hw_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
-                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
-                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
-                ("sw_power_cap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4))]
-        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-        while not self.stop_flag:
-            try:
-                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.rows.append((float(sm), float(mx), [n for n, b in bits if r & b]))
-            except Exception:
-                pass
-            time.sleep(0.002)
-
-    def start(self):
+            pass
         try:
-            nv, h = self._nvml_handle()
-            self.mode = "nvml"
-            self.th = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
-            self.th.start()
-            return
-        except Exception:
-            self.mode = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.mode = "nvidia-smi"
+            self.proc = subprocess.Popen([sys.executable, "-c", _POLLER, bus, str(gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode()) if bus != "-" else pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.nv = None
 
     def _read(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) >= 7 and parts[1].replace(".", "").isdigit() and parts[2].replace(".", "").isdigit():
-                self.rows.append((float(parts[1]), float(parts[2]), [names[i] for i in range(4) if parts[3 + i].lower().startswith("active")]))
+            self.lines.append(line)
+
+    def _edge_sample(self):
+        if self.nv is None:
+            return
+        try:
+            self.edge.append((time.time(), float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)),
+                              float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)),
+                              int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))))
+        except Exception:
+            pass
+
+    def start(self):
+        self._edge_sample()
+        self.t0 = time.time()
 
     def stop(self):
-        if self.mode is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
-        self.stop_flag = True
+        t1 = time.time()
+        self._edge_sample()
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        if self.th is not None:
             self.th.join(timeout=2)
-        sm = [r[0] for r in self.rows]
-        mx = [r[1] for r in self.rows]
-        reasons = sorted({n for r in self.rows for n in r[2]})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows), "source": self.mode}
+        rows = list(self.edge)
+        inside = 0
+        for line in self.lines:
+            p = line.split()
+            if len(p) == 4:
+                t = float(p[0])
+                if self.t0 is not None and self.t0 <= t <= t1:
+                    rows.append((t, float(p[1]), float(p[2]), int(p[3]))); inside += 1
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
+        reasons = sorted({n for r in rows for n, b in self.BITS if r[3] & b})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": max(r[2] for r in rows), "reasons": reasons,
+                "samples": len(rows), "samples_inside_timed_region": inside, "source": "nvml (poller process, 1 ms)"}
 
 
 def cpu_pipeline_sequential(orc, synth, scans):
@@ -250,6 +271,7 @@ def bench_mapping(args, synth, rank, world, local_rank):
         q, t = synth.pose(k)
         return np.concatenate([q, t + np.array([0.05, -0.04, 0.02])])
 
+    sampler = ClockSampler(local_rank)
     # the shard twice: resident in HBM (`value`) and in pinned host memory (`e2e`)
     dev_c, dev_s = torch.from_numpy(my_c).cuda(), torch.from_numpy(my_s).cuda()
     pin_c, pin_s = torch.from_numpy(my_c).pin_memory(), torch.from_numpy(my_s).pin_memory()
@@ -268,7 +290,7 @@ def bench_mapping(args, synth, rank, world, local_rank):
             err = max(err, float(np.abs(x[4:] - synth.pose(stacks[i][2])[1]).max()))
         torch.cuda.synchronize(); t1 = time.perf_counter(); barrier()
         return t1 - t0, ctx.launch_count() - l0, err, st
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler.start()
     secs, launches, err, st = run(K)
     clocks = sampler.stop()
     secs_host, _, _, _ = run(K, host=True)
@@ -386,6 +408,7 @@ def main():
         if world > 1:
             dist.barrier()
 
+    sampler = ClockSampler(local_rank)   # spawns the NVML poller now; the window is marked around the timed region
     scans = gen_scans(synth, n_scans_needed, synth.BASE_SEED + 1 + rank)
     counts = [s.shape[0] for s in scans]
     maxn = max(counts)
@@ -464,7 +487,6 @@ def main():
         for c in ctxs: c.close()
         return t1 - t0, same
 
-    sampler = ClockSampler(local_rank)
     sampler.start()
     sync_dev, devms_sync, _, pose_sync = run("device", K)
     sync_e2e, _, _, _ = run("host", K)
