@@ -220,3 +220,52 @@ void orc_eig3_sym(const double A[9], double ev[3], double V[9]) { eig3_sym(A, ev
 void orc_lsq_5x3(const double A[15], const double b[5], double n[3]) { lsq_5x3(A, b, n); }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ cube store (cubemap.cc)
+extern "C" {
+void* orc_cubemap_create() { return new orc::CubeMap(); }
+void orc_cubemap_free(void* h) { delete (orc::CubeMap*)h; }
+// one mapping frame ; pose7 out ; info[0..5] = optimised, n valid cubes, corner_from_map, surf_from_map, corner_stack, surf_stack sizes
+int orc_cubemap_step(void* h, const float* corner, int nc, const float* surf, int ns, const double q_odom[4], const double t_odom[3],
+                     float line_res, float plane_res, int outer, int max_iters, int sort_mode, double pose7[7], int info[6]) {
+  orc::CubeMap* m = (orc::CubeMap*)h;
+  orc::SolveOptions opt; opt.max_num_iterations = max_iters;
+  orc::Cloud c(nc), s(ns);
+  for (int i = 0; i < nc; ++i) c[i] = orc::PointXYZI{corner[4 * i], corner[4 * i + 1], corner[4 * i + 2], corner[4 * i + 3]};
+  for (int i = 0; i < ns; ++i) s[i] = orc::PointXYZI{surf[4 * i], surf[4 * i + 1], surf[4 * i + 2], surf[4 * i + 3]};
+  const int rc = m->step(c, s, q_odom, t_odom, line_res, plane_res, outer, opt, (orc::SortMode)sort_mode);
+  for (int k = 0; k < 7; ++k) pose7[k] = m->pose[k];
+  info[0] = rc; info[1] = (int)m->valid.size(); info[2] = (int)m->corner_from_map.size(); info[3] = (int)m->surf_from_map.size();
+  info[4] = (int)m->corner_stack.size(); info[5] = (int)m->surf_stack.size();
+  return rc;
+}
+// which: 0 corner_from_map, 1 surf_from_map, 2 corner_stack, 3 surf_stack ; returns the size, copies at most cap points
+int orc_cubemap_get(void* h, int which, float* out, int cap) {
+  orc::CubeMap* m = (orc::CubeMap*)h;
+  const orc::Cloud& c = which == 0 ? m->corner_from_map : which == 1 ? m->surf_from_map : which == 2 ? m->corner_stack : m->surf_stack;
+  const int n = (int)c.size();
+  for (int i = 0; i < n && i < cap; ++i) { out[4 * i] = c[i].x; out[4 * i + 1] = c[i].y; out[4 * i + 2] = c[i].z; out[4 * i + 3] = c[i].intensity; }
+  return n;
+}
+// cube bookkeeping: centre offsets, the valid cube indices of the last step, total stored points per type
+void orc_cubemap_state(void* h, int cen[3], int* n_valid, int valid[125], long long totals[2], double q_wmap_wodom[4], double t_wmap_wodom[3]) {
+  orc::CubeMap* m = (orc::CubeMap*)h;
+  cen[0] = m->cen_w; cen[1] = m->cen_h; cen[2] = m->cen_d;
+  *n_valid = (int)m->valid.size();
+  for (size_t i = 0; i < m->valid.size() && i < 125; ++i) valid[i] = m->valid[i];
+  totals[0] = totals[1] = 0;
+  for (const auto& c : m->corner) totals[0] += (long long)c.size();
+  for (const auto& c : m->surf) totals[1] += (long long)c.size();
+  for (int k = 0; k < 4; ++k) q_wmap_wodom[k] = m->q_wmap_wodom[k];
+  for (int k = 0; k < 3; ++k) t_wmap_wodom[k] = m->t_wmap_wodom[k];
+}
+// points of one cube (index i + 21 j + 441 k) ; which: 0 corner, 1 surf
+int orc_cubemap_cube(void* h, int which, int index, float* out, int cap) {
+  orc::CubeMap* m = (orc::CubeMap*)h;
+  if (index < 0 || index >= 21 * 21 * 11) return -1;
+  const orc::Cloud& c = which == 0 ? m->corner[index] : m->surf[index];
+  const int n = (int)c.size();
+  for (int i = 0; i < n && i < cap; ++i) { out[4 * i] = c[i].x; out[4 * i + 1] = c[i].y; out[4 * i + 2] = c[i].z; out[4 * i + 3] = c[i].intensity; }
+  return n;
+}
+}

@@ -147,6 +147,28 @@ void transform_associate_to_map(const double q_wmap_wodom[4], const double t_wma
 void transform_update(const double x[7], const double q_wodom_curr[4], const double t_wodom_curr[3],
                       double q_wmap_wodom[4], double t_wmap_wodom[3]);
 
+// ------------------------------------------------------------------ cubemap.cc    (laserMapping.cpp:74-108,309-550,736-801)
+// The 21 x 21 x 11 ring buffer of 50 m cubes and the whole per-frame mapping loop around it.
+class CubeMap {
+ public:
+  CubeMap();
+  // one frame of alaserMapping's process(): pose hand-off, shift, gather, stack filters, optimisation, insertion,
+  // per-cube re-filter.  Returns 1 if the optimisation ran (map thick enough).  `pose` = parameters[7] afterwards.
+  int step(const Cloud& corner_last, const Cloud& surf_last, const double q_wodom_curr[4], const double t_wodom_curr[3],
+           float line_res, float plane_res, int outer_iters, const SolveOptions& opt, SortMode mode);
+  std::vector<Cloud> corner, surf;        // laserCloudCornerArray / laserCloudSurfArray (4851 cubes each)
+  int cen_w = 10, cen_h = 10, cen_d = 5;  // laserCloudCenWidth / Height / Depth
+  double q_wmap_wodom[4] = {0, 0, 0, 1}, t_wmap_wodom[3] = {0, 0, 0};
+  double pose[7] = {0, 0, 0, 1, 0, 0, 0};
+  // state of the last step, for frame-by-frame parity checks
+  std::vector<int> valid;                 // laserCloudValidInd
+  Cloud corner_from_map, surf_from_map, corner_stack, surf_stack;
+  int frames = 0;
+ private:
+  void shift_for(int& ci, int& cj, int& ck);
+  void insert(const Cloud& stack, const double x[7], std::vector<Cloud>& cubes);
+};
+
 // 3x3 symmetric eigen (ascending eigenvalues, eigenvectors in columns, row-major V) -- Eigen::SelfAdjointEigenSolver stand-in
 void eig3_sym(const double A[9], double evals[3], double V[9]);
 // least squares solve of 5x3 A n = b by column-pivoted Householder QR (Eigen colPivHouseholderQr stand-in)

@@ -77,6 +77,13 @@ def lib():
         L.orc_transform_update.argtypes = [_f64p] * 5
         L.orc_eig3_sym.argtypes = [_f64p, _f64p, _f64p]
         L.orc_lsq_5x3.argtypes = [_f64p, _f64p, _f64p]
+        L.orc_cubemap_create.restype = C.c_void_p
+        L.orc_cubemap_free.argtypes = [C.c_void_p]
+        L.orc_cubemap_step.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, C.c_int, _f64p, _f64p, C.c_float, C.c_float, C.c_int,
+                                       C.c_int, C.c_int, _f64p, _i32p]
+        L.orc_cubemap_get.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int]
+        L.orc_cubemap_state.argtypes = [C.c_void_p, _i32p, _i32p, _i32p, C.POINTER(C.c_longlong), _f64p, _f64p]
+        L.orc_cubemap_cube.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -308,6 +315,65 @@ class Mapping:
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_map_free(self.h)
+            self.h = None
+
+
+def transform_associate_to_map(q_wmap_wodom, t_wmap_wodom, q_wodom_curr, t_wodom_curr):
+    """laserMapping.cpp:142-146 -> parameters[7]"""
+    x = np.zeros(7)
+    lib().orc_transform_associate_to_map(_dp(np.ascontiguousarray(q_wmap_wodom, np.float64)), _dp(np.ascontiguousarray(t_wmap_wodom, np.float64)),
+                                         _dp(np.ascontiguousarray(q_wodom_curr, np.float64)), _dp(np.ascontiguousarray(t_wodom_curr, np.float64)), _dp(x))
+    return x
+
+
+def transform_update(x, q_wodom_curr, t_wodom_curr):
+    """laserMapping.cpp:148-152 -> (q_wmap_wodom, t_wmap_wodom)"""
+    q = np.zeros(4); t = np.zeros(3)
+    lib().orc_transform_update(_dp(np.ascontiguousarray(x, np.float64)), _dp(np.ascontiguousarray(q_wodom_curr, np.float64)),
+                               _dp(np.ascontiguousarray(t_wodom_curr, np.float64)), _dp(q), _dp(t))
+    return q, t
+
+
+class CubeMap:
+    """laserMapping.cpp's 21 x 21 x 11 cube store and the per-frame loop around it (oracle/cubemap.cc)"""
+
+    def __init__(self):
+        self.h = lib().orc_cubemap_create()
+
+    def step(self, corner_last, surf_last, q_wodom_curr, t_wodom_curr, line_res=0.4, plane_res=0.8, outer=2, max_iters=4,
+             sort_mode=SORT_CANONICAL):
+        c, s = _cloud(corner_last), _cloud(surf_last)
+        pose = np.zeros(7)
+        info = np.zeros(6, np.int32)
+        lib().orc_cubemap_step(self.h, _fp(c), c.shape[0], _fp(s), s.shape[0], _dp(np.ascontiguousarray(q_wodom_curr, np.float64)),
+                               _dp(np.ascontiguousarray(t_wodom_curr, np.float64)), line_res, plane_res, outer, max_iters, sort_mode,
+                               _dp(pose), info.ctypes.data_as(_i32p))
+        keys = ["optimised", "n_valid", "corner_from_map", "surf_from_map", "corner_stack", "surf_stack"]
+        return pose, dict(zip(keys, (int(v) for v in info)))
+
+    def _get(self, fn, *a):
+        n = fn(self.h, *a, None, 0)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        fn(self.h, *a, _fp(out), n)
+        return out[:max(n, 0)].copy()
+
+    def cloud(self, which):
+        """0 corner_from_map, 1 surf_from_map, 2 corner_stack, 3 surf_stack of the last step"""
+        return self._get(lib().orc_cubemap_get, which)
+
+    def cube(self, which, index):
+        return self._get(lib().orc_cubemap_cube, which, index)
+
+    def state(self):
+        cen = np.zeros(3, np.int32); nv = np.zeros(1, np.int32); valid = np.zeros(125, np.int32)
+        tot = (C.c_longlong * 2)(); q = np.zeros(4); t = np.zeros(3)
+        lib().orc_cubemap_state(self.h, cen.ctypes.data_as(_i32p), nv.ctypes.data_as(_i32p), valid.ctypes.data_as(_i32p), tot, _dp(q), _dp(t))
+        return {"centre": tuple(int(v) for v in cen), "valid": [int(v) for v in valid[:nv[0]]], "total_corner": int(tot[0]),
+                "total_surf": int(tot[1]), "q_wmap_wodom": q, "t_wmap_wodom": t}
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_cubemap_free(self.h)
             self.h = None
 
 
