@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "aloam_odometry_set_last", "aloam_odometry_register", "aloam_map_upload", "aloam_mapping_register",
     "aloam_voxel_filter", "aloam_scan_to_pose", "aloam_scan_to_pose_device", "aloam_reset_odometry", "aloam_knn",
     "aloam_odometry_associate", "aloam_normal_equations", "aloam_solve", "aloam_debug_features", "aloam_mapping_associate",
-    "aloam_comm_unique_id", "aloam_comm_init", "aloam_scan_stream", "aloam_profile_enable", "aloam_profile_read", "aloam_launch_count",
+    "aloam_comm_unique_id", "aloam_comm_init", "aloam_scan_stream", "aloam_mapper_reset", "aloam_mapper_step", "aloam_profile_enable", "aloam_profile_read", "aloam_launch_count",
 ]
 
 
@@ -79,6 +79,10 @@ def lib():
         L.aloam_map_upload.argtypes = [C.c_void_p, cv, cv]
         L.aloam_mapping_register.argtypes = [C.c_void_p, cv, cv, dp, C.POINTER(Stats)]
         L.aloam_voxel_filter.argtypes = [C.c_void_p, cv, C.c_float, C.POINTER(cv)]
+        L.aloam_mapper_reset.argtypes = [C.c_void_p]
+        L.aloam_mapper_step.argtypes = [C.c_void_p, cv, cv, dp, dp, dp, dp, C.POINTER(Stats)]
+        L.aloam_mapper_debug_state.argtypes = [C.c_void_p, ip, ip, ip, dp, dp, C.POINTER(C.c_longlong)]
+        L.aloam_mapper_debug_cube.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(cv)]
         L.aloam_scan_to_pose.argtypes = [C.c_void_p, cv, dp, dp, C.POINTER(Stats)]
         L.aloam_scan_to_pose_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, dp, dp, C.POINTER(Stats)]
         L.aloam_reset_odometry.argtypes = [C.c_void_p]
@@ -207,6 +211,32 @@ class Aloam:
         a = CloudView(C.cast(C.c_void_p(int(corner_ptr)), C.POINTER(C.c_float)), int(n_corner), stride)
         b = CloudView(C.cast(C.c_void_p(int(surf_ptr)), C.POINTER(C.c_float)), int(n_surf), stride)
         _check(lib().aloam_map_upload(self._h, a, b))
+
+    # --- map cube store (laserMapping.cpp:309-550,736-801)
+    def mapper_reset(self):
+        _check(lib().aloam_mapper_reset(self._h))
+
+    def mapper_step(self, corner_last, surf_last, q_wodom_curr, t_wodom_curr):
+        """one alaserMapping frame -> (q_w_curr, t_w_curr, stats)"""
+        a, ka = _view(corner_last)
+        b, kb = _view(surf_last)
+        qo = np.ascontiguousarray(q_wodom_curr, np.float64); to = np.ascontiguousarray(t_wodom_curr, np.float64)
+        q = np.zeros(4); t = np.zeros(3)
+        st = Stats()
+        _check(lib().aloam_mapper_step(self._h, a, b, _dp(qo), _dp(to), _dp(q), _dp(t), C.byref(st)))
+        return q, t, st.as_dict()
+
+    def mapper_state(self):
+        cen = (C.c_int * 3)(); nv = C.c_int(0); valid = (C.c_int * 125)(); tot = (C.c_longlong * 2)()
+        q = np.zeros(4); t = np.zeros(3)
+        _check(lib().aloam_mapper_debug_state(self._h, cen, C.byref(nv), valid, _dp(q), _dp(t), tot))
+        return {"centre": tuple(cen), "valid": list(valid[:nv.value]), "q_wmap_wodom": q, "t_wmap_wodom": t,
+                "total_corner": int(tot[0]), "total_surf": int(tot[1])}
+
+    def mapper_cube(self, which, cube_index):
+        out = CloudView()
+        _check(lib().aloam_mapper_debug_cube(self._h, which, cube_index, C.byref(out)))
+        return _out(out)
 
     def mapping_register(self, corner_stack, surf_stack, x):
         a, ka = _view(corner_stack)

@@ -17,6 +17,7 @@ extern "C" {
 
 void aloam_map_free_impl(aloam_ctx* c);
 void aloam_comm_free_impl(aloam_ctx* c);
+void aloam_mapper_free_impl(aloam_ctx* c);
 int aloam_map_knn_impl(aloam_ctx* c, int which, aloam_cloud_view queries, int k, int* idx, float* sqdist);
 
 void aloam_default_config(aloam_config* cfg, int n_scans) {
@@ -87,6 +88,7 @@ int aloam_destroy(aloam_ctx* c) {
   aloam_map_free_impl(c);
   { void* vp[] = {c->d_vox_keys[0], c->d_vox_keys[1], c->d_vox_vals[0], c->d_vox_vals[1], c->d_vox_hist, c->d_vox_offs, c->d_vox_misc}; for (void* p : vp) if (p) cudaFree(p); }
   aloam_comm_free_impl(c);
+  aloam_mapper_free_impl(c);
   for (Pt4* p : c->h_out) if (p) cudaFreeHost(p);
   if (c->h_ints) cudaFreeHost(c->h_ints);
   if (c->h_dbl) cudaFreeHost(c->h_dbl);

@@ -64,6 +64,7 @@ struct aloam_ctx {
   void* comm = nullptr;          // ncclComm_t when shard_count > 1 (comm.cu)
   double* d_lm_tot = nullptr;    // [32] all-reduced normal equations of one evaluation (sharded LM)
   void* d_lm_state = nullptr;    // device-resident trust-region state (sharded LM)
+  void* mapper = nullptr;        // map cube store (cubemap.cu), created on first use
   // scan-to-map: uploaded submap (corner, surf) with hash grids, stack queries, fit debug records
   MapCloud map_corner = {}, map_surf = {};
   int max_map = 0, map_slots = 0;

@@ -153,6 +153,26 @@ int aloam_debug_features(aloam_ctx* ctx, float* curvature, int* label, int* scan
 int aloam_mapping_associate(aloam_ctx* ctx, aloam_cloud_view corner_stack, aloam_cloud_view surf_stack,
                             const double x[7], double* fits);
 
+/* ---- map cube store + the mapping loop around it (laserMapping.cpp:74-108,142-163,309-550,736-801).
+ * The 21 x 21 x 11 ring buffer of 50 m cubes lives in device memory (fixed-capacity slabs, created on first use: 6.4 GB).
+ * aloam_mapper_step is one frame of alaserMapping's process(): pose hand-off from the odometry (transformAssociateToMap),
+ * ring-buffer shift, gather of the <= 75 valid cubes (device to device), stack filters at line_res / plane_res,
+ * optimisation against the gathered submap (skipped while it is thinner than 10 corner / 50 surf points), transformUpdate,
+ * insertion of the registered stacks and per-cube VoxelGrid of the valid cubes.  corner_last / surf_last are the
+ * less-sharp / less-flat clouds of the scan (what /laser_cloud_corner_last and /laser_cloud_surf_last carry); the
+ * odometry pose is q_wodom_curr / t_wodom_curr; the refined pose is returned.  ALOAM_ERR_CAPACITY: a cube holds more
+ * than 16 k corner / 64 k surf points, or the submap exceeds cfg.max_map_points. */
+int aloam_mapper_reset(aloam_ctx* ctx);
+int aloam_mapper_step(aloam_ctx* ctx, aloam_cloud_view corner_last, aloam_cloud_view surf_last,
+                      const double q_wodom_curr[4], const double t_wodom_curr[3], double q_w_curr[4], double t_w_curr[3],
+                      aloam_stats* stats);
+/* inspection (tests): ring-buffer centre offsets, valid cube indices of the last step (i + 21 j + 441 k), the map-to-
+ * odometry transform, total stored points per type; and the points of one cube (which: 0 corner, 1 surf; host view,
+ * valid until the next call) */
+int aloam_mapper_debug_state(aloam_ctx* ctx, int centre[3], int* n_valid, int valid[125], double q_wmap_wodom[4],
+                             double t_wmap_wodom[3], long long totals[2]);
+int aloam_mapper_debug_cube(aloam_ctx* ctx, int which, int cube_index, aloam_cloud_view* out);
+
 /* ---- multi-GPU scan-to-map (one process per GPU).  Rank 0 creates the 128-byte id and ships it to the others;
  * after aloam_comm_init each rank uploads only ITS shard of the submap (x-slabs of aloam_shard_slab_cells() cells of
  * 1.00001 m, owner = slab mod world, plus one cell of halo) and aloam_mapping_register fits only the stack points
