@@ -362,7 +362,7 @@ def main():
                     help="odometry = BASELINE configs[1] (the contract line); mapping = configs[2] (1M-pt map) / configs[3] (8M-pt map sharded over --gpus)")
     ap.add_argument("--map-points", type=int, default=0, help="mapping workload: total map points (default 1M per GPU)")
     args = ap.parse_args()
-    K, W = args.steps, max(args.warmup, 0)
+    K, W = max(args.steps, 1), max(args.warmup, 3)   # never fewer than 3 untimed warm-up steps
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
