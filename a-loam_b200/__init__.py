@@ -315,10 +315,10 @@ class Aloam:
 
     def profile_read(self):
         """{kernel name: (total ms, launches)} measured with CUDA events on the ctx stream"""
-        ms = (C.c_double * 16)()
-        cnt = (C.c_longlong * 16)()
-        names = (C.c_char_p * 16)()
-        n = lib().aloam_profile_read(self._h, ms, cnt, names, 16)
+        ms = (C.c_double * 32)()
+        cnt = (C.c_longlong * 32)()
+        names = (C.c_char_p * 32)()
+        n = lib().aloam_profile_read(self._h, ms, cnt, names, 32)
         return {names[k].decode(): (ms[k], cnt[k]) for k in range(n) if names[k] and cnt[k] > 0}
 
     def launch_count(self):

@@ -90,6 +90,7 @@ int aloam_destroy(aloam_ctx* c) {
   aloam_comm_free_impl(c);
   aloam_mapper_free_impl(c);
   for (Pt4* p : c->h_out) if (p) cudaFreeHost(p);
+  if (c->h_vox_out) cudaFreeHost(c->h_vox_out);
   if (c->h_ints) cudaFreeHost(c->h_ints);
   if (c->h_dbl) cudaFreeHost(c->h_dbl);
   if (c->h_summary) cudaFreeHost(c->h_summary);

@@ -38,7 +38,7 @@ bool load_nccl() {
 }
 }  // namespace
 
-void launch_lm_sharded(aloam_ctx* c, const BlockRec* blocks, int n, double* pose, const LmParams& lp, LmSummary* summary) {
+void launch_lm_sharded(aloam_ctx* c, const BlockRec* blocks, const int* d_n, double* pose, const LmParams& lp, LmSummary* summary) {
   const int evals = 1 + lp.max_iters;
   double* local = c->d_lm_tot + 32;
   for (int e = 0; e < evals; ++e) {
@@ -50,12 +50,20 @@ void launch_lm_sharded(aloam_ctx* c, const BlockRec* blocks, int n, double* pose
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = kLmCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_lm_eval_shard, blocks, n, (const double*)pose, c->d_lm_state, first, lp.huber_a, local);
+    cudaLaunchKernelEx(&cfg, k_lm_eval_shard, blocks, d_n, (const double*)pose, c->d_lm_state, first, lp.huber_a, local);
     prof_end(c);
     ncclResult_t r = g_nccl.AllReduce(local, c->d_lm_tot, 32, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream);
     if (r != ncclSuccess) fprintf(stderr, "[aloam_b200] ncclAllReduce failed: %s\n", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     LAUNCH(c, KID_LM_SOLVE, k_lm_tr_shard, 1, 32, 0, c->d_lm_state, (const double*)c->d_lm_tot, pose, first, last, lp, summary);
   }
+}
+
+// sum of two ints over the ranks, in place (global submap sizes for the thin-map test, mapping.cu)
+int comm_allreduce_int2(aloam_ctx* c, int* d_two) {
+  if (c->shard_count <= 1) return ALOAM_OK;
+  ncclResult_t r = g_nccl.AllReduce(d_two, d_two, 2, ncclInt32, ncclSum, (ncclComm_t)c->comm, c->stream);
+  if (r != ncclSuccess) { fprintf(stderr, "[aloam_b200] ncclAllReduce failed: %s\n", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return ALOAM_ERR_COMM; }
+  return ALOAM_OK;
 }
 
 extern "C" {

@@ -17,6 +17,7 @@ constexpr int kMaxSharpPerRing = 12, kMaxLessSharpPerRing = 120, kMaxFlatPerRing
 constexpr int kFusedSharpSlots = 64 * kMaxSharpPerRing;  // 768
 constexpr int kFusedFlatSlots = 64 * kMaxFlatPerRing;    // 1536
 constexpr int kMaxQueries = ALOAM_MAX_QUERIES;
+constexpr int kProfSlots = 192;                       // kernel launches timed per profile window (one API call)
 constexpr int kFeatSlots = 4;                          // feature-set ring of the fused / stream paths
 constexpr int kMaxStreamScans = 4096;                   // scans per aloam_scan_stream call                       // API-path capacity for sharp / flat query clouds
 
@@ -67,9 +68,15 @@ struct aloam_ctx {
   void* mapper = nullptr;        // map cube store (cubemap.cu), created on first use
   // scan-to-map: uploaded submap (corner, surf) with hash grids, stack queries, fit debug records
   MapCloud map_corner = {}, map_surf = {};
+  Pt4* d_map_pts[2] = {nullptr, nullptr};   // staging for maps handed in as host views (device views are indexed in place)
   int max_map = 0, map_slots = 0;
+  int map_n[2] = {0, 0};          // points indexed on this rank (corner, surf)
+  int map_global_n[2] = {0, 0};   // size of the whole submap (== map_n unless the map is sharded over ranks)
   bool have_map = false;
   Pt4 *d_stack_corner = nullptr, *d_stack_surf = nullptr;
+  int* d_stack_counts = nullptr;  // [4] {n_corner, n_surf, total} of the stacks being registered
+  float4* d_nbr = nullptr;        // [queries][5] neighbours found by k_map_knn5 (x, y, z, index bits)
+  double* d_map_pose = nullptr;   // [7] scan-to-map pose being refined (parameters[7], laserMapping.cpp:110)
   double* d_fits = nullptr;      // [queries][14] debug / test records of the line / plane fits
   BlockRec* d_map_blocks = nullptr;
   // general voxel filter (voxel.cu): radix-sort ping-pong buffers, histograms, small scalars
@@ -85,14 +92,15 @@ struct aloam_ctx {
   double* d_poses = nullptr;     // device [kMaxStreamScans][7]: per-scan world poses of a stream call (one D2H at the end)
   // pinned host mirrors
   Pt4* h_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  Pt4* h_vox_out = nullptr;     // result of aloam_voxel_filter (never aliases the feature views)
   int* h_ints = nullptr;        // scratch ints (counts etc.)
   double* h_dbl = nullptr;      // scratch doubles
   LmSummary* h_summary = nullptr;
   ScanScalars* h_sc = nullptr;
   // per-kernel profiler (bench.py roofline leg) + cumulative launch counter
   bool prof_on = false;
-  cudaEvent_t prof_ev[64] = {};
-  int prof_kid[32] = {};
+  cudaEvent_t prof_ev[2 * kProfSlots] = {};
+  int prof_kid[kProfSlots] = {};
   int prof_n = 0;
   double prof_ms[ALOAM_N_KERNEL_IDS] = {};
   long long prof_cnt[ALOAM_N_KERNEL_IDS] = {};
@@ -108,17 +116,17 @@ struct aloam_ctx {
 namespace {
 
 enum { KID_CLASSIFY = 0, KID_RING_SCAN, KID_SCATTER, KID_RING_FEATURES, KID_COMPACT, KID_GRID_BUILD, KID_ODOM_ASSOC, KID_LM_SOLVE,
-       KID_RING_OFFSETS, KID_KNN_LAST, KID_PACK_BLOCKS, KID_MAP_GRID, KID_MAP_KNN_FIT, KID_VOXEL, KID_MAP_KNN };
+       KID_RING_OFFSETS, KID_KNN_LAST, KID_PACK_BLOCKS, KID_MAP_GRID, KID_MAP_KNN5, KID_VOXEL, KID_MAP_KNN, KID_MAP_FIT, KID_CUBES, KID_LM_SHARD };
 const char* const kKernelNames[ALOAM_N_KERNEL_IDS] = {"k_classify", "k_ring_scan", "k_scatter", "k_ring_features", "k_compact",
-    "k_rab_build(3 launches)", "k_odom_assoc", "k_lm_solve", "k_ring_offsets", "k_knn_last", "k_pack_blocks", "k_map_grid", "k_map_knn_fit",
-    "k_voxel", "k_map_knn", ""};
+    "k_rab_build(3 launches)", "k_odom_assoc", "k_lm_solve", "k_ring_offsets", "k_knn_last", "k_pack_blocks", "k_map_grid(4 launches)", "k_map_knn5",
+    "k_voxel", "k_map_knn", "k_map_fit", "k_cube_store", "k_lm_shard"};
 
 inline void prof_begin(aloam_ctx* c, int kid) {
   ++c->launches;
-  if (c->prof_on && c->prof_n < 32) { cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream); c->prof_kid[c->prof_n] = kid; }
+  if (c->prof_on && c->prof_n < kProfSlots) { cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream); c->prof_kid[c->prof_n] = kid; }
 }
 inline void prof_end(aloam_ctx* c) {
-  if (c->prof_on && c->prof_n < 32) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream); ++c->prof_n; }
+  if (c->prof_on && c->prof_n < kProfSlots) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream); ++c->prof_n; }
 }
 // call after the stream has been synchronised
 inline void prof_collect(aloam_ctx* c) {
@@ -158,13 +166,10 @@ void launch_lm(aloam_ctx* c, bool pdl, Args... args) {
 
 // sharded LM (comm.cu): per evaluation one kernel for the local blocks, one ncclAllReduce of 28 doubles, one step kernel
 }  // namespace
-void launch_lm_sharded(aloam_ctx* c, const aloam::BlockRec* blocks, int n, double* pose, const aloam::LmParams& lp, aloam::LmSummary* summary);
+void launch_lm_sharded(aloam_ctx* c, const aloam::BlockRec* blocks, const int* d_n, double* pose, const aloam::LmParams& lp, aloam::LmSummary* summary);
+void map_index_build(aloam_ctx* c, const Pt4* d_corner, const Pt4* d_surf, int n_upper);
+void map_register_device(aloam_ctx* c, const Pt4* d_corner_stack, const Pt4* d_surf_stack, const int* d_counts3, int nq_upper, double* d_pose, bool want_fits);
 namespace {
-inline void launch_lm_step(aloam_ctx* c, const BlockRec* blocks, int n, double* pose, const LmParams& lp, LmSummary* summary) {
-  if (c->shard_count <= 1) launch_lm(c, false, blocks, (const int*)nullptr, n, pose, lp, summary, 0, (double*)nullptr, (double*)nullptr, 0);
-  else launch_lm_sharded(c, blocks, n, pose, lp, summary);
-}
-
 LmParams lm_params(const aloam_config& c) {
   LmParams p;
   p.max_iters = c.inner_iters; p.huber_a = c.huber;

@@ -8,7 +8,7 @@
 #define ALOAM_ERR_RING_TOO_LARGE_DEV (-7)    // == ALOAM_ERR_RING_TOO_LARGE
 #define ALOAM_LM_THREADS 288
 #define ALOAM_LM_MAX_TRACE 8
-#define ALOAM_N_KERNEL_IDS 16
+#define ALOAM_N_KERNEL_IDS 32
 
 namespace aloam {
 
@@ -66,29 +66,32 @@ __global__ void k_knn_last(LastCloud cloud, const Pt4* queries, int nq, int* idx
 
 // ---- mapping.cu
 // hash grid over a map cloud = what replaces the kd-tree builds of laserMapping.cpp:558-559
+struct GridDyn {   // device-resident: everything about the indexed cloud that the kernels need and the host may not know
+  int n;           // points in the cloud
+  unsigned mask;   // table size - 1 (power of two >= 1.25 n)
+  int cursor;      // storage cursor of k_grid_alloc
+  int owned;       // sharded: points in cells this rank owns (halo excluded)
+};
 struct GridTable {
-  unsigned long long* keys;  // [mask+1] packed cell coordinates, ~0 = empty
-  int* cnt;                  // [mask+1] points in the cell
-  int* start;                // [mask+1] first slot of the cell in gpts
-  int* cursor;               // [1] storage cursor
-  int* slot_of;              // [capacity] table slot of point i
-  int* rank_of;              // [capacity] rank of point i inside its cell
-  float4* gpts;              // [capacity] cell-contiguous copy: x, y, z, bits(original index)
-  unsigned mask;             // table size - 1 (power of two)
-  float cs, inv_cs;          // cell edge [m]
+  uint4* slots;      // [cap_slots] one 16-byte word per slot: {cell key lo, hi (~0 = empty), points in the cell, end of its slice in gpts}
+  GridDyn* dyn;
+  float4* gpts;      // [capacity] cell-contiguous copy: x, y, z, bits(original index)
+  unsigned cap_slots;
+  float cs, inv_cs;  // cell edge [m]
 };
-struct MapCloud {
-  Pt4* pts;     // uploaded cloud, original order
-  int n;        // host-known size
-  GridTable grid;
-};
+struct MapCloud { GridTable grid; };
+unsigned grid_mask_for(int n, unsigned cap_slots);
+__global__ void k_grid_setup(GridTable a, const int* na, GridTable b, const int* nb);
 __global__ void k_grid_clear(GridTable a, GridTable b);
-__global__ void k_grid_insert(GridTable a, const Pt4* pa, int na, GridTable b, const Pt4* pb, int nb);
+__global__ void k_grid_insert(GridTable a, const Pt4* pa, GridTable b, const Pt4* pb, int shard_rank, int shard_count);
 __global__ void k_grid_alloc(GridTable a, GridTable b);
-__global__ void k_grid_fill(GridTable a, const Pt4* pa, int na, GridTable b, const Pt4* pb, int nb);
-// 5-NN + line / plane fit + residual block per stack point (laserMapping.cpp:577-687); queries = corner then surf
-__global__ void k_map_assoc(const Pt4* corner_stack, int n_corner, const Pt4* surf_stack, int n_surf, MapCloud corner_map,
-                            MapCloud surf_map, const double* pose7, BlockRec* blocks, double* fits, int shard_rank, int shard_count);
+__global__ void k_grid_fill(GridTable a, const Pt4* pa, GridTable b, const Pt4* pb);
+// 5-NN (warp per stack point) then line / plane fit + residual block (thread per stack point), laserMapping.cpp:577-687;
+// counts3 = {n_corner, n_surf, total} in device memory, queries = corner then surf
+__global__ void k_map_knn5(const Pt4* corner_stack, const Pt4* surf_stack, const int* counts3, MapCloud corner_map, MapCloud surf_map,
+                           const double* pose7, float4* nbr, int shard_rank, int shard_count);
+__global__ void k_map_fit(const Pt4* corner_stack, const Pt4* surf_stack, const int* counts3, const float4* nbr, BlockRec* blocks,
+                          double* fits);
 __global__ void k_map_knn(MapCloud map, const Pt4* queries, int nq, int k, int* idx, float* sqd);
 
 // ---- lm.cu
@@ -115,7 +118,7 @@ __global__ void k_lm_solve(const BlockRec* blocks, const int* n_blocks_ptr, int 
 // sharded solve: per-evaluation kernels around an ncclAllReduce (see lm.cu, comm.cu)
 size_t lm_state_bytes();
 size_t lm_dynamic_smem_bytes();   // dynamic shared memory of k_lm_solve / k_lm_eval_shard (opt-in > 48 KB)
-__global__ void k_lm_eval_shard(const BlockRec* blocks, int n, const double* x7, void* state, int first, double huber_a, double* local32);
+__global__ void k_lm_eval_shard(const BlockRec* blocks, const int* n_ptr, const double* x7, void* state, int first, double huber_a, double* local32);
 __global__ void k_lm_tr_shard(void* state, const double* tot32, double* x7, int first, int last, LmParams prm, LmSummary* summary);
 // packs API-side residual blocks (11 doubles) into BlockRec
 __global__ void k_pack_blocks(const double* packed, int n, BlockRec* out);

@@ -575,8 +575,9 @@ size_t lm_dynamic_smem_bytes() { return (size_t)NT * RS * sizeof(double); }
 // "stop" the remaining kernels return immediately.  Every rank runs the identical step on identical totals.
 size_t lm_state_bytes() { return sizeof(TrState); }
 
-__global__ void __launch_bounds__(NT, 1) k_lm_eval_shard(const BlockRec* __restrict__ blocks, int n, const double* __restrict__ x7,
+__global__ void __launch_bounds__(NT, 1) k_lm_eval_shard(const BlockRec* __restrict__ blocks, const int* __restrict__ n_ptr, const double* __restrict__ x7,
                                                          void* state, int first, double huber_a, double* __restrict__ local32) {
+  const int n = *n_ptr;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) double s_red[];
   __shared__ double s_part[NW][32];

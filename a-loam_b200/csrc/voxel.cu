@@ -217,9 +217,12 @@ extern "C" int aloam_voxel_filter_impl(aloam_ctx* c, aloam_cloud_view in, float 
   if (!c || !out || !(leaf > 0.f)) return ALOAM_ERR_INVALID_ARG;
   int rc = check_view(in); if (rc) return rc;
   if (in.n > c->max_points) return ALOAM_ERR_CAPACITY;
-  out->data = reinterpret_cast<const float*>(c->h_out[4]); out->n = 0; out->stride_floats = 4;
-  if (in.n == 0) return ALOAM_OK;
   CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  // the result has its OWN pinned buffer: a caller may pass a view returned by aloam_extract_features (h_out[*]) straight
+  // back in, so the output must not alias any other ctx-owned view
+  if (!c->h_vox_out) CUDA_CHECK_RET(cudaMallocHost((void**)&c->h_vox_out, (size_t)c->max_points * sizeof(Pt4)));
+  out->data = reinterpret_cast<const float*>(c->h_vox_out); out->n = 0; out->stride_floats = 4;
+  if (in.n == 0) return ALOAM_OK;
   const int n = in.n;
   if (!c->d_vox_keys[0]) {
     const size_t mp = (size_t)c->max_points;
@@ -255,7 +258,7 @@ extern "C" int aloam_voxel_filter_impl(aloam_ctx* c, aloam_cloud_view in, float 
   }
   const int nblk = (n + VCH - 1) / VCH;
   if (dxyz[0] * dxyz[1] * dxyz[2] > (long long)INT_MAX) {   // "leaf size is too small": PCL returns the input unchanged
-    CUDA_CHECK_RET(cudaMemcpyAsync(c->h_out[4], d_in, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(cudaMemcpyAsync(c->h_vox_out, d_in, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
     out->n = n;
     return ALOAM_OK;
@@ -281,7 +284,7 @@ extern "C" int aloam_voxel_filter_impl(aloam_ctx* c, aloam_cloud_view in, float 
   CUDA_CHECK_RET(cudaGetLastError());
   const int m = c->h_ints[48];
   if (m > 0) {
-    CUDA_CHECK_RET(cudaMemcpyAsync(c->h_out[4], d_out, (size_t)m * 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(cudaMemcpyAsync(c->h_vox_out, d_out, (size_t)m * 16, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
   }
   prof_collect(c);

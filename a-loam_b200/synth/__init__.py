@@ -74,3 +74,56 @@ def voxel_downsample(cloud, leaf):
     sums = np.add.reduceat(cloud[order].astype(np.float64), starts, axis=0)
     counts = np.diff(np.r_[starts, len(ks)])[:, None]
     return (sums / counts).astype(np.float32)
+
+
+def rotation_matrix(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+MAP_SCANS = list(range(0, 24))        # scans whose features make the base map
+MAP_QUERY_SCANS = list(range(24, 40))  # scans registered against it (not part of the map)
+
+
+def build_map(features, total_points, sensor="HDL-64", seed=BASE_SEED + 3, line_res=0.4, plane_res=0.8):
+    """Synthetic voxel map for the scan-to-map configs: union of the less-sharp / less-flat features of
+    scans MAP_SCANS at their true poses, voxel-filtered at line_res / plane_res, then replicated with 2 cm jitter on a
+    lattice of parallel streets (y pitch 30 m, 7 columns) and stacked levels (z pitch 8 m, 18 levels) INSIDE the
+    250 x 250 x 150 m volume of the reference's 5 x 5 x 3-cube submap (laserMapping.cpp:512-529) to exactly
+    total_points // 5 corner + the rest surf points.  The tile at offset 0 (the one the query scans see) is a clean
+    filtered map; if one lattice of tiles is not enough the other tiles are added again with an x shift and fresh jitter.
+    `features(raw) -> (less_sharp, less_flat)` is the extraction to use (the product's or the oracle's)."""
+    corner, surf = [], []
+    for k in MAP_SCANS:
+        ls, lf = features(scan(sensor, k))
+        qk, tk = pose(k)
+        R = rotation_matrix(qk)
+        for src, dst in ((ls, corner), (lf, surf)):
+            w = src.copy()
+            w[:, :3] = (src[:, :3].astype(np.float64) @ R.T + tk).astype(np.float32)
+            dst.append(w)
+    cbase = voxel_downsample(np.concatenate(corner), line_res)
+    sbase = voxel_downsample(np.concatenate(surf), plane_res)
+    rng = np.random.default_rng(seed)
+    offsets = [(0.0, 0.0, 0.0)]
+    for lvl in sorted(range(-9, 9), key=abs):
+        for col in sorted(range(-3, 4), key=abs):
+            if lvl or col:
+                offsets.append((0.0, 30.0 * col, 8.0 * lvl))
+
+    def tile(base, target):
+        out, n, rounds = [base], len(base), 0
+        while n < target:
+            for ox, oy, oz in offsets[1:]:
+                c = base.copy()
+                c[:, :3] += np.array([ox + 0.37 * rounds, oy, oz], np.float32) + rng.normal(0, 0.02, (len(base), 3)).astype(np.float32)
+                out.append(c)
+                n += len(c)
+                if n >= target:
+                    break
+            rounds += 1
+        return np.ascontiguousarray(np.concatenate(out)[:target])
+
+    return tile(cbase, total_points // 5), tile(sbase, total_points - total_points // 5)

@@ -1,24 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- scans/sec of the A-LOAM per-scan registration hot path on B200 (BASELINE.json metric).
 
-A "step" = one HDL-64-shaped synthetic scan (64x2000 firing pattern, ~128k returns, ~102k kept) through the
-whole hot path: feature extraction -> 2 x (correspondence search + LM solve) -> pose integration -> index build
-for the next scan, i.e. configs[1] of BASELINE.json.  Scans are consecutive poses of one seeded trajectory; the
+Headline (`value`, `e2e`): BASELINE configs[1].  A "step" = one HDL-64-shaped synthetic scan (64x2000 firing pattern,
+~128k returns, ~102k kept) through the whole scan-to-scan path: feature extraction -> 2 x (correspondence search + LM
+solve) -> pose integration -> index build for the next scan.  Scans are consecutive poses of one seeded trajectory; the
 odometry of scan k depends on scan k-1 exactly as in the reference (warm start + "last" clouds).
+  value : K scans already resident in HBM through ONE pipelined aloam_scan_stream call
+  e2e   : the same call on pinned HOST buffers (H2D of every raw scan and D2H of the poses inside the timed region)
+The K-step region is timed REPEATS times on consecutive, never-seen-before stretches of the trajectory (exactly K steps
+each, barrier + synchronize on both sides); the line reports the median repeat.  L2 hygiene: every step reads a raw scan
+that has not been touched before and the distinct raw scans of a run exceed the 126 MB L2.
 
-  value : scans/s with the raw scans already resident in HBM (aloam_scan_to_pose_device)
-  e2e   : scans/s through the public C ABI with HOST buffers: per step the raw scan is copied host->device from
-          pinned memory and the pose is read back (aloam_scan_to_pose)
-  --impl reference : the CPU oracle (a C++ restatement of the reference's Ceres+PCL path -- the reference itself
-          cannot be built in this image) run as the reference runs it: extraction and odometry as two pipelined
-          single-threaded stages (ascanRegistration | alaserOdometry)
-
-L2 hygiene: every step reads a raw scan that has never been touched before (1 + warmup + steps distinct scans of
-~2 MB each; with the defaults 141 MB > the 126 MB L2), so inputs always come from HBM.
-Timing: each C-ABI call is synchronous (returns after its stream is drained), so the K-step loop is bracketed by
-barrier + synchronize and timed on the host; the per-call device time (CUDA events on the context's stream) is
-reported next to it.  Multi-GPU: one process per GPU, independent scan streams (replicas, weak scaling, no
-data-path collective), time = max over ranks.
+Sub-records in the same JSON line:
+  mapping : BASELINE configs[2] (N = 1: 1M-point voxel map) / configs[3] (N > 1: N x 1M-point map sharded over the ranks,
+            one ncclAllReduce of the normal equations per LM evaluation): per step the rank's shard is re-indexed (the
+            reference rebuilds both kd-trees per frame) and the scan is registered with 2 x <= 4 LM iterations; L2 is
+            flushed between steps; pose error vs the CPU oracle; roofline of the index build (K0) and the 5-NN kernel.
+  batch   : BASELINE configs[4]: HDL-32 32x2200 scan stream, 16 trajectories in flight in ONE context (shared launches).
+  pose_rmse_vs_oracle_{m,rad}: RMSE of the K timed world poses against the CPU oracle run on the same scans.
+--impl reference : the CPU oracle (a C++ restatement of the reference's Ceres+PCL path -- the reference itself cannot be
+  built in this image) run as the reference runs it: extraction and odometry as two pipelined single-threaded stages.
+Multi-GPU: one process per GPU; the odometry path does not shard (replicas, weak scaling, no data-path collective), the
+mapping path shards the map; every time is the max over ranks.
 """
 import argparse
 import importlib
@@ -37,11 +40,22 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 SENSOR = "HDL-64"
+REPEATS = 7               # timed K-step regions (median reported)
+L2_BYTES = 126e6
+NOMINAL_SCAN_BYTES = 16 * 127_600   # ~127.6k returns per synthetic HDL-64 scan
 
 
-def gen_scans(synth, count, seed):
-    scans = [synth.scan(SENSOR, k, seed=seed) for k in range(count)]
-    return scans
+def frozen_config(args, K, W):
+    """identical for both arms (`--impl reference` prints the same dict): a function of the command line only"""
+    n_scans = 1 + W + REPEATS * K
+    return {"workload": "HDL-64 synthetic 64x2000 scan-to-scan odometry (BASELINE.json configs[1]): feature extraction + "
+                        "2 x (k-NN association + <=4-iter LM) + index build, consecutive scans of one trajectory",
+            "sensor": SENSOR, "azimuth_steps": 2000, "beams": 64, "outer_iters": 2, "inner_iters": 4,
+            "parallelism": "replicas x%d (independent scan streams, no collective); mapping sub-record: map sharded x%d" % (max(args.gpus, 1), max(args.gpus, 1)),
+            "repeats": REPEATS,
+            "l2": "every step reads a raw scan never touched before; %d distinct raw scans of ~%.2f MB = ~%.0f MB per run %s the 126 MB L2"
+                  % (n_scans, NOMINAL_SCAN_BYTES / 1e6, n_scans * NOMINAL_SCAN_BYTES / 1e6,
+                     ">" if n_scans * NOMINAL_SCAN_BYTES > L2_BYTES else "< (NOT larger than)")}
 
 
 _POLLER = r"""
@@ -62,15 +76,14 @@ while True:
         out.write('%.6f %d %d %d\n' % (time.time(), sm, mx, r)); out.flush()
     except Exception:
         pass
-    time.sleep(0.001)
+    time.sleep(0.002)
 """
 
 
 class ClockSampler:
-    """SM clock and clock-event (throttle) reasons sampled WHILE the timed region runs.  The timed regions here last tens
-    of milliseconds, so the samples come from a separate process that polls NVML every millisecond (a thread of this
-    process is starved by the launch loop); it is spawned early, `start()` / `stop()` only mark the window.  One
-    synchronous sample is added at each end of the window, so the result is never empty."""
+    """SM clock and clock-event (throttle) reasons sampled WHILE the timed regions run.  The samples come from a separate
+    process that polls NVML every 2 ms (a thread of this process is starved by the launch loop); it is spawned early,
+    `start()` / `stop()` only mark the window.  One synchronous sample is added at each end, so the result is never empty."""
     BITS = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
 
     def __init__(self, gpu_index):
@@ -146,16 +159,22 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
         reasons = sorted({n for r in rows for n, b in self.BITS if r[3] & b})
         return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": max(r[2] for r in rows), "reasons": reasons,
-                "samples": len(rows), "samples_inside_timed_region": inside, "source": "nvml (poller process, 1 ms)"}
+                "samples": len(rows), "samples_inside_timed_region": inside, "source": "nvml (poller process, 2 ms)"}
 
 
-def cpu_pipeline_sequential(orc, synth, scans):
-    """single-threaded oracle: extract -> register -> integrate -> set_last per scan; returns seconds per stage"""
-    ns, _, mr = synth.SENSORS[SENSOR][:3]
+def rot_angle(q1, q2):
+    return 2.0 * float(np.arccos(min(1.0, abs(float(np.dot(q1, q2))))))
+
+
+def cpu_odometry_sequential(orc, synth, scans, sensor=SENSOR):
+    """single-threaded oracle: extract -> register -> integrate -> set_last per scan.
+    Returns (seconds, extraction seconds, odometry seconds, world poses (n, 7))"""
+    ns, _, mr = synth.SENSORS[sensor][:3]
     od = orc.Odometry()
     q = np.array([0, 0, 0, 1.0]); t = np.zeros(3)
     qw = np.array([0, 0, 0, 1.0]); tw = np.zeros(3)
     t_ext = t_odo = 0.0
+    poses = np.zeros((len(scans), 7))
     t0 = time.perf_counter()
     for k, raw in enumerate(scans):
         a = time.perf_counter()
@@ -168,7 +187,8 @@ def cpu_pipeline_sequential(orc, synth, scans):
         c = time.perf_counter()
         t_ext += b - a
         t_odo += c - b
-    return time.perf_counter() - t0, t_ext, t_odo
+        poses[k, :4] = qw; poses[k, 4:] = tw
+    return time.perf_counter() - t0, t_ext, t_odo, poses
 
 
 def cpu_pipeline_two_stage(orc, synth, scans, warmup):
@@ -204,57 +224,49 @@ def cpu_pipeline_two_stage(orc, synth, scans, warmup):
     return time.perf_counter() - t_start
 
 
-def _rot(q):
-    x, y, z, w = q
-    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
-                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
-                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+def pose_rmse(got, ref):
+    """translation RMSE [m] and rotation RMSE [rad] (angle 2 acos|q.q'|) over rows of (q xyzw, t)"""
+    dt = np.linalg.norm(got[:, 4:] - ref[:, 4:], axis=1)
+    dr = np.array([rot_angle(a[:4], b[:4]) for a, b in zip(got, ref)])
+    return float(np.sqrt(np.mean(dt ** 2))), float(np.sqrt(np.mean(dr ** 2))), float(dt.max()), float(dr.max())
 
 
-def bench_mapping(args, synth, rank, world, local_rank):
-    """BASELINE configs[2]/[3]: HDL-64 scan-to-map against a synthetic voxel map of 1M points per GPU (200k corner +
-    800k surf), 2 outer x <= 4 inner LM iterations (<= 10 normal-equation builds).  A step = index build over the
-    resident submap (what replaces the reference's per-frame kd-tree builds) + 2 x (5-NN + fits) + LM.  With
-    --gpus N the map is N x 1M points split into x-slabs over the ranks (one ncclAllReduce of the 6x6/6x1 system per
-    evaluation); every rank holds the same stacks.  `e2e` additionally uploads the shard from host memory each step."""
-    import torch
-    import torch.distributed as dist
-    pkg = importlib.import_module("a-loam_b200")
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def committed_traffic(kernel):
+    """dram bytes per launch from the committed `ncu --set full` captures (profiles/traffic.json), or None"""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(kernel)
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def mapping_record(args, synth, pkg, ctx_feat, rank, world, local_rank, dist, torch, K, W):
+    """BASELINE configs[2] / [3]: scan-to-map against a 1M-point-per-GPU voxel map (N > 1: sharded, real ncclAllReduce)."""
     shard = importlib.import_module("a-loam_b200.shard")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    K, W = args.steps, max(args.warmup, 3)
-    total_pts = args.map_points or 1_000_000 * world
-    ctx = pkg.Aloam(n_scans=64, device=local_rank, max_points=200000, max_map_points=int(total_pts * 1.05 / world) + 200000)
-    # base map: features of 12 scans at their true poses (product's own extraction), voxel-filtered at 0.4 / 0.8
-    corner, surf = [], []
-    for k in list(range(0, 24, 2)):
-        f = ctx.extract_features(synth.scan(SENSOR, k))
-        qk, tk = synth.pose(k); R = _rot(qk)
-        for src, dst in [(f["less_sharp"], corner), (f["less_flat"], surf)]:
-            w = src.copy(); w[:, :3] = (src[:, :3].astype(np.float64) @ R.T + tk).astype(np.float32); dst.append(w)
-    cbase = synth.voxel_downsample(np.concatenate(corner), 0.4)
-    sbase = synth.voxel_downsample(np.concatenate(surf), 0.8)
-    rng = np.random.default_rng(20240901 + 3)
+    total_pts = 1_000_000 * world
+    Km = min(K, len(synth.MAP_QUERY_SCANS) - 3)
+    Wm = 3
 
-    def tile(base, target):
-        """replicate the base map with jitter on a lattice of offsets (parallel streets / stacked levels) to `target` points"""
-        out = [base]
-        n = len(base); k = 0
-        while n < target:
-            k += 1
-            off = np.array([0.0, 45.0 * ((k + 1) // 2) * (1 if k % 2 else -1), 0.0], np.float32)
-            c = base.copy(); c[:, :3] += off + rng.normal(0, 0.02, (len(base), 3)).astype(np.float32)
-            out.append(c); n += len(c)
-        return np.ascontiguousarray(np.concatenate(out)[:target])
-    cmap = tile(cbase, total_pts // 5)
-    smap = tile(sbase, total_pts - total_pts // 5)
+    def feats(raw):
+        f = ctx_feat.extract_features(raw)
+        return f["less_sharp"], f["less_flat"]
+    cmap, smap = synth.build_map(feats, total_pts)
     my_c, my_s = shard.shard_cloud(cmap, rank, world), shard.shard_cloud(smap, rank, world)
+    m_loc = len(my_c) + len(my_s)
+    ctx = pkg.Aloam(n_scans=64, device=local_rank, max_points=200000, max_map_points=max(len(my_c), len(my_s)) + 1024)
     stacks = []
-    for k in range(1, 1 + W + K):
-        f = ctx.extract_features(synth.scan(SENSOR, (2 * k + 1) % 24))
-        stacks.append((ctx.voxel_filter(f["less_sharp"], 0.4), ctx.voxel_filter(f["less_flat"], 0.8), (2 * k + 1) % 24))
+    for k in synth.MAP_QUERY_SCANS[:Wm + Km]:
+        f = ctx_feat.extract_features(synth.scan(SENSOR, k))
+        q, t = synth.pose(k)
+        x0 = np.concatenate([q, t + np.array([0.05, -0.04, 0.02])])
+        stacks.append((ctx.voxel_filter(f["less_sharp"], 0.4), ctx.voxel_filter(f["less_flat"], 0.8), x0, k))
     if world > 1:
         idb = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -267,78 +279,151 @@ def bench_mapping(args, synth, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
-    def x0_of(k):
-        q, t = synth.pose(k)
-        return np.concatenate([q, t + np.array([0.05, -0.04, 0.02])])
-
-    sampler = ClockSampler(local_rank)
-    # the shard twice: resident in HBM (`value`) and in pinned host memory (`e2e`)
     dev_c, dev_s = torch.from_numpy(my_c).cuda(), torch.from_numpy(my_s).cuda()
     pin_c, pin_s = torch.from_numpy(my_c).pin_memory(), torch.from_numpy(my_s).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # 2 x L2
 
-    def run(timed, profile=False, host=False):
-        ctx.profile_enable(profile)
+    def run(host, profile=False):
         mc, ms = (pin_c, pin_s) if host else (dev_c, dev_s)
-        def upload():
+        step_s = []
+        poses = []
+        launches = 0
+        ctx.profile_enable(False)
+        for i in range(Wm + Km):
+            if i == Wm and profile:
+                ctx.profile_enable(True)
+            flush.fill_(i & 0xFF)          # L2 flush between steps (the shard + its index fit in L2)
+            barrier()
+            l0 = ctx.launch_count()
+            t0 = time.perf_counter()
             ctx.map_upload_ptr(mc.data_ptr(), mc.shape[0], ms.data_ptr(), ms.shape[0])
-        for i in range(W):
-            upload(); ctx.mapping_register(stacks[i][0], stacks[i][1], x0_of(stacks[i][2]))
-        barrier(); l0 = ctx.launch_count(); t0 = time.perf_counter(); err = 0.0
-        for i in range(W, W + timed):
-            upload()
-            x, st = ctx.mapping_register(stacks[i][0], stacks[i][1], x0_of(stacks[i][2]))
-            err = max(err, float(np.abs(x[4:] - synth.pose(stacks[i][2])[1]).max()))
-        torch.cuda.synchronize(); t1 = time.perf_counter(); barrier()
-        return t1 - t0, ctx.launch_count() - l0, err, st
-    sampler.start()
-    secs, launches, err, st = run(K)
-    clocks = sampler.stop()
-    secs_host, _, _, _ = run(K, host=True)
-    run(K, profile=True)
+            x, st = ctx.mapping_register(stacks[i][0], stacks[i][1], stacks[i][2])
+            t1 = time.perf_counter()
+            if i >= Wm:
+                step_s.append(t1 - t0); poses.append(x); launches += ctx.launch_count() - l0
+        ts = torch.tensor(step_s, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)     # every step: the slowest rank
+        return float(ts.sum()), poses, launches, st
+
+    secs, poses, launches, st = run(False)
+    secs_host, poses_host, _, _ = run(True)
+    run(False, profile=True)
     prof = ctx.profile_read()
-    if world > 1:
-        th = torch.tensor([secs_host], dtype=torch.float64, device="cuda"); dist.all_reduce(th, op=dist.ReduceOp.MAX); secs_host = float(th[0])
-    if world > 1:
-        tt = torch.tensor([secs], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); secs = float(tt[0])
+    ctx.profile_enable(False)
+    rec = None
     if rank == 0:
-        per_kernel = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / K, "ms_per_step": v[0] / K} for k, v in prof.items()}
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        m_loc = len(my_c) + len(my_s)
-        grid_ms = per_kernel.get("k_map_grid", {}).get("ms_per_step", 0.0)
-        grid_bytes = 36 * m_loc    # 16 B read + 16 B cell-sorted copy + 4 B slot (SURVEY.md 8d "K0 index build")
-        line = {"metric": "scans/sec", "value": K / secs, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * secs / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-                "config": {"workload": "HDL-64 scan-to-map, %d-pt synthetic voxel map (%d corner + %d surf), %s, 2 outer x <=4 inner LM iterations; per step the"
-                                       " shard is copied into the context and re-indexed (the reference rebuilds both kd-trees per frame): value = shard resident in HBM, e2e = shard in pinned host memory" %
-                                       (total_pts, len(cmap), len(smap), "1 GPU" if world == 1 else "x-slab shards + halo over %d GPUs, ncclAllReduce(32 f64) per evaluation" % world),
-                           "map_points_this_rank": m_loc, "stack_points": int(len(stacks[W][0]) + len(stacks[W][1])), "l2": "map shard %.0f MB streamed each step (> L2 together with its cell-sorted copy)" % (16 * m_loc / 1e6)},
-                "clocks": clocks, "gpu_launches": launches,
-                "e2e": {"value": K / secs_host, "unit": "scans/s", "ms_per_step": 1e3 * secs_host / K, "h2d_bytes_per_step": 16 * m_loc + 16 * int(len(stacks[W][0]) + len(stacks[W][1])), "d2h_bytes_per_step": 56 + 4 * 560},
-                "roofline": {"bound": "hbm", "kernel": "k_map_grid (K0: clear + insert + alloc + fill)", "achieved": (grid_bytes / (grid_ms * 1e-3) / 1e9) if grid_ms else 0.0,
-                             "peak": peak, "unit": "GB/s", "frac": (grid_bytes / (grid_ms * 1e-3) / 1e9 / peak) if grid_ms else 0.0, "traffic": None,
-                             "algorithmic_bytes_per_launch": grid_bytes, "per_kernel": per_kernel},
-                "pose_error_vs_truth_max_m": err, "last_stats": st}
-        emit(line)
+        import pyoracle as orc
+        peak, peak_src = peak_hbm()
+        per_kernel = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / Km, "ms_per_step": v[0] / Km} for k, v in prof.items()}
+        nq = int(len(stacks[Wm][0]) + len(stacks[Wm][1]))
+        # oracle on the WHOLE map (what the sharded ranks must reproduce together): pose parity + CPU baseline
+        m = orc.Mapping()
+        t0 = time.perf_counter(); m.set_map(cmap, smap); tree_s = time.perf_counter() - t0
+        n_chk = min(3, Km)
+        err_t = err_r = 0.0
+        reg_s = 0.0
+        for j in range(n_chk):
+            cs, ss, x0, _k = stacks[Wm + j]
+            t0 = time.perf_counter(); xr, _info = m.register(cs, ss, x0); reg_s += time.perf_counter() - t0
+            err_t = max(err_t, float(np.abs(poses[j][4:] - xr[4:]).max())); err_r = max(err_r, rot_angle(poses[j][:4], xr[:4]))
+        cpu_val = 1.0 / (tree_s + reg_s / n_chk)
+        roofs = {}
+        for name, alg in (("k_map_grid(4 launches)", 36 * m_loc), ("k_map_knn5", 16 * m_loc + 16 * nq + 8 * 5 * nq)):
+            if name in per_kernel:
+                launches_per_unit = 4 if "grid" in name else 1
+                ms_unit = per_kernel[name]["ms_per_launch"] * launches_per_unit
+                ach = alg / (ms_unit * 1e-3) / 1e9
+                roofs[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes": alg,
+                               "ms": ms_unit, "traffic": committed_traffic(name.split("(")[0] + ("_%dM" % (m_loc // 1_000_000 or 1)))}
+        if "k_map_knn5" in roofs:
+            roofs["k_map_knn5"]["note"] = ("grid-pruned search: it touches only the 27 cells around each query, far fewer bytes than the 16 M of the "
+                                           "algorithmic model (SURVEY.md 8d); `traffic` is the measured DRAM volume")
+        rec = {"metric": "scans/sec", "value": Km / secs, "unit": "scans/s", "n_gpus": world, "steps": Km, "warmup": Wm, "ms_per_step": 1e3 * secs / Km,
+               "scaling": "weak", "config": {"workload": "HDL-64 scan-to-map (BASELINE.json configs[%d]): %d-point synthetic voxel map (%d corner + %d surf) inside the "
+                                                         "250x250x150 m submap volume, %s; per step the rank's shard (%d points) is re-indexed and the scan registered with "
+                                                         "2 outer x <=4 inner LM iterations" % (2 if world == 1 else 3, total_pts, len(cmap), len(smap),
+                                                         "1 GPU" if world == 1 else "x-slab shards + 1-cell halo over %d GPUs, one ncclAllReduce(32 f64) per LM evaluation" % world, m_loc),
+                                            "stack_points": nq, "l2": "256 MB written between steps (shard + index fit in L2 otherwise)"},
+               "gpu_launches": launches,
+               "e2e": {"value": Km / secs_host, "unit": "scans/s", "ms_per_step": 1e3 * secs_host / Km, "h2d_bytes_per_step": 16 * m_loc + 16 * nq, "d2h_bytes_per_step": 56 + 4 * 560,
+                       "api": "aloam_map_upload + aloam_mapping_register with the shard and the stacks in host memory"},
+               "roofline": roofs, "per_kernel": per_kernel,
+               "cpu_baseline": {"value": cpu_val, "unit": "scans/s", "cores": 1, "kind": "port",
+                                "sample": "%d scans against the whole %d-point map: two kd-tree builds %.3f s per frame (laserMapping.cpp:558-559) + "
+                                          "2 x (5-NN + fits + LM) %.3f s" % (n_chk, total_pts, tree_s, reg_s / n_chk)},
+               "pose_vs_oracle_max": {"m": err_t, "rad": err_r, "scans": n_chk, "tolerance": 1e-4},
+               "host_equals_device_path": bool(all(np.array_equal(a, b) for a, b in zip(poses, poses_host))),
+               "last_stats": st}
     ctx.close()
+    del flush
+    return rec
+
+
+def batch_record(args, synth, pkg, rank, world, local_rank, dist, torch, K, W):
+    """BASELINE configs[4]: HDL-32 32x2200, B trajectories in flight in ONE context / ONE host thread (shared launches)."""
+    if not hasattr(pkg.Aloam, "scan_stream_batch"):
+        return None
+    B = 16
+    sensor = "HDL-32"
+    Kb, Wb = K, 3
+    n = 1 + Wb + Kb
+    # B trajectories = B differently seeded noise realisations of the trajectory (same poses, different returns)
+    scans = [[synth.scan(sensor, k, seed=synth.BASE_SEED + 100 + 16 * rank + b) for k in range(n)] for b in range(B)]
+    maxn = max(s.shape[0] for tr in scans for s in tr)
+    host = torch.zeros((n, B, maxn, 4), dtype=torch.float32).pin_memory()
+    counts = np.zeros((n, B), np.int32)
+    for b in range(B):
+        for k in range(n):
+            s = scans[b][k]; host[k, b, :s.shape[0]] = torch.from_numpy(s); counts[k, b] = s.shape[0]
+    dev = host.to("cuda")
+    ctx = pkg.Aloam(n_scans=32, device=local_rank, max_points=maxn + 1024, max_batch=B, max_ring_points=2304)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def run(base):
+        ctx.reset_odometry()
+        ptrs = np.array([[base[k, b].data_ptr() for b in range(B)] for k in range(n)], np.uint64)
+        ctx.scan_stream_batch(ptrs[:1 + Wb], counts[:1 + Wb], base is dev)
+        barrier()
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        poses = ctx.scan_stream_batch(ptrs[1 + Wb:], counts[1 + Wb:], base is dev)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        return t1 - t0, poses, ctx.launch_count() - l0
+    secs, poses, launches = run(dev)
+    secs_host, poses_h, _ = run(host)
+    tt = torch.tensor([secs, secs_host], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.destroy_process_group()
-    return 0
-
-
-class _QuietStdout:
-    """Everything native libraries print on fd 1 while the benchmark runs (NCCL's version banner, ...) goes to stderr, so
-    that stdout carries exactly one JSON line."""
-
-    def __enter__(self):
-        sys.stdout.flush()
-        self.saved = os.dup(1)
-        os.dup2(2, 1)
-        return self
-
-    def __exit__(self, *a):
-        sys.stdout.flush()
-        os.dup2(self.saved, 1)
-        os.close(self.saved)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    secs, secs_host = float(tt[0]), float(tt[1])
+    rec = None
+    if rank == 0:
+        # parity: lane 0 equals its solo run bit for bit; lane 0 vs the CPU oracle
+        solo = pkg.Aloam(n_scans=32, device=local_rank, max_points=maxn + 1024, max_ring_points=2304)
+        sp, _ = solo.scan_stream([dev[k, 0].data_ptr() for k in range(n)], counts[:, 0], True)
+        solo.close()
+        import pyoracle as orc
+        _, _, _, op = cpu_odometry_sequential(orc, synth, scans[0][:1 + Wb + min(Kb, 8)], sensor)
+        got = np.concatenate([np.zeros((0, 7)), poses[:min(Kb, 8), 0]])
+        rm, rr, mm, mr_ = pose_rmse(got, op[1 + Wb:])
+        rec = {"metric": "scans/sec", "value": B * Kb * world / secs, "unit": "scans/s", "n_gpus": world, "steps": Kb, "warmup": Wb, "batch": B,
+               "ms_per_step": 1e3 * secs / Kb, "scaling": "weak",
+               "config": {"workload": "HDL-32 synthetic 32x2200 scan stream (BASELINE.json configs[4]), %d trajectories in flight per GPU in one context "
+                                      "(aloam_scan_stream_batch: every kernel launch covers all %d scans of a step)" % (B, B),
+                          "points_per_scan_raw": int(counts.mean())},
+               "e2e": {"value": B * Kb * world / secs_host, "unit": "scans/s", "h2d_bytes_per_step": int(16 * counts[1 + Wb:].sum() / Kb), "d2h_bytes_per_step": 56 * B},
+               "gpu_launches": launches,
+               "lane0_equals_solo_run": bool(np.array_equal(poses[:, 0], sp[1 + Wb:])),
+               "host_equals_device_path": bool(np.array_equal(poses, poses_h)),
+               "pose_rmse_vs_oracle_m": rm, "pose_rmse_vs_oracle_rad": rr}
+    ctx.close()
+    return rec
 
 
 def emit(line):
@@ -353,38 +438,32 @@ def main():
     os.dup2(2, 1)   # from here on fd 1 is stderr; the JSON line is written to the saved descriptor by emit()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="extra measurement at N=1: this many independent trajectories on one GPU (0/1 = skip)")
-    ap.add_argument("--workload", default="odometry", choices=["odometry", "mapping"],
-                    help="odometry = BASELINE configs[1] (the contract line); mapping = configs[2] (1M-pt map) / configs[3] (8M-pt map sharded over --gpus)")
-    ap.add_argument("--map-points", type=int, default=0, help="mapping workload: total map points (default 1M per GPU)")
+    ap.add_argument("--no-mapping", action="store_true", help="skip the scan-to-map sub-record (configs[2] / [3])")
+    ap.add_argument("--no-batch", action="store_true", help="skip the batched-stream sub-record (configs[4])")
     args = ap.parse_args()
     K, W = max(args.steps, 1), max(args.warmup, 3)   # never fewer than 3 untimed warm-up steps
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    n_scans_needed = 1 + W + K
-
+    n_scans_needed = 1 + W + REPEATS * K
+    config = frozen_config(args, K, W)
     synth = importlib.import_module("a-loam_b200.synth")
-    if args.workload == "mapping":
-        return bench_mapping(args, synth, rank, world, local_rank)
-    config = {"workload": "HDL-64 synthetic 64x2000 scan-to-scan odometry (BASELINE.json configs[1]): feature extraction + "
-                          "2 x (k-NN association + <=4-iter LM) + index build, consecutive scans of one trajectory",
-              "sensor": SENSOR, "azimuth_steps": 2000, "beams": 64, "outer_iters": 2, "inner_iters": 4,
-              "parallelism": "replicas x%d (independent scan streams, no collective)" % max(world, 1)}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         import pyoracle as orc
-        scans = gen_scans(synth, n_scans_needed, synth.BASE_SEED + 1)
+        n_ref = 1 + W + K
+        scans = [synth.scan(SENSOR, k, seed=synth.BASE_SEED + 1) for k in range(n_ref)]
         # weak scaling like the GPU arm: one independent scan stream (a two-thread pipeline) per GPU of the job, as far as
         # the host has cores for them
         n_rep = max(1, min(args.gpus, (os.cpu_count() or 2) // 2))
         secs_rep = [None] * n_rep
+
         def rep(j):
             secs_rep[j] = cpu_pipeline_two_stage(orc, synth, scans, W)
         ths = [threading.Thread(target=rep, args=(j,)) for j in range(n_rep)]
@@ -417,8 +496,8 @@ def main():
         if world > 1:
             dist.barrier()
 
-    sampler = ClockSampler(local_rank)   # spawns the NVML poller now; the window is marked around the timed region
-    scans = gen_scans(synth, n_scans_needed, synth.BASE_SEED + 1 + rank)
+    sampler = ClockSampler(local_rank)   # spawns the NVML poller now; the window is marked around the timed regions
+    scans = [synth.scan(SENSOR, k, seed=synth.BASE_SEED + 1 + rank) for k in range(n_scans_needed)]
     counts = [s.shape[0] for s in scans]
     maxn = max(counts)
     host = torch.zeros((n_scans_needed, maxn, 4), dtype=torch.float32).pin_memory()
@@ -427,102 +506,80 @@ def main():
     dev = host.to("cuda", non_blocking=False)
     torch.cuda.synchronize()
     ctx = pkg.Aloam(n_scans=64, device=local_rank, max_points=maxn + 1024)
+    distinct_bytes = 16 * int(sum(counts))
 
-    def run(mode, timed_steps, profile=False):
-        """returns (wall seconds for the timed steps, sum of per-call device ms, launches, last pose)"""
+    def run_stream(mode):
+        """warm-up call (1 + W scans), then REPEATS timed calls of exactly K scans each on fresh stretches of the trajectory"""
         ctx.reset_odometry()
-        ctx.profile_enable(profile)
+        ctx.profile_enable(False)
+        base = dev if mode == "device" else host
+        ptrs = [base[i].data_ptr() for i in range(n_scans_needed)]
+        poses_all = [ctx.scan_stream(ptrs[:1 + W], counts[:1 + W], mode == "device")[0]]
+        secs, devms, launches = [], [], 0
+        for r in range(REPEATS):
+            a, b = 1 + W + r * K, 1 + W + (r + 1) * K
+            barrier()
+            l0 = ctx.launch_count()
+            t0 = time.perf_counter()
+            poses, st = ctx.scan_stream(ptrs[a:b], counts[a:b], mode == "device")
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            barrier()
+            secs.append(t1 - t0); devms.append(st.ms_total); launches = ctx.launch_count() - l0
+            poses_all.append(poses)
+        return secs, devms, launches, np.concatenate(poses_all)
+
+    def run_sync(mode, profile=False):
+        """one synchronous aloam_scan_to_pose(_device) call per scan (latency mode); profiling covers the timed steps only"""
+        ctx.reset_odometry()
+        ctx.profile_enable(False)
 
         def step(i):
             if mode == "device":
                 return ctx.scan_to_pose_device(dev[i].data_ptr(), counts[i])
             return ctx.scan_to_pose_ptr(host[i].data_ptr(), counts[i])
-        for i in range(1 + W):       # frame 0 only initialises; then W untimed warm-up steps
+        for i in range(1 + W):
             step(i)
         barrier()
-        l0 = ctx.launch_count()
+        if profile:
+            ctx.profile_enable(True)
         dev_ms = 0.0
         t0 = time.perf_counter()
-        for i in range(1 + W, 1 + W + timed_steps):
+        for i in range(1 + W, 1 + W + K):
             q, t, st = step(i)
             dev_ms += st.ms_total
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         barrier()
-        return t1 - t0, dev_ms, ctx.launch_count() - l0, (q, t)
-
-    def run_stream(mode, timed_steps):
-        """the pipelined C-ABI call (aloam_scan_stream): one call for the warm-up scans, one timed call for the K scans"""
-        ctx.reset_odometry()
-        ctx.profile_enable(False)
-        base = dev if mode == "device" else host
-        ptrs = [base[i].data_ptr() for i in range(n_scans_needed)]
-        ctx.scan_stream(ptrs[:1 + W], counts[:1 + W], mode == "device")
-        barrier()
-        l0 = ctx.launch_count()
-        t0 = time.perf_counter()
-        poses, st = ctx.scan_stream(ptrs[1 + W:1 + W + timed_steps], counts[1 + W:1 + W + timed_steps], mode == "device")
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        barrier()
-        return t1 - t0, st.ms_total, ctx.launch_count() - l0, (poses[-1][:4], poses[-1][4:])
-
-    def run_multi(n_streams, timed_steps):
-        """n_streams independent trajectories (one context and one host thread each) sharing this GPU: aggregate scans/s"""
-        import threading
-        ctxs = [pkg.Aloam(n_scans=64, device=local_rank, max_points=maxn + 1024) for _ in range(n_streams)]
-        ptrs = [dev[i].data_ptr() for i in range(n_scans_needed)]
-        for c in ctxs:
-            c.scan_stream(ptrs[:1 + W], counts[:1 + W], True)
-        torch.cuda.synchronize()
-        res = [None] * n_streams
-        reps = 4    # each trajectory goes over the timed scans `reps` times (one pipelined call each): a longer region than
-                    # thread start-up jitter; the trajectory simply continues, every stream sees the same sequence
-        go = threading.Event()
-        def work(j):
-            go.wait()
-            for _ in range(reps):
-                res[j] = ctxs[j].scan_stream(ptrs[1 + W:1 + W + timed_steps], counts[1 + W:1 + W + timed_steps], True)[0]
-        th = [threading.Thread(target=work, args=(j,)) for j in range(n_streams)]
-        for t_ in th: t_.start()
-        time.sleep(0.05)
-        t0 = time.perf_counter()
-        go.set()
-        for t_ in th: t_.join()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        t1 = t0 + (t1 - t0) / reps   # per pass over the timed scans
-        same = all(np.array_equal(res[0], r) for r in res[1:])
-        for c in ctxs: c.close()
-        return t1 - t0, same
+        return t1 - t0, dev_ms, np.concatenate([q, t])
 
     sampler.start()
-    sync_dev, devms_sync, _, pose_sync = run("device", K)
-    sync_e2e, _, _, _ = run("host", K)
-    secs_dev, devms_dev, launches, pose_dev = run_stream("device", K)
-    secs_e2e, devms_e2e, _, pose_e2e = run_stream("host", K)
+    secs_dev, devms_dev, launches, poses_dev = run_stream("device")
+    secs_e2e, _, _, poses_e2e = run_stream("host")
+    sync_dev, devms_sync, pose_sync = run_sync("device")
+    sync_e2e, _, _ = run_sync("host")
     clocks = sampler.stop()
-    multi = None
-    if world == 1 and args.streams > 1:
-        secs_multi, same = run_multi(args.streams, K)
-        multi = {"streams": args.streams, "value": args.streams * K / secs_multi, "unit": "scans/s", "identical_poses_across_streams": bool(same),
-                 "note": "%d independent trajectories, one context + one host thread each, on the same GPU (HBM-resident scans), "
-                         "each going 4 times over the timed scans; the headline value is ONE trajectory" % args.streams}
-    _, _, _, _ = run("device", K, profile=True)
+    run_sync("device", profile=True)
     prof = ctx.profile_read()
     ctx.profile_enable(False)
 
-    # max over ranks
+    # max over ranks of every timed region, then the median repeat
+    tt = torch.tensor(secs_dev + secs_e2e + [sync_dev, sync_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
-        tt = torch.tensor([secs_dev, secs_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        secs_dev, secs_e2e = float(tt[0]), float(tt[1])
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt[0])
+    tt = tt.cpu().numpy()
+    rep_dev, rep_e2e = tt[:REPEATS], tt[REPEATS:2 * REPEATS]
+    sync_dev, sync_e2e = float(tt[-2]), float(tt[-1])
+    med_dev, med_e2e = float(np.median(rep_dev)), float(np.median(rep_e2e))
+
+    mapping = None if args.no_mapping else mapping_record(args, synth, pkg, ctx, rank, world, local_rank, dist, torch, K, W)
+    batch = None if args.no_batch else batch_record(args, synth, pkg, rank, world, local_rank, dist, torch, K, W)
 
     if rank == 0:
-        # sizes of one representative scan for the algorithmic-bytes model (DESIGN.md section 4)
+        import pyoracle as orc
         feats = ctx.extract_features(scans[1 + W])
         n_raw = counts[1 + W]
         n_full = feats["full"].shape[0]
@@ -535,60 +592,56 @@ def main():
             "k_scatter": 16 * n_raw + n_raw + 16 * n_full,
             "k_ring_features": 16 * n_full + 16 * n_out + 5 * n_full,
             "k_compact": 2 * 16 * n_out,
-            "k_tile_bounds": 16 * n_m / 2 + 32 * (n_m / 32) / 2,   # per launch (two launches, one per cloud)
+            "k_rab_build(3 launches)": 16 * n_m + 16 * n_m + 8 * n_m,
             "k_odom_assoc": 16 * n_m + 16 * n_q + 8 * 3 * n_q + 88 * n_q,
-            "k_lm_solve": 88 * (768 + 1536) * 5,
+            "k_lm_solve": 88 * (768 + 1536),
         }
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
+        peak, peak_src = peak_hbm()
         per_kernel = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / K, "ms_per_step": v[0] / K} for k, v in prof.items()}
         dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
         dom_ms = per_kernel[dom]["ms_per_launch"]
         achieved = alg_bytes.get(dom, 0) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or null
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            traffic = tj["traffic"] if tj.get("kernel") == dom else tj.get("others", {}).get(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes.get(dom, 0),
+                    "traffic": committed_traffic(dom), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes.get(dom, 0),
                     "ms_per_launch": dom_ms, "per_kernel": per_kernel,
-                    "note": "single ~2 MB scans are latency/occupancy bound, not HBM bound (SURVEY.md 8d): frac is expected << 1"}
+                    "note": "single ~2 MB scans are latency/occupancy bound, not HBM bound (SURVEY.md 8d): frac is expected << 1; per_kernel is "
+                            "measured with CUDA events around every launch of the K timed steps of the synchronous API (launches_per_step = launches / K)"}
 
+        # pose RMSE of the K timed scans of the first repeat against the CPU oracle on the same scans (BASELINE.json metric)
+        n_chk = 1 + W + K
+        tot, t_ext, t_odo, oposes = cpu_odometry_sequential(orc, synth, scans[:n_chk])
+        rm, rr, mm, mr_ = pose_rmse(poses_dev[1 + W:n_chk], oposes[1 + W:])
+        rm_e, rr_e, _, _ = pose_rmse(poses_e2e[1 + W:n_chk], oposes[1 + W:])
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            import pyoracle as orc
-            sample = scans[:min(len(scans), 1 + 60)]
-            tot, t_ext, t_odo = cpu_pipeline_sequential(orc, synth, sample)
-            cpu_baseline = {"value": (len(sample) - 1) / tot, "unit": "scans/s", "cores": 1, "kind": "port",
+            cpu_baseline = {"value": (n_chk - 1) / tot, "unit": "scans/s", "cores": 1, "kind": "port",
                             "sample": "%d consecutive HDL-64 scans of the same stream, single thread; extraction %.1f ms/scan, "
                                       "odometry (kd-tree builds + 2 x (association + LM)) %.1f ms/scan" %
-                                      (len(sample), 1e3 * t_ext / len(sample), 1e3 * t_odo / len(sample))}
+                                      (n_chk, 1e3 * t_ext / n_chk, 1e3 * t_odo / n_chk)}
         total_scans = K * world
-        config["points_per_scan_raw"] = n_raw
-        config["points_per_scan_kept"] = n_full
-        config["queries_per_scan"] = n_q
-        config["targets_per_scan"] = n_m
-        config["l2"] = ("inputs larger than L2: %d distinct raw scans of %.2f MB = %.0f MB > 126 MB, each read once"
-                        % (n_scans_needed, 16 * n_raw / 1e6, 16 * n_raw * n_scans_needed / 1e6))
-        line = {"metric": "scans/sec", "value": total_scans / secs_dev, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": 1e3 * secs_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        line = {"metric": "scans/sec", "value": total_scans / med_dev, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": 1e3 * med_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32/f64", "data": "synthetic", "config": config, "clocks": clocks,
-                "device_ms_per_step": devms_dev / K,
+                "timing": {"repeats": REPEATS, "statistic": "median", "ms_per_step_each_repeat": [1e3 * float(s) / K for s in rep_dev],
+                           "timed_region_s_total": float(rep_dev.sum()), "device_ms_per_step": float(np.median(devms_dev)) / K},
+                "workload_stats": {"points_per_scan_raw": n_raw, "points_per_scan_kept": n_full, "queries_per_scan": n_q, "targets_per_scan": n_m,
+                                   "distinct_input_bytes": distinct_bytes, "inputs_larger_than_l2": bool(distinct_bytes > L2_BYTES)},
                 "api": "aloam_scan_stream: K scans in one pipelined call (upload | ring binning | per-ring features | compaction + index | association + LM on five streams)",
-                "multi_stream": multi,
                 "sync_api": {"value": total_scans / sync_dev, "e2e": total_scans / sync_e2e, "ms_per_step": 1e3 * sync_dev / K,
-                             "device_ms_per_step": devms_sync / K, "note": "one synchronous aloam_scan_to_pose(_device) call per scan (latency mode)"},
-                "e2e": {"value": total_scans / secs_e2e, "unit": "scans/s", "h2d_bytes_per_step": 16 * n_raw,
-                        "d2h_bytes_per_step": 56 + 4 * 560 + 32, "ms_per_step": 1e3 * secs_e2e / K,
+                             "device_ms_per_step": devms_sync / K,
+                             "note": "the live drop-in call a ROS node makes once per scan: one synchronous aloam_scan_to_pose(_device) per scan (latency mode); "
+                                     "the headline value / e2e are the offline pipelined call over K scans"},
+                "e2e": {"value": total_scans / med_e2e, "unit": "scans/s", "h2d_bytes_per_step": 16 * n_raw,
+                        "d2h_bytes_per_step": 56 + 4 * 560 + 32, "ms_per_step": 1e3 * med_e2e / K,
+                        "ms_per_step_each_repeat": [1e3 * float(s) / K for s in rep_e2e],
                         "api": "aloam_scan_stream with host pinned raw scans (H2D of every raw scan and D2H of every pose inside the timed region)"},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "pose_check": {"t_w_device_vs_host_path_maxabs": float(np.abs(pose_dev[1] - pose_e2e[1]).max()),
-                               "t_w_stream_vs_sync_maxabs": float(np.abs(pose_dev[1] - pose_sync[1]).max())}}
+                "pose_rmse_vs_oracle_m": rm, "pose_rmse_vs_oracle_rad": rr,
+                "pose_check": {"vs_oracle_max_m": mm, "vs_oracle_max_rad": mr_, "scans": K, "tolerance": 1e-4,
+                               "e2e_path_rmse_vs_oracle_m": rm_e, "e2e_path_rmse_vs_oracle_rad": rr_e,
+                               "device_vs_host_path_identical": bool(np.array_equal(poses_dev, poses_e2e)),
+                               "t_w_stream_vs_sync_maxabs": float(np.abs(poses_dev[W + K, 4:] - pose_sync[4:]).max())},
+                "mapping": mapping, "batch": batch}
         emit(line)
     ctx.close()
     if world > 1:
