@@ -1,4 +1,4 @@
-// Internal: the context object behind the C ABI and the helpers shared by capi.cu and mapping.cu.
+// Internal: the context object behind the C ABI and the helpers shared by capi.cu, mapping.cu, cubemap.cu, comm.cu.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -16,10 +16,10 @@ namespace {
 constexpr int kMaxSharpPerRing = 12, kMaxLessSharpPerRing = 120, kMaxFlatPerRing = 24;
 constexpr int kFusedSharpSlots = 64 * kMaxSharpPerRing;  // 768
 constexpr int kFusedFlatSlots = 64 * kMaxFlatPerRing;    // 1536
-constexpr int kMaxQueries = ALOAM_MAX_QUERIES;
-constexpr int kProfSlots = 192;                       // kernel launches timed per profile window (one API call)
+constexpr int kMaxQueries = ALOAM_MAX_QUERIES;         // API-path capacity for sharp / flat query clouds
+constexpr int kProfSlots = 192;                        // kernel launches timed per profile window (one API call)
 constexpr int kFeatSlots = 4;                          // feature-set ring of the fused / stream paths
-constexpr int kMaxStreamScans = 4096;                   // scans per aloam_scan_stream call                       // API-path capacity for sharp / flat query clouds
+constexpr int kMaxStreamScans = 4096;                  // scans x lanes per aloam_scan_stream(_batch) call
 
 struct FeatBuf {
   Pt4 *sharp = nullptr, *less_sharp = nullptr, *flat = nullptr, *less_flat = nullptr;
@@ -28,34 +28,37 @@ struct FeatBuf {
   RabIndex g_ls = {}, g_lf = {};           // (azimuth bucket x ring) indices over less_sharp / less_flat
 };
 
+// Everything one trajectory owns on the device.  A context has cfg.max_batch of them; the single-trajectory entry points
+// use lane 0, aloam_scan_stream_batch drives lanes 0 .. batch-1 in lockstep with shared launches.
+struct Lane {
+  float* d_raw[2] = {nullptr, nullptr};          // raw-scan staging, double-buffered by scan parity
+  int8_t* d_ring = nullptr;
+  int *d_hist = nullptr, *d_offsets = nullptr, *d_scan_start = nullptr, *d_scan_end = nullptr;
+  int* d_ring_start[2] = {nullptr, nullptr};
+  ScanScalars* d_sc = nullptr;                   // [3]: scan k uses slot k%3 and re-arms the next
+  Pt4* d_full[2] = {nullptr, nullptr};           // ring-major cloud, double-buffered for the pipelined stream call
+  // per-ring staging sets: in the stream call k_compact(k) runs on the index stream while k_ring_features(k+1) fills the other set
+  Pt4 *st_sharp[2] = {}, *st_less_sharp[2] = {}, *st_flat[2] = {}, *st_less_flat[2] = {};
+  int* st_counts[2] = {};
+  FeatBuf feat[kFeatSlots];                      // ring of feature sets: odometry k reads sets k-1 and k while extraction runs ahead
+  BlockRec* d_blocks = nullptr;
+  int* d_corr = nullptr;
+  double *d_pose = nullptr, *d_world = nullptr;  // para_q/para_t (laserOdometry.cpp:97-98) and q_w_curr/t_w_curr (:93-94)
+  LmSummary* d_summary = nullptr;                // [4]
+};
+
 }  // namespace
 
 struct aloam_ctx {
   aloam_config cfg;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int max_points = 0, nblocks_max = 0;
-  // raw scan + ring binning
-  float* d_raw = nullptr;
-  int8_t* d_ring = nullptr;
-  int *d_hist = nullptr, *d_offsets = nullptr, *d_ring_start = nullptr, *d_scan_start = nullptr, *d_scan_end = nullptr;
-  ScanScalars* d_sc = nullptr;  // [3]: scan k uses slot k%3 and re-arms the next; B(k) may still read slot k while A(k+1) re-arms k+2
-  Pt4 *d_full = nullptr, *d_full2 = nullptr;   // ring-major cloud, double-buffered for the pipelined stream call
-  int* d_ring_start2 = nullptr;
-  float* d_curv = nullptr;
+  int max_points = 0, nblocks_max = 0, max_ring = ALOAM_MAX_RING, n_lanes = 1;
+  std::vector<Lane> lanes;
+  float* d_curv = nullptr;         // debug outputs of the last extraction (lane 0 only)
   int8_t* d_label = nullptr;
-  Pt4 *st_sharp = nullptr, *st_less_sharp = nullptr, *st_flat = nullptr, *st_less_flat = nullptr;
-  int* st_counts = nullptr;
-  // second set of per-ring staging buffers: in the stream call k_compact(k) runs on the index stream while
-  // k_ring_features(k+1) is already filling the other set
-  Pt4 *st_sharp2 = nullptr, *st_less_sharp2 = nullptr, *st_flat2 = nullptr, *st_less_flat2 = nullptr;
-  int* st_counts2 = nullptr;
-  FeatBuf feat[kFeatSlots];   // ring of feature sets: odometry k reads sets k-1 and k while extraction runs up to kFeatSlots-2 scans ahead
-  // odometry
-  BlockRec* d_blocks = nullptr;
-  int* d_corr = nullptr;
-  double *d_pose = nullptr, *d_world = nullptr, *d_out28 = nullptr, *d_packed = nullptr;
-  LmSummary* d_summary = nullptr;  // [4]
+  int* d_scan_nfull = nullptr;     // [kMaxStreamScans] ring-major cloud size of every (scan, lane) of a stream call
+  double *d_out28 = nullptr, *d_packed = nullptr;
   int* d_err = nullptr;
   Pt4* d_query = nullptr;
   int* d_knn_idx = nullptr;
@@ -63,7 +66,8 @@ struct aloam_ctx {
   // multi-GPU sharding of the map (spatial slabs + halo): this process's rank / world and its communicator
   int shard_rank = 0, shard_count = 1;
   void* comm = nullptr;          // ncclComm_t when shard_count > 1 (comm.cu)
-  double* d_lm_tot = nullptr;    // [32] all-reduced normal equations of one evaluation (sharded LM)
+  void* peer = nullptr;          // peer-memory exchange of the sharded LM (comm.cu), when enabled
+  double* d_lm_tot = nullptr;    // [64] all-reduced normal equations of one evaluation (sharded LM)
   void* d_lm_state = nullptr;    // device-resident trust-region state (sharded LM)
   void* mapper = nullptr;        // map cube store (cubemap.cu), created on first use
   // scan-to-map: uploaded submap (corner, surf) with hash grids, stack queries, fit debug records
@@ -77,26 +81,28 @@ struct aloam_ctx {
   int* d_stack_counts = nullptr;  // [4] {n_corner, n_surf, total} of the stacks being registered
   float4* d_nbr = nullptr;        // [queries][5] neighbours found by k_map_knn5 (x, y, z, index bits)
   double* d_map_pose = nullptr;   // [7] scan-to-map pose being refined (parameters[7], laserMapping.cpp:110)
-  double* d_fits = nullptr;      // [queries][14] debug / test records of the line / plane fits
+  double* d_fits = nullptr;       // [queries][14] debug / test records of the line / plane fits
   BlockRec* d_map_blocks = nullptr;
+  LmSummary* d_map_summary = nullptr;   // [4] summaries of the scan-to-map solves
   // general voxel filter (voxel.cu): radix-sort ping-pong buffers, histograms, small scalars
   unsigned* d_vox_keys[2] = {nullptr, nullptr};
   int* d_vox_vals[2] = {nullptr, nullptr};
   int *d_vox_hist = nullptr, *d_vox_offs = nullptr, *d_vox_misc = nullptr;
-  // pipelined scan stream (aloam_scan_stream): extraction + index build on s_ext, association + LM on `stream`,
-  // host->device copies of the raw scans on s_h2d, all chained by events
-  cudaStream_t s_ext = nullptr, s_exa = nullptr, s_idx = nullptr, s_h2d = nullptr;
-  cudaEvent_t ev_feat[kFeatSlots] = {}, ev_idx[kFeatSlots] = {}, ev_odo[kFeatSlots] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {}, ev_a[2] = {}, ev_b[2] = {}, ev_cmp[2] = {};
-  float* d_raw2 = nullptr;       // second raw-scan staging buffer
+  // pipelined scan stream: ring binning on s_exa, per-ring features on s_ext, compaction + index on s_idx, association + LM
+  // on `stream`, host->device copies of the raw scans on s_h2d, scan-to-map on s_map; all chained by events
+  cudaStream_t s_ext = nullptr, s_exa = nullptr, s_idx = nullptr, s_h2d = nullptr, s_map = nullptr;
+  cudaEvent_t ev_feat[kFeatSlots] = {}, ev_idx[kFeatSlots] = {}, ev_odo[kFeatSlots] = {}, ev_mapdone[kFeatSlots] = {}, ev_h2d[2] = {}, ev_rawfree[2] = {},
+              ev_a[2] = {}, ev_b[2] = {}, ev_cmp[2] = {};
   double* h_poses = nullptr;     // pinned [kMaxStreamScans][7]
-  double* d_poses = nullptr;     // device [kMaxStreamScans][7]: per-scan world poses of a stream call (one D2H at the end)
+  double* d_poses = nullptr;     // device [kMaxStreamScans][7]: per-(scan, lane) world poses of a stream call (one D2H at the end)
+  int* h_scan_nfull = nullptr;   // pinned [kMaxStreamScans]
   // pinned host mirrors
   Pt4* h_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   Pt4* h_vox_out = nullptr;     // result of aloam_voxel_filter (never aliases the feature views)
   int* h_ints = nullptr;        // scratch ints (counts etc.)
   double* h_dbl = nullptr;      // scratch doubles
-  LmSummary* h_summary = nullptr;
-  ScanScalars* h_sc = nullptr;
+  LmSummary* h_summary = nullptr;   // [n_lanes][4]
+  ScanScalars* h_sc = nullptr;      // [n_lanes][3]
   // per-kernel profiler (bench.py roofline leg) + cumulative launch counter
   bool prof_on = false;
   cudaEvent_t prof_ev[2 * kProfSlots] = {};
@@ -105,7 +111,7 @@ struct aloam_ctx {
   double prof_ms[ALOAM_N_KERNEL_IDS] = {};
   long long prof_cnt[ALOAM_N_KERNEL_IDS] = {};
   long long launches = 0;
-  // state
+  // state (all lanes advance in lockstep)
   int parity = 0;         // ScanScalars slot of the next scan
   int frame = 0;          // fused pipeline: scans seen
   int cur = 0;            // fused pipeline: feat[] slot of the most recent scan
@@ -157,19 +163,26 @@ void launch_ex(aloam_ctx* c, int kid, K kernel, dim3 grid, dim3 block, size_t sm
 
 #define LAUNCH_PDL(c, kid, kernel, grid, block, smem, ...) launch_ex(c, kid, kernel, dim3(grid), dim3(block), smem, 1, true, __VA_ARGS__)
 
-// the LM kernel runs as one thread-block cluster (distributed-shared-memory reduction, see lm.cu)
+// the LM kernel runs as one thread-block cluster per trajectory (distributed-shared-memory reduction, see lm.cu)
 constexpr int kLmCluster = 8;
-template <typename... Args>
-void launch_lm(aloam_ctx* c, bool pdl, Args... args) {
-  launch_ex(c, KID_LM_SOLVE, k_lm_solve, dim3(kLmCluster), dim3(ALOAM_LM_THREADS), lm_dynamic_smem_bytes(), kLmCluster, pdl, args...);
+inline void launch_lm_batch(aloam_ctx* c, bool pdl, const Batch<LmArgs>& args, int lanes, const LmParams& lp, int mode, int integrate) {
+  launch_ex(c, KID_LM_SOLVE, k_lm_solve, dim3(kLmCluster, lanes), dim3(ALOAM_LM_THREADS), lm_dynamic_smem_bytes(), kLmCluster, pdl, args, lp, mode, integrate);
+}
+// single solve: blocks, n (device pointer or host value), pose in / out
+inline void launch_lm(aloam_ctx* c, bool pdl, const BlockRec* blocks, const int* n_ptr, int n_host, double* x7, const LmParams& lp, LmSummary* summary,
+                      int mode, double* out28, double* world7, int integrate) {
+  Batch<LmArgs> b = {};
+  b.a[0] = LmArgs{blocks, n_ptr, n_host, x7, summary, out28, world7};
+  launch_lm_batch(c, pdl, b, 1, lp, mode, integrate);
 }
 
-// sharded LM (comm.cu): per evaluation one kernel for the local blocks, one ncclAllReduce of 28 doubles, one step kernel
 }  // namespace
+// sharded LM (comm.cu): per evaluation one kernel for the local blocks, one exchange of 32 doubles, one step kernel
 void launch_lm_sharded(aloam_ctx* c, const aloam::BlockRec* blocks, const int* d_n, double* pose, const aloam::LmParams& lp, aloam::LmSummary* summary);
 void map_index_build(aloam_ctx* c, const Pt4* d_corner, const Pt4* d_surf, int n_upper);
 void map_register_device(aloam_ctx* c, const Pt4* d_corner_stack, const Pt4* d_surf_stack, const int* d_counts3, int nq_upper, double* d_pose, bool want_fits);
 namespace {
+
 LmParams lm_params(const aloam_config& c) {
   LmParams p;
   p.max_iters = c.inner_iters; p.huber_a = c.huber;
@@ -198,91 +211,13 @@ int upload_cloud(aloam_ctx* c, aloam_cloud_view v, Pt4* dst, int capacity) {
 LastCloud last_corner(const FeatBuf& f) { return LastCloud{f.less_sharp, f.counts + 1, f.g_ls}; }
 LastCloud last_surf(const FeatBuf& f) { return LastCloud{f.less_flat, f.counts + 3, f.g_lf}; }
 
-// feature extraction kernels on a raw scan already in device memory
-// Feature extraction is issued in two halves so that the pipelined stream call can run them on different streams:
-//   A  ring binning   (k_classify, k_ring_scan, k_scatter)  raw scan -> ring-major cloud `full[buf]`, ring_start[buf]
-//   B  per-ring work  (k_ring_features, k_compact)          full[buf] -> the four feature clouds of `out`
-// `sc_slot` (returned by A, consumed by B) is the ScanScalars parity slot of this scan.
-int run_features_a(aloam_ctx* c, const float* d_raw, int n, int stride, int buf, int* sc_slot) {
-  const int nb = (n + 1023) / 1024;
-  const float thres = c->cfg.minimum_range;
-  ScanScalars* sc = c->d_sc + c->parity;
-  ScanScalars* sc_next = c->d_sc + (c->parity + 1) % 3;
-  Pt4* full = buf ? c->d_full2 : c->d_full;
-  int* rstart = buf ? c->d_ring_start2 : c->d_ring_start;
-  LAUNCH(c, KID_CLASSIFY, k_classify, nb, 256, 0, d_raw, n, stride, c->cfg.n_scans, thres * thres, c->d_ring, c->d_hist, sc);
-  LAUNCH_PDL(c, KID_RING_SCAN, k_ring_scan, 1, 1024, 0, d_raw, stride, nb, c->cfg.n_scans, c->d_hist, c->d_offsets, rstart,
-         c->d_scan_start, c->d_scan_end, sc, sc_next);
-  LAUNCH_PDL(c, KID_SCATTER, k_scatter, nb, 256, 0, d_raw, n, stride, c->d_ring, c->d_offsets, sc, full);
-  *sc_slot = c->parity;
-  c->parity = (c->parity + 1) % 3;
-  CUDA_CHECK_RET(cudaGetLastError());
-  return ALOAM_OK;
-}
-// B1: per-ring kernel -> staging set `buf` ; B2: ring-ordered concatenation of the staging set into `out`
-int run_features_b1(aloam_ctx* c, int buf, int sc_slot) {
-  Pt4* full = buf ? c->d_full2 : c->d_full;
-  int* rstart = buf ? c->d_ring_start2 : c->d_ring_start;
-  LAUNCH(c, KID_RING_FEATURES, k_ring_features, c->cfg.n_scans, 256, ring_features_smem_bytes(), full, rstart,
-         c->cfg.n_scans, 0.2f, buf ? c->st_sharp2 : c->st_sharp, buf ? c->st_less_sharp2 : c->st_less_sharp,
-         buf ? c->st_flat2 : c->st_flat, buf ? c->st_less_flat2 : c->st_less_flat, buf ? c->st_counts2 : c->st_counts,
-         c->d_curv, c->d_label, c->d_sc + sc_slot);
-  CUDA_CHECK_RET(cudaGetLastError());
-  return ALOAM_OK;
-}
-int run_features_b2(aloam_ctx* c, int buf, FeatBuf& out, bool pdl) {
-  launch_ex(c, KID_COMPACT, k_compact, dim3(c->cfg.n_scans), dim3(128), 0, 1, pdl, c->cfg.n_scans,
-            (const Pt4*)(buf ? c->st_sharp2 : c->st_sharp), (const Pt4*)(buf ? c->st_less_sharp2 : c->st_less_sharp),
-            (const Pt4*)(buf ? c->st_flat2 : c->st_flat), (const Pt4*)(buf ? c->st_less_flat2 : c->st_less_flat),
-            (const int*)(buf ? c->st_counts2 : c->st_counts), out.sharp, out.less_sharp, out.flat, out.less_flat, out.counts, out.rs_ls, out.rs_lf);
-  CUDA_CHECK_RET(cudaGetLastError());
-  return ALOAM_OK;
-}
-int run_features_b(aloam_ctx* c, int buf, int sc_slot, FeatBuf& out) {
-  int rc = run_features_b1(c, buf, sc_slot);
-  if (rc) return rc;
-  return run_features_b2(c, buf, out, true);
-}
-int run_features(aloam_ctx* c, const float* d_raw, int n, int stride, FeatBuf& out) {
-  int slot = 0;
-  int rc = run_features_a(c, d_raw, n, stride, 0, &slot);
-  if (rc) return rc;
-  return run_features_b(c, 0, slot, out);
-}
-
-// index over the two "last" clouds: count -> scan -> fill (n_ls / n_lf = host upper bounds on the cloud sizes)
-void run_grid_build(aloam_ctx* c, FeatBuf& f, int n_ls, int n_lf) {
-  const int pb = (std::max(std::max(n_ls, n_lf), 1) + 255) / 256;
-  LAUNCH(c, KID_GRID_BUILD, k_rab_count, dim3(pb, 2), 256, 0, f.g_ls, f.less_sharp, f.counts + 1, f.g_lf, f.less_flat, f.counts + 3);
-  LAUNCH_PDL(c, KID_GRID_BUILD, k_rab_scan, 2, 1024, 0, f.g_ls, f.g_lf);
-  LAUNCH_PDL(c, KID_GRID_BUILD, k_rab_fill, dim3(pb, 2), 256, 0, f.g_ls, f.less_sharp, f.counts + 1, f.g_lf, f.less_flat, f.counts + 3);
-}
-
-// outer_iters x (association + LM) ; `cur` supplies sharp/flat, `last` the targets ; pose in c->d_pose
-// `pose_slot` (device, 7 doubles, may be null): the integrated world pose is also written there by the last solve
-void run_register(aloam_ctx* c, const FeatBuf& cur, const FeatBuf& last, int sharp_slots, int flat_slots, bool integrate,
-                  int* d_corr, double* pose_slot = nullptr) {
-  OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan};
-  const LmParams lp = lm_params(c->cfg);
-  const int slots = sharp_slots + flat_slots;
-  for (int it = 0; it < c->cfg.outer_iters; ++it) {
-    // within one call the chain association -> LM -> association -> LM is launched with programmatic dependencies
-    if (slots > 0)
-      launch_ex(c, KID_ODOM_ASSOC, k_odom_assoc, dim3((slots + 7) / 8), dim3(256), 0, 1, it > 0, (const Pt4*)cur.sharp, (const Pt4*)cur.flat,
-                (const int*)cur.counts, last_corner(last), last_surf(last), (const double*)c->d_pose, op, c->d_blocks, d_corr, sharp_slots);
-    const bool last_it = it == c->cfg.outer_iters - 1;
-    launch_lm(c, slots > 0, (const BlockRec*)c->d_blocks, (const int*)nullptr, slots, c->d_pose, lp, c->d_summary + (it & 3), 0,
-              (integrate && last_it) ? pose_slot : (double*)nullptr, c->d_world, (integrate && last_it) ? 1 : 0);
-  }
-}
-
-void fill_stats(aloam_ctx* c, aloam_stats* st, int outer, int flags, float ms) {
+void fill_stats_from(const LmSummary* h_summary, aloam_stats* st, int outer, int flags, float ms) {
   if (!st) return;
   std::memset(st, 0, sizeof(*st));
   st->flags = flags;
   st->ms_total = ms;
   for (int it = 0; it < outer && it < 4; ++it) {
-    const LmSummary& s = c->h_summary[it];
+    const LmSummary& s = h_summary[it];
     st->lm_iters += s.num_iterations;
     st->accepted_steps += s.num_successful;
     st->termination[it] = s.termination;
@@ -293,6 +228,7 @@ void fill_stats(aloam_ctx* c, aloam_stats* st, int outer, int flags, float ms) {
     }
   }
 }
+inline void fill_stats(aloam_ctx* c, aloam_stats* st, int outer, int flags, float ms) { fill_stats_from(c->h_summary, st, outer, flags, ms); }
 
 int check_view(const aloam_cloud_view& v) {
   if (v.n < 0) return ALOAM_ERR_INVALID_ARG;
@@ -301,4 +237,3 @@ int check_view(const aloam_cloud_view& v) {
 }
 
 }  // namespace
-

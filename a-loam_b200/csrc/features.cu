@@ -72,10 +72,16 @@ __device__ __forceinline__ float ori_first_half(float x, float y, float start_or
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CT) k_classify(const float* __restrict__ raw, int n, int stride, int n_scans,
-                                                 float thres2, int8_t* __restrict__ ring_out,
-                                                 int* __restrict__ hist, ScanScalars* __restrict__ sc) {
+__global__ void __launch_bounds__(CT) k_classify(const __grid_constant__ Batch<ClassifyArgs> B, int n_scans, float thres2) {
   pdl_launch_dependents();   // the next kernel of the stream may become resident (it blocks in pdl_wait())
+  // blockIdx.y = trajectory (lane) of the batch; a lane with fewer returns than the largest one has idle trailing CTAs
+  const ClassifyArgs& A = B.a[blockIdx.y];
+  const float* __restrict__ raw = A.raw;
+  const int n = A.n, stride = A.stride;
+  int8_t* __restrict__ ring_out = A.ring_out;
+  int* __restrict__ hist = A.hist;
+  ScanScalars* __restrict__ sc = A.sc;
+  if (blockIdx.x * CHUNK >= n && blockIdx.x > 0) return;
   __shared__ int s_hist[64];
   __shared__ int s_first, s_last, s_half;
   const int tid = threadIdx.x;
@@ -131,13 +137,19 @@ __global__ void __launch_bounds__(CT) k_classify(const float* __restrict__ raw, 
 
 // ---------------------------------------------------------------------------------------------------------------
 // one CTA of 1024 threads: thread (r = t>>4, s = t&15) owns slice s of ring r's per-block histogram column
-__global__ void __launch_bounds__(1024) k_ring_scan(const float* __restrict__ raw, int stride, int nblocks,
-                                                    int n_scans, const int* __restrict__ hist,
-                                                    int* __restrict__ offsets, int* __restrict__ ring_start,
-                                                    int* __restrict__ scan_start, int* __restrict__ scan_end,
-                                                    ScanScalars* __restrict__ sc, ScanScalars* __restrict__ sc_next) {
+__global__ void __launch_bounds__(1024) k_ring_scan(const __grid_constant__ Batch<RingScanArgs> B, int n_scans) {
   pdl_launch_dependents();
   pdl_wait();   // launched with a programmatic dependency on the previous kernel of the stream
+  const RingScanArgs& A = B.a[blockIdx.x];   // one CTA per trajectory of the batch
+  const float* __restrict__ raw = A.raw;
+  const int stride = A.stride, nblocks = A.nblocks;
+  const int* __restrict__ hist = A.hist;
+  int* __restrict__ offsets = A.offsets;
+  int* __restrict__ ring_start = A.ring_start;
+  int* __restrict__ scan_start = A.scan_start;
+  int* __restrict__ scan_end = A.scan_end;
+  ScanScalars* __restrict__ sc = A.sc;
+  ScanScalars* __restrict__ sc_next = A.sc_next;
   __shared__ int s_tot[64];
   __shared__ int s_start[65];
   const int t = threadIdx.x, r = t >> 4, s = t & 15;
@@ -189,17 +201,24 @@ __global__ void __launch_bounds__(1024) k_ring_scan(const float* __restrict__ ra
       else if ((double)(end_ori - start_ori) < kPi) end_ori = (float)((double)end_ori + 2 * kPi);
     }
     sc->end_ori = end_ori;
+    if (A.n_full_out) *A.n_full_out = s_start[64];   // per-scan record of a stream call (0 = nothing survived the filters)
     // arm the other parity slot for the next scan
     sc_next->first_valid = INT_MAX; sc_next->last_valid = -1; sc_next->half_idx = INT_MAX; sc_next->n_full = 0;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CT) k_scatter(const float* __restrict__ raw, int n, int stride,
-                                                const int8_t* __restrict__ ring_in, const int* __restrict__ offsets,
-                                                const ScanScalars* __restrict__ sc, Pt4* __restrict__ full) {
+__global__ void __launch_bounds__(CT) k_scatter(const __grid_constant__ Batch<ScatterArgs> B) {
   pdl_launch_dependents();
   pdl_wait();   // launched with a programmatic dependency on the previous kernel of the stream
+  const ScatterArgs& A = B.a[blockIdx.y];
+  const float* __restrict__ raw = A.raw;
+  const int n = A.n, stride = A.stride;
+  const int8_t* __restrict__ ring_in = A.ring_in;
+  const int* __restrict__ offsets = A.offsets;
+  const ScanScalars* __restrict__ sc = A.sc;
+  Pt4* __restrict__ full = A.full;
+  if (blockIdx.x * CHUNK >= n) return;
   __shared__ int s_cnt[ITERS * (CT / 32)][64];  // [slot = it*8 + warp][ring], then exclusive prefix over slots
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   for (int k = tid; k < ITERS * (CT / 32) * 64; k += CT) (&s_cnt[0][0])[k] = 0;
@@ -428,25 +447,35 @@ __device__ __forceinline__ void pick_segment(const float* curv, const unsigned c
   __syncwarp();
 }
 
-__device__ long long g_dbg_cycles[64 * 8];   // per-ring phase time stamps (clock64) of the last k_ring_features launch
+__device__ long long g_dbg_cycles[65 * 8];   // per-ring phase time stamps (clock64) of the last k_ring_features launch
 
-// dynamic shared memory layout (bytes): pts 16*MAXR | keys 8*MAXR | curv 4*MAXR | label MAXR | gap 4*(MAXR/32+2) | picked same
-constexpr int MAXR = ALOAM_MAX_RING;
-size_t ring_features_smem_bytes() { return (size_t)MAXR * (16 + 8 + 4 + 1 + 1) + 2 * 4 * (MAXR / 32 + 2) + 64; }
+// dynamic shared memory layout (bytes), maxr = ring capacity of the context (multiple of 32, <= ALOAM_MAX_RING), P = sort width
+// (next power of two >= maxr, >= 512):  pts 16*maxr | keys 8*P | curv 4*maxr | label maxr | gap 4*(maxr/32+2) | picked same | fb maxr
+// The smaller the ring capacity the more CTAs are resident per SM (2048: 65 KB -> 3 per SM; 4096: 131 KB -> 1 per SM),
+// which is what a batch of trajectories needs.
+__host__ __device__ inline int sort_width(int maxr) { int p = 512; while (p < maxr) p <<= 1; return p; }
+size_t ring_features_smem_bytes(int maxr) { return (size_t)maxr * (16 + 4 + 1 + 1) + (size_t)sort_width(maxr) * 8 + 2 * 4 * (maxr / 32 + 2) + 64; }
 
-__global__ void __launch_bounds__(256) k_ring_features(const Pt4* __restrict__ full, const int* __restrict__ ring_start,
-                                                       int n_scans, float leaf, Pt4* __restrict__ st_sharp,
-                                                       Pt4* __restrict__ st_less_sharp, Pt4* __restrict__ st_flat,
-                                                       Pt4* __restrict__ st_less_flat, int* __restrict__ st_counts,
-                                                       float* __restrict__ dbg_curv, int8_t* __restrict__ dbg_label,
-                                                       ScanScalars* __restrict__ sc) {
+__global__ void __launch_bounds__(256) k_ring_features(const __grid_constant__ Batch<RingFeatArgs> B, int n_scans, float leaf, int MAXR) {
   pdl_launch_dependents();   // the next kernel of the stream may become resident (it blocks in pdl_wait())
+  const RingFeatArgs& A = B.a[blockIdx.y];   // blockIdx.x = ring, blockIdx.y = trajectory of the batch
+  const Pt4* __restrict__ full = A.full;
+  const int* __restrict__ ring_start = A.ring_start;
+  Pt4* __restrict__ st_sharp = A.st_sharp;
+  Pt4* __restrict__ st_less_sharp = A.st_less_sharp;
+  Pt4* __restrict__ st_flat = A.st_flat;
+  Pt4* __restrict__ st_less_flat = A.st_less_flat;
+  int* __restrict__ st_counts = A.st_counts;
+  float* __restrict__ dbg_curv = A.dbg_curv;
+  int8_t* __restrict__ dbg_label = A.dbg_label;
+  ScanScalars* __restrict__ sc = A.sc;
   extern __shared__ __align__(16) unsigned char smem[];
+  const int PW = sort_width(MAXR);
   Pt4* pts = reinterpret_cast<Pt4*>(smem);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + (size_t)MAXR * 16);
-  float* curv = reinterpret_cast<float*>(smem + (size_t)MAXR * 24);
-  signed char* label = reinterpret_cast<signed char*>(smem + (size_t)MAXR * 28);
-  unsigned* gap = reinterpret_cast<unsigned*>(smem + (size_t)MAXR * 29);
+  float* curv = reinterpret_cast<float*>(smem + (size_t)MAXR * 16 + (size_t)PW * 8);
+  signed char* label = reinterpret_cast<signed char*>(curv + MAXR);
+  unsigned* gap = reinterpret_cast<unsigned*>(label + MAXR);
   unsigned* picked = gap + (MAXR / 32 + 2);
   unsigned char* fb = reinterpret_cast<unsigned char*>(picked + (MAXR / 32 + 2));   // [MAXR]
   __shared__ unsigned short s_less[6][20], s_flat[6][4];
@@ -472,7 +501,7 @@ __global__ void __launch_bounds__(256) k_ring_features(const Pt4* __restrict__ f
   int P = 32;
   while (P < nr) P <<= 1;
 
-  long long* dbg = g_dbg_cycles + ring * 8;
+  long long* dbg = g_dbg_cycles + (blockIdx.y == 0 ? ring : 64) * 8;   // lane 0 only; the other lanes write a dummy row
   if (tid == 0) dbg[0] = clock64();
   for (int i = tid; i < nr; i += blockDim.x) pts[i] = full[g0 + i];
   for (int i = tid; i < MAXR / 32 + 2; i += blockDim.x) { gap[i] = 0; picked[i] = 0; }
@@ -678,15 +707,22 @@ void features_debug_cycles(long long* host64x8) { cudaMemcpyFromSymbol(host64x8,
 
 // ---------------------------------------------------------------------------------------------------------------
 // ring-ordered concatenation of the staged per-ring outputs ; also ring_start tables of the two "less" clouds
-__global__ void __launch_bounds__(128) k_compact(int n_scans, const Pt4* __restrict__ st_sharp,
-                                                 const Pt4* __restrict__ st_less_sharp, const Pt4* __restrict__ st_flat,
-                                                 const Pt4* __restrict__ st_less_flat, const int* __restrict__ st_counts,
-                                                 Pt4* __restrict__ sharp, Pt4* __restrict__ less_sharp,
-                                                 Pt4* __restrict__ flat, Pt4* __restrict__ less_flat,
-                                                 int* __restrict__ counts, int* __restrict__ rs_less_sharp,
-                                                 int* __restrict__ rs_less_flat) {
+__global__ void __launch_bounds__(128) k_compact(const __grid_constant__ Batch<CompactArgs> B, int n_scans, int MAXR) {
   pdl_launch_dependents();
   pdl_wait();   // launched with a programmatic dependency on the previous kernel of the stream
+  const CompactArgs& A = B.a[blockIdx.y];
+  const Pt4* __restrict__ st_sharp = A.st_sharp;
+  const Pt4* __restrict__ st_less_sharp = A.st_less_sharp;
+  const Pt4* __restrict__ st_flat = A.st_flat;
+  const Pt4* __restrict__ st_less_flat = A.st_less_flat;
+  const int* __restrict__ st_counts = A.st_counts;
+  Pt4* __restrict__ sharp = A.sharp;
+  Pt4* __restrict__ less_sharp = A.less_sharp;
+  Pt4* __restrict__ flat = A.flat;
+  Pt4* __restrict__ less_flat = A.less_flat;
+  int* __restrict__ counts = A.counts;
+  int* __restrict__ rs_less_sharp = A.rs_ls;
+  int* __restrict__ rs_less_flat = A.rs_lf;
   __shared__ int s_off[4];
   const int ring = blockIdx.x, tid = threadIdx.x;
   if (tid < 4) {

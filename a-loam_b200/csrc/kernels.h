@@ -12,21 +12,30 @@
 
 namespace aloam {
 
+// ---- batching: one launch covers up to ALOAM_MAX_BATCH independent trajectories ("lanes").  Every per-trajectory
+// kernel takes its arguments as a by-value array indexed by blockIdx.y (or .z / .x where noted); a single trajectory is
+// the batch of one.  __grid_constant__ keeps the array in the constant bank (no local copy for the dynamic index).
+#ifndef ALOAM_MAX_BATCH
+#define ALOAM_MAX_BATCH 16   // == the public header
+#endif
+template <typename T> struct Batch { T a[ALOAM_MAX_BATCH]; };
+
 // ---- features.cu
-size_t ring_features_smem_bytes();
+size_t ring_features_smem_bytes(int max_ring);
 void features_debug_cycles(long long* host64x8);
-__global__ void k_classify(const float* raw, int n, int stride, int n_scans, float thres2, int8_t* ring_out, int* hist,
-                           ScanScalars* sc);
-__global__ void k_ring_scan(const float* raw, int stride, int nblocks, int n_scans, const int* hist, int* offsets,
-                            int* ring_start, int* scan_start, int* scan_end, ScanScalars* sc, ScanScalars* sc_next);
-__global__ void k_scatter(const float* raw, int n, int stride, const int8_t* ring_in, const int* offsets,
-                          const ScanScalars* sc, Pt4* full);
-__global__ void k_ring_features(const Pt4* full, const int* ring_start, int n_scans, float leaf, Pt4* st_sharp,
-                                Pt4* st_less_sharp, Pt4* st_flat, Pt4* st_less_flat, int* st_counts, float* dbg_curv,
-                                int8_t* dbg_label, ScanScalars* sc);
-__global__ void k_compact(int n_scans, const Pt4* st_sharp, const Pt4* st_less_sharp, const Pt4* st_flat,
-                          const Pt4* st_less_flat, const int* st_counts, Pt4* sharp, Pt4* less_sharp, Pt4* flat,
-                          Pt4* less_flat, int* counts, int* rs_less_sharp, int* rs_less_flat);
+struct ClassifyArgs { const float* raw; int n, stride; int8_t* ring_out; int* hist; ScanScalars* sc; };
+struct RingScanArgs { const float* raw; int stride, nblocks; const int* hist; int* offsets; int* ring_start; int* scan_start; int* scan_end;
+                      ScanScalars* sc; ScanScalars* sc_next; int* n_full_out; };
+struct ScatterArgs { const float* raw; int n, stride; const int8_t* ring_in; const int* offsets; const ScanScalars* sc; Pt4* full; };
+struct RingFeatArgs { const Pt4* full; const int* ring_start; Pt4 *st_sharp, *st_less_sharp, *st_flat, *st_less_flat; int* st_counts;
+                      float* dbg_curv; int8_t* dbg_label; ScanScalars* sc; };
+struct CompactArgs { const Pt4 *st_sharp, *st_less_sharp, *st_flat, *st_less_flat; const int* st_counts; Pt4 *sharp, *less_sharp, *flat, *less_flat;
+                     int* counts; int *rs_ls, *rs_lf; };
+__global__ void k_classify(const __grid_constant__ Batch<ClassifyArgs> B, int n_scans, float thres2);          // grid (blocks, lanes)
+__global__ void k_ring_scan(const __grid_constant__ Batch<RingScanArgs> B, int n_scans);                       // grid (lanes)
+__global__ void k_scatter(const __grid_constant__ Batch<ScatterArgs> B);                                       // grid (blocks, lanes)
+__global__ void k_ring_features(const __grid_constant__ Batch<RingFeatArgs> B, int n_scans, float leaf, int max_ring);   // grid (rings, lanes)
+__global__ void k_compact(const __grid_constant__ Batch<CompactArgs> B, int n_scans, int max_ring);           // grid (rings, lanes)
 
 // ---- odometry.cu
 // (azimuth bucket x ring) index over one cloud = what replaces a kd-tree build (laserOdometry.cpp:567-568)
@@ -44,9 +53,10 @@ struct LastCloud {
   RabIndex index;
 };
 __global__ void k_ring_offsets(const Pt4* pts, int n, int* ring_start, int* err);
-__global__ void k_rab_count(RabIndex a, const Pt4* pa, const int* na, RabIndex b, const Pt4* pb, const int* nb);
-__global__ void k_rab_scan(RabIndex a, RabIndex b);
-__global__ void k_rab_fill(RabIndex a, const Pt4* pa, const int* na, RabIndex b, const Pt4* pb, const int* nb);
+struct RabArgs { RabIndex a; const Pt4* pa; const int* na; RabIndex b; const Pt4* pb; const int* nb; };
+__global__ void k_rab_count(const __grid_constant__ Batch<RabArgs> B);   // grid (blocks, 2 clouds, lanes)
+__global__ void k_rab_scan(const __grid_constant__ Batch<RabArgs> B);    // grid (2 clouds, lanes)
+__global__ void k_rab_fill(const __grid_constant__ Batch<RabArgs> B);    // grid (blocks, 2 clouds, lanes)
 
 // one residual block, ready for the LM kernel (doubles; built once per association like the Ceres cost functions)
 struct __align__(8) BlockRec {
@@ -59,9 +69,9 @@ struct __align__(8) BlockRec {
 };
 #define ALOAM_MAX_QUERIES 16384   // capacity of the sharp / flat query buffers (ctx.h kMaxQueries)
 struct OdomParams { double dist_sq_thresh; double nearby_scan; };
-__global__ void k_odom_assoc(const Pt4* sharp, const Pt4* flat, const int* feat_counts /*[4]*/, LastCloud corner,
-                             LastCloud surf, const double* pose7, OdomParams prm, BlockRec* blocks,
-                             int* corr /*[(n_sharp+n_flat)][4] a,b,c,valid*/, int max_sharp);
+struct AssocArgs { const Pt4* sharp; const Pt4* flat; const int* feat_counts /*[4]*/; LastCloud corner, surf; const double* pose7;
+                   BlockRec* blocks; int* corr /*[(n_sharp+n_flat)][4] a,b,c,valid ; may be null*/; };
+__global__ void k_odom_assoc(const __grid_constant__ Batch<AssocArgs> B, OdomParams prm, int max_sharp);   // grid (query groups, lanes)
 __global__ void k_knn_last(LastCloud cloud, const Pt4* queries, int nq, int* idx, float* sqd);
 
 // ---- mapping.cu
@@ -113,8 +123,8 @@ struct LmSummary {
 };
 // mode 0: full trust-region solve, x updated in place ; mode 1: one evaluation, out28 = [JtJ upper 21, g 6, cost]
 // integrate != 0 : after the solve compose the world pose (laserOdometry.cpp:504-505): world7 <- world7 (+) x
-__global__ void k_lm_solve(const BlockRec* blocks, const int* n_blocks_ptr, int n_blocks_host, double* x7,
-                           LmParams prm, LmSummary* summary, int mode, double* out28, double* world7, int integrate);
+struct LmArgs { const BlockRec* blocks; const int* n_blocks_ptr; int n_blocks_host; double* x7; LmSummary* summary; double* out28; double* world7; };
+__global__ void k_lm_solve(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate);   // grid (8, lanes), clusters of 8 along x
 // sharded solve: per-evaluation kernels around an ncclAllReduce (see lm.cu, comm.cu)
 size_t lm_state_bytes();
 size_t lm_dynamic_smem_bytes();   // dynamic shared memory of k_lm_solve / k_lm_eval_shard (opt-in > 48 KB)

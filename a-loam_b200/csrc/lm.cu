@@ -485,10 +485,16 @@ __global__ void k_pack_blocks(const double* __restrict__ packed, int n, BlockRec
   out[i] = r;
 }
 
-__global__ void __launch_bounds__(NT, 1) k_lm_solve(const BlockRec* __restrict__ blocks, const int* __restrict__ n_blocks_ptr,
-                                                    int n_blocks_host, double* __restrict__ x7, LmParams prm,
-                                                    LmSummary* __restrict__ summary, int mode, double* __restrict__ out28,
-                                                    double* __restrict__ world7, int integrate) {
+__global__ void __launch_bounds__(NT, 1) k_lm_solve(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate) {
+  // one cluster (8 CTAs along x) per trajectory of the batch: blockIdx.y selects it
+  const LmArgs& A = B.a[blockIdx.y];
+  const BlockRec* __restrict__ blocks = A.blocks;
+  const int* __restrict__ n_blocks_ptr = A.n_blocks_ptr;
+  const int n_blocks_host = A.n_blocks_host;
+  double* __restrict__ x7 = A.x7;
+  LmSummary* __restrict__ summary = A.summary;
+  double* __restrict__ out28 = A.out28;
+  double* __restrict__ world7 = A.world7;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) double s_red[];   // [NT][RS] transpose scratch
   __shared__ double s_part[NW][32];

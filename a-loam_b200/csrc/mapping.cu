@@ -535,7 +535,7 @@ int ensure_map_buffers(aloam_ctx* c) {
   if (cudaMalloc((void**)&c->d_stack_corner, mp * 16) != cudaSuccess || cudaMalloc((void**)&c->d_stack_surf, mp * 16) != cudaSuccess ||
       cudaMalloc((void**)&c->d_fits, 2 * mp * 14 * 8) != cudaSuccess || cudaMalloc((void**)&c->d_map_blocks, 2 * mp * sizeof(BlockRec)) != cudaSuccess ||
       cudaMalloc((void**)&c->d_nbr, 2 * mp * 5 * sizeof(float4)) != cudaSuccess || cudaMalloc((void**)&c->d_stack_counts, 4 * sizeof(int)) != cudaSuccess ||
-      cudaMalloc((void**)&c->d_map_pose, 8 * sizeof(double)) != cudaSuccess)
+      cudaMalloc((void**)&c->d_map_pose, 8 * sizeof(double)) != cudaSuccess || cudaMalloc((void**)&c->d_map_summary, 4 * sizeof(LmSummary)) != cudaSuccess)
     return ALOAM_ERR_CUDA;
   return ALOAM_OK;
 }
@@ -572,9 +572,9 @@ void map_register_device(aloam_ctx* c, const Pt4* d_corner_stack, const Pt4* d_s
     launch_ex(c, KID_MAP_FIT, k_map_fit, dim3(fb), dim3(128), 0, 1, true, d_corner_stack, d_surf_stack, d_counts3, (const float4*)c->d_nbr,
               c->d_map_blocks, want_fits ? c->d_fits : (double*)nullptr);
     if (c->shard_count <= 1)
-      launch_lm(c, true, (const BlockRec*)c->d_map_blocks, d_counts3 + 2, 0, d_pose, lp, c->d_summary + (it & 3), 0, (double*)nullptr, (double*)nullptr, 0);
+      launch_lm(c, true, (const BlockRec*)c->d_map_blocks, d_counts3 + 2, 0, d_pose, lp, c->d_map_summary + (it & 3), 0, (double*)nullptr, (double*)nullptr, 0);
     else
-      launch_lm_sharded(c, c->d_map_blocks, d_counts3 + 2, d_pose, lp, c->d_summary + (it & 3));
+      launch_lm_sharded(c, c->d_map_blocks, d_counts3 + 2, d_pose, lp, c->d_map_summary + (it & 3));
   }
 }
 
@@ -586,7 +586,7 @@ void aloam_map_free_impl(aloam_ctx* c) {
     void* ps[] = {c->d_map_pts[t], m->grid.slots, m->grid.dyn, m->grid.gpts};
     for (void* p : ps) if (p) cudaFree(p);
   }
-  void* qs[] = {c->d_stack_corner, c->d_stack_surf, c->d_fits, c->d_map_blocks, c->d_nbr, c->d_stack_counts, c->d_map_pose};
+  void* qs[] = {c->d_stack_corner, c->d_stack_surf, c->d_fits, c->d_map_blocks, c->d_nbr, c->d_stack_counts, c->d_map_pose, c->d_map_summary};
   for (void* p : qs) if (p) cudaFree(p);
 }
 
@@ -654,7 +654,7 @@ int aloam_mapping_register_impl(aloam_ctx* c, aloam_cloud_view corner_stack, alo
   CUDA_CHECK_RET(cudaMemcpyAsync(c->d_map_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
   map_register_device(c, c->d_stack_corner, c->d_stack_surf, c->d_stack_counts, corner_stack.n + surf_stack.n, c->d_map_pose, false);
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 8, c->d_map_pose, 56, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, c->d_map_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaEventRecord(c->ev1, c->stream));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
   CUDA_CHECK_RET(cudaGetLastError());

@@ -56,12 +56,12 @@ __device__ __forceinline__ int bucket_of(float x, float y) {
 }  // namespace
 
 // blockIdx.y selects the cloud (0 = a, 1 = b)
-__global__ void k_rab_count(RabIndex a, const Pt4* __restrict__ pa, const int* __restrict__ na, RabIndex b,
-                            const Pt4* __restrict__ pb, const int* __restrict__ nb) {
+__global__ void k_rab_count(const __grid_constant__ Batch<RabArgs> B) {
   pdl_launch_dependents();   // the next kernel of the stream may become resident (it blocks in pdl_wait())
-  const RabIndex& g = blockIdx.y == 0 ? a : b;
-  const Pt4* __restrict__ pts = blockIdx.y == 0 ? pa : pb;
-  const int n = blockIdx.y == 0 ? *na : *nb;
+  const RabArgs& A = B.a[blockIdx.z];
+  const RabIndex& g = blockIdx.y == 0 ? A.a : A.b;
+  const Pt4* __restrict__ pts = blockIdx.y == 0 ? A.pa : A.pb;
+  const int n = blockIdx.y == 0 ? *A.na : *A.nb;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Pt4 p = pts[i];
@@ -72,10 +72,10 @@ __global__ void k_rab_count(RabIndex a, const Pt4* __restrict__ pa, const int* _
 }
 
 // one CTA per cloud: exclusive scan of the ALOAM_NB*64 cell counts -> start[], and reset the counts for the next build
-__global__ void __launch_bounds__(1024) k_rab_scan(RabIndex a, RabIndex b) {
+__global__ void __launch_bounds__(1024) k_rab_scan(const __grid_constant__ Batch<RabArgs> B) {
   pdl_launch_dependents();
   pdl_wait();   // launched with a programmatic dependency on the previous kernel of the stream
-  const RabIndex& g = blockIdx.x == 0 ? a : b;
+  const RabIndex& g = blockIdx.x == 0 ? B.a[blockIdx.y].a : B.a[blockIdx.y].b;
   constexpr int NC = ALOAM_NB * 64, PER = NC / 1024;
   __shared__ int s_w[32];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -100,13 +100,13 @@ __global__ void __launch_bounds__(1024) k_rab_scan(RabIndex a, RabIndex b) {
   if (t == 1023) g.start[NC] = run;
 }
 
-__global__ void k_rab_fill(RabIndex a, const Pt4* __restrict__ pa, const int* __restrict__ na, RabIndex b,
-                           const Pt4* __restrict__ pb, const int* __restrict__ nb) {
+__global__ void k_rab_fill(const __grid_constant__ Batch<RabArgs> B) {
   pdl_launch_dependents();
   pdl_wait();   // launched with a programmatic dependency on the previous kernel of the stream
-  const RabIndex& g = blockIdx.y == 0 ? a : b;
-  const Pt4* __restrict__ pts = blockIdx.y == 0 ? pa : pb;
-  const int n = blockIdx.y == 0 ? *na : *nb;
+  const RabArgs& A = B.a[blockIdx.z];
+  const RabIndex& g = blockIdx.y == 0 ? A.a : A.b;
+  const Pt4* __restrict__ pts = blockIdx.y == 0 ? A.pa : A.pb;
+  const int n = blockIdx.y == 0 ? *A.na : *A.nb;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Pt4 p = pts[i];
@@ -270,12 +270,18 @@ __device__ __forceinline__ int rab_nearest(const RabIndex& g, float qx, float qy
 
 }  // namespace
 
-__global__ void __launch_bounds__(256) k_odom_assoc(const Pt4* __restrict__ sharp, const Pt4* __restrict__ flat,
-                                                    const int* __restrict__ feat_counts, LastCloud corner,
-                                                    LastCloud surf, const double* __restrict__ pose7, OdomParams prm,
-                                                    BlockRec* __restrict__ blocks, int* __restrict__ corr, int max_sharp) {
+__global__ void __launch_bounds__(256) k_odom_assoc(const __grid_constant__ Batch<AssocArgs> B, OdomParams prm, int max_sharp) {
   pdl_launch_dependents();   // the LM solve that follows may become resident now; it blocks in its own pdl_wait()
   pdl_wait();                // the preceding LM solve (pose7 producer, blocks consumer) has completed
+  const AssocArgs& A = B.a[blockIdx.y];   // blockIdx.y = trajectory of the batch
+  const Pt4* __restrict__ sharp = A.sharp;
+  const Pt4* __restrict__ flat = A.flat;
+  const int* __restrict__ feat_counts = A.feat_counts;
+  const LastCloud& corner = A.corner;
+  const LastCloud& surf = A.surf;
+  const double* __restrict__ pose7 = A.pose7;
+  BlockRec* __restrict__ blocks = A.blocks;
+  int* __restrict__ corr = A.corr;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = lane_id();
   const bool is_corner = wid < max_sharp;

@@ -233,7 +233,7 @@ extern "C" int aloam_voxel_filter_impl(aloam_ctx* c, aloam_cloud_view in, float 
     CUDA_CHECK_RET(cudaMalloc((void**)&c->d_vox_misc, 64 * 4 + (size_t)nb_max * 4));
   }
   Pt4* d_in = c->d_query;        // staging buffers that already exist in the context
-  Pt4* d_out = c->d_full;
+  Pt4* d_out = c->lanes[0].d_full[0];
   rc = upload_cloud(c, in, d_in, c->max_points); if (rc) return rc;
   int* mm6 = c->d_vox_misc; int* d_total = c->d_vox_misc + 8; int* block_heads = c->d_vox_misc + 64;
   const int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};

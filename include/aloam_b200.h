@@ -41,6 +41,7 @@ extern "C" {
 #define ALOAM_ERR_COMM (-10)
 
 #define ALOAM_MAX_RING_POINTS 4096
+#define ALOAM_MAX_BATCH 16
 
 #define ALOAM_FLAG_FEW_CORRESPONDENCES 1
 #define ALOAM_FLAG_MAP_TOO_THIN 2
@@ -62,7 +63,10 @@ typedef struct aloam_config {
   double nearby_scan;    /* 2.5 NEARBY_SCAN, laserOdometry.cpp:66 */
   int device;            /* CUDA device ordinal */
   int max_points;        /* capacity of one raw scan (reference: 400000 static arrays, scanRegistration.cpp:66-69) */
-  int max_map_points;    /* capacity of the uploaded submap, corner + surf (0 = mapping not used) */
+  int max_map_points;    /* capacity of the uploaded submap, per cloud type (0 = mapping not used) */
+  int max_batch;         /* trajectories a context can advance in lockstep (aloam_scan_stream_batch); 1..ALOAM_MAX_BATCH, default 1 */
+  int max_ring_points;   /* capacity of one scan ring, multiple of 32, <= ALOAM_MAX_RING_POINTS (default).  Smaller rings take
+                            less shared memory per ring CTA, so more of them are resident per SM (batched streams) */
 } aloam_config;
 
 typedef struct aloam_cloud_view {
@@ -127,7 +131,16 @@ int aloam_scan_to_pose_device(aloam_ctx* ctx, const float* d_raw_xyzi, int n, do
  * poses: n_scans x 7 doubles (q_w xyzw, t_w). */
 int aloam_scan_stream(aloam_ctx* ctx, const aloam_cloud_view* raws, int n_scans, int device_resident, double* poses,
                       aloam_stats* stats_last);
-int aloam_reset_odometry(aloam_ctx* ctx); /* forget pose, warm start and "last" clouds */
+/* batched form (BASELINE configs[4], SURVEY.md 8b "aloam_*_batch"): `batch` independent trajectories advance in lockstep and
+ * SHARE every kernel launch (ring CTAs of all trajectories in one grid, one LM cluster per trajectory, ...), so one
+ * context and one host thread fill the GPU.  raws: n_scans x batch views, scan-major (raws[k * batch + b] = scan k of
+ * trajectory b); poses: n_scans x batch x 7 doubles in the same order; stats_last: `batch` entries or NULL.  Every
+ * trajectory keeps the reference's warm-start chain (laserOdometry.cpp:97-98,504-505) and its result is bit-identical to
+ * running it alone through aloam_scan_stream.  batch <= cfg.max_batch; all trajectories of a context share the frame
+ * counter (the first scan of a fresh / reset context only initialises, laserOdometry.cpp:267-271). */
+int aloam_scan_stream_batch(aloam_ctx* ctx, const aloam_cloud_view* raws, int n_scans, int batch, int device_resident,
+                            double* poses, aloam_stats* stats_last);
+int aloam_reset_odometry(aloam_ctx* ctx); /* forget pose, warm start and "last" clouds (all trajectories) */
 
 /* ---- fine-grained entry points (tests; or to keep Ceres in the loop) */
 /* exact k-NN replacing pcl::KdTreeFLANN::nearestKSearch: which = 0 corner_last, 1 surf_last (laserOdometry.cpp:302,390),
