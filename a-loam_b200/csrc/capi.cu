@@ -193,7 +193,8 @@ int aloam_create(const aloam_config* cfg_in, aloam_ctx** out) {
   TRY(halloc(&c->h_ints, 4096)); TRY(halloc(&c->h_dbl, 4096));
   TRY(halloc(&c->h_summary, (size_t)4 * c->n_lanes)); TRY(halloc(&c->h_sc, (size_t)3 * c->n_lanes));
   TRY(cudaMemset(c->d_err, 0, 16));
-  TRY(cudaFuncSetAttribute(k_ring_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_features_smem_bytes(c->max_ring)));
+  // function attributes are process-wide: always opt in to the largest ring capacity, whatever this context uses
+  TRY(cudaFuncSetAttribute(k_ring_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_features_smem_bytes(ALOAM_MAX_RING)));
   TRY(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dynamic_smem_bytes()));
   TRY(cudaFuncSetAttribute(k_lm_eval_shard, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dynamic_smem_bytes()));
 #undef TRY
