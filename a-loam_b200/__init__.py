@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "aloam_odometry_set_last", "aloam_odometry_register", "aloam_map_upload", "aloam_mapping_register",
     "aloam_voxel_filter", "aloam_scan_to_pose", "aloam_scan_to_pose_device", "aloam_reset_odometry", "aloam_knn",
     "aloam_odometry_associate", "aloam_normal_equations", "aloam_solve", "aloam_debug_features", "aloam_mapping_associate",
-    "aloam_comm_unique_id", "aloam_comm_init", "aloam_scan_stream", "aloam_scan_stream_batch", "aloam_mapper_reset", "aloam_mapper_step", "aloam_profile_enable", "aloam_profile_read", "aloam_launch_count",
+    "aloam_comm_unique_id", "aloam_comm_init", "aloam_scan_stream", "aloam_scan_stream_batch", "aloam_transform_to_end", "aloam_mapper_reset", "aloam_mapper_step", "aloam_profile_enable", "aloam_profile_read", "aloam_launch_count",
 ]
 
 
@@ -30,7 +30,7 @@ class Config(C.Structure):
     _fields_ = [("n_scans", C.c_int), ("minimum_range", C.c_float), ("line_res", C.c_float), ("plane_res", C.c_float),
                 ("outer_iters", C.c_int), ("inner_iters", C.c_int), ("huber", C.c_double), ("dist_sq_thresh", C.c_double),
                 ("nearby_scan", C.c_double), ("device", C.c_int), ("max_points", C.c_int), ("max_map_points", C.c_int),
-                ("max_batch", C.c_int), ("max_ring_points", C.c_int)]
+                ("max_batch", C.c_int), ("distortion", C.c_int), ("max_ring_points", C.c_int)]
 
 
 class CloudView(C.Structure):
@@ -89,6 +89,7 @@ def lib():
         L.aloam_reset_odometry.argtypes = [C.c_void_p]
         L.aloam_scan_stream.argtypes = [C.c_void_p, C.POINTER(cv), C.c_int, C.c_int, dp, C.POINTER(Stats)]
         L.aloam_scan_stream_batch.argtypes = [C.c_void_p, C.POINTER(cv), C.c_int, C.c_int, C.c_int, dp, C.POINTER(Stats)]
+        L.aloam_transform_to_end.argtypes = [C.c_void_p, cv, dp, dp, C.c_int, C.POINTER(cv)]
         L.aloam_knn.argtypes = [C.c_void_p, C.c_int, cv, C.c_int, ip, fp]
         L.aloam_odometry_associate.argtypes = [C.c_void_p, cv, cv, dp, dp, ip, ip]
         L.aloam_normal_equations.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp, dp]
@@ -323,6 +324,13 @@ class Aloam:
         _check(lib().aloam_scan_stream_batch(self._h, views, n, b, int(device_resident), _dp(poses), st))
         self.last_batch_stats = [s.as_dict() for s in st]
         return poses
+
+    def transform_to_end(self, cloud, q, t, distortion=True):
+        v, keep = _view(cloud)
+        o = CloudView()
+        _check(lib().aloam_transform_to_end(self._h, v, _dp(np.ascontiguousarray(q, np.float64)), _dp(np.ascontiguousarray(t, np.float64)),
+                                            int(distortion), C.byref(o)))
+        return _out(o)
 
     def reset_odometry(self):
         _check(lib().aloam_reset_odometry(self._h))

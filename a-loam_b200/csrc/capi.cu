@@ -30,7 +30,7 @@ void aloam_default_config(aloam_config* cfg, int n_scans) {
   cfg->outer_iters = 2; cfg->inner_iters = 4; cfg->huber = 0.1;
   cfg->dist_sq_thresh = 25.0; cfg->nearby_scan = 2.5;
   cfg->device = 0; cfg->max_points = 400000; cfg->max_map_points = 0;
-  cfg->max_batch = 1; cfg->max_ring_points = ALOAM_MAX_RING_POINTS;
+  cfg->max_batch = 1; cfg->distortion = 0; cfg->max_ring_points = ALOAM_MAX_RING_POINTS;
 }
 
 const char* aloam_strerror(int code) {
@@ -286,7 +286,7 @@ void run_grid_build(aloam_ctx* c, int nb, int slot, int n_ls, int n_lf) {
 // outer_iters x (association + LM) ; feat[cur] supplies sharp/flat, feat[last] the targets ; pose in lane.d_pose
 // pose_slots (device, lane-major 7 doubles each, may be null): the integrated world pose is also written there by the last solve
 void run_register(aloam_ctx* c, int nb, int cur, int last, int sharp_slots, int flat_slots, bool integrate, bool want_corr, double* pose_slots) {
-  OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan};
+  OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan, c->cfg.distortion};
   const LmParams lp = lm_params(c->cfg);
   const int slots = sharp_slots + flat_slots;
   for (int it = 0; it < c->cfg.outer_iters; ++it) {
@@ -444,7 +444,7 @@ int aloam_odometry_associate(aloam_ctx* c, aloam_cloud_view sharp, aloam_cloud_v
   for (int k = 0; k < 4; ++k) c->h_dbl[k] = q[k];
   for (int k = 0; k < 3; ++k) c->h_dbl[4 + k] = t[k];
   CUDA_CHECK_RET(cudaMemcpyAsync(L.d_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
-  OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan};
+  OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan, c->cfg.distortion};
   const int slots = sharp.n + flat.n;
   if (slots > 0) {
     Batch<AssocArgs> aa = {};
@@ -679,6 +679,25 @@ int aloam_knn(aloam_ctx* c, int which, aloam_cloud_view queries, int k, int* idx
   }
   if (which == 2 || which == 3) return aloam_map_knn_impl(c, which, queries, k, idx, sqdist);
   return ALOAM_ERR_INVALID_ARG;
+}
+
+int aloam_transform_to_end(aloam_ctx* c, aloam_cloud_view in, const double q[4], const double t[3], int distortion, aloam_cloud_view* out) {
+  if (!c || !q || !t || !out) return ALOAM_ERR_INVALID_ARG;
+  int rc = check_view(in); if (rc) return rc;
+  if (in.n > c->max_points) return ALOAM_ERR_CAPACITY;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  out->data = reinterpret_cast<const float*>(c->h_out[0]); out->n = in.n; out->stride_floats = 4;
+  if (in.n == 0) return ALOAM_OK;
+  rc = upload_cloud(c, in, c->d_query, c->max_points); if (rc) return rc;
+  for (int k = 0; k < 4; ++k) c->h_dbl[k] = q[k];
+  for (int k = 0; k < 3; ++k) c->h_dbl[4 + k] = t[k];
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->d_out28, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
+  Pt4* d_out = c->lanes[0].d_full[0];
+  LAUNCH(c, KID_KNN_LAST, k_transform_to_end, (in.n + 255) / 256, 256, 0, c->d_query, in.n, c->d_out28, distortion, d_out);
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_out[0], d_out, (size_t)in.n * 16, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK_RET(cudaGetLastError());
+  return ALOAM_OK;
 }
 
 static int run_lm_api(aloam_ctx* c, const double* blocks, int n_blocks, const double x[7], int mode) {

@@ -59,6 +59,22 @@ __device__ __forceinline__ void warp_argmin(float& d2, int& idx) {
   idx = (int)mi;
 }
 
+// Eigen QuaternionBase::slerp(s, q) called on the identity (laserOdometry.cpp:120, lidarFactor.hpp:29-30,81-82): double
+// precision, (x, y, z, w).  |q.w| >= 1 - eps takes the linear blend, q.w < 0 flips the second weight; slerp(1, q) == q exactly.
+__device__ __forceinline__ void slerp_identity(const double* q, double s, double* o) {
+  const double one = 1.0 - 2.220446049250313e-16;
+  const double d = q[3], ad = fabs(d);
+  double w0, w1;
+  if (ad >= one) { w0 = 1.0 - s; w1 = s; }
+  else {
+    const double th = acos(ad), sth = sin(th);
+    w0 = sin((1.0 - s) * th) / sth;
+    w1 = sin(s * th) / sth;
+  }
+  if (d < 0.0) w1 = -w1;
+  o[0] = w1 * q[0]; o[1] = w1 * q[1]; o[2] = w1 * q[2]; o[3] = w0 + w1 * q[3];
+}
+
 __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
   // ((dx*dx) + dy*dy) + dz*dz in float, no contraction (compiled with -fmad=false)
   float dx = ax - bx, dy = ay - by, dz = az - bz;

@@ -63,12 +63,14 @@ struct __align__(8) BlockRec {
   double cp[3];  // curr_point (untransformed)
   double a[3];   // edge: last_point_a          plane: last_point_j      plane-norm: unit normal
   double b[3];   // edge: last_point_b          plane: ljm_norm          plane-norm: unused
-  double s;      // edge: 1 / |a-b| (1 / de.norm()) plane: unused         plane-norm: negative_OA_dot_norm
+  double s;      // edge / plane: interpolation ratio s of the functor (1 unless DISTORTION)     plane-norm: negative_OA_dot_norm
+  double w;      // edge: 1 / |a-b| (1 / de.norm())
   int type;      // 0 edge, 1 plane, 2 plane-norm, -1 = no residual (query without correspondence)
   int pad;
 };
 #define ALOAM_MAX_QUERIES 16384   // capacity of the sharp / flat query buffers (ctx.h kMaxQueries)
-struct OdomParams { double dist_sq_thresh; double nearby_scan; };
+struct OdomParams { double dist_sq_thresh; double nearby_scan; int distortion; /* laserOdometry.cpp:59 #define DISTORTION */ };
+__global__ void k_transform_to_end(const Pt4* in, int n, const double* pose7, int distortion, Pt4* out);
 struct AssocArgs { const Pt4* sharp; const Pt4* flat; const int* feat_counts /*[4]*/; LastCloud corner, surf; const double* pose7;
                    BlockRec* blocks; int* corr /*[(n_sharp+n_flat)][4] a,b,c,valid ; may be null*/; };
 __global__ void k_odom_assoc(const __grid_constant__ Batch<AssocArgs> B, OdomParams prm, int max_sharp);   // grid (query groups, lanes)

@@ -63,23 +63,78 @@ __device__ __forceinline__ void huber_rho(double huber_a, double sq, double& rho
   }
 }
 
-__device__ __forceinline__ void eval_block(const BlockRec& rb, const double* x, double huber_a, double* acc) {
-  // lp = R(q) cp + t   (s == 1 for every block the reference builds; slerp(1, q) == q)
-  const V3 u{x[0], x[1], x[2]};
-  const double w = x[3];
-  const V3 cp{rb.cp[0], rb.cp[1], rb.cp[2]};
+// General interpolation ratio s != 1 (DISTORTION build, lidarFactor.hpp:27-33,79-85): lp = slerp(I, q, s) p + s t.
+// With Ceres' left-multiplicative Plus, a perturbation eps = 2 dtheta of q moves q^s by the left perturbation M eps,
+// M = s Jl(s phi) Jl(phi)^-1 (phi = rotation vector of q, Jl = left Jacobian of SO(3)), a polynomial m0 I + m1 K + m2 K^2 in
+// K = [phi / |phi|]x.  Row of a residual with gradient g wrt lp:  [ (2 (Rp x g))^T M , s g^T ].  The same closed form as
+// include/lidarFactor.hpp (checked there against Jet autodiff of the literal functor); M = I for s = 1.
+struct StartFrame {
+  V3 Rp;             // R^s p
+  V3 k;              // rotation axis
+  double m0, m1, m2, s;
+};
+__device__ __noinline__ void start_frame_general(const double* x, const V3& cp, double s, StartFrame& F) {
+  double qs[4];
+  slerp_identity(x, s, qs);
+  const V3 u{qs[0], qs[1], qs[2]};
   V3 uv = crossd(u, cp);
   uv.x += uv.x; uv.y += uv.y; uv.z += uv.z;
   const V3 c2 = crossd(u, uv);
-  const V3 Rp{cp.x + w * uv.x + c2.x, cp.y + w * uv.y + c2.y, cp.z + w * uv.z + c2.z};
-  const V3 lp{Rp.x + x[4], Rp.y + x[5], Rp.z + x[6]};
-  // d lp / d dtheta = -2 [Rp]x  (Ceres Plus is delta_q (x) q with a half-angle delta) ; d lp / d t = I
-  // row of J for a residual with gradient n wrt lp:  [ n^T (-2[Rp]x) , n^T ] = [ 2 (Rp x n)^T , n^T ]
+  F.Rp = V3{cp.x + qs[3] * uv.x + c2.x, cp.y + qs[3] * uv.y + c2.y, cp.z + qs[3] * uv.z + c2.z};
+  F.s = s;
+  const double sgn = x[3] < 0.0 ? -1.0 : 1.0;
+  const double vx = sgn * x[0], vy = sgn * x[1], vz = sgn * x[2], w = sgn * x[3];
+  const double vn = sqrt(vx * vx + vy * vy + vz * vz);
+  if (vn < 1e-12) { F.k = V3{1.0, 0.0, 0.0}; F.m0 = s; F.m1 = 0.0; F.m2 = 0.0; return; }
+  const double th = 2.0 * atan2(vn, w);
+  F.k = V3{vx / vn, vy / vn, vz / vn};
+  const double uang = s * th;
+  const double a1 = fabs(uang) < 1e-8 ? 0.5 * uang : (1.0 - cos(uang)) / uang;
+  const double a2 = fabs(uang) < 1e-4 ? uang * uang / 6.0 : 1.0 - sin(uang) / uang;
+  const double b1 = -0.5 * th;
+  const double b2 = 1.0 - 0.5 * th * cos(0.5 * th) / sin(0.5 * th);
+  F.m0 = s;
+  F.m1 = s * (b1 + a1 - a1 * b2 - a2 * b1);
+  F.m2 = s * (b2 + a2 + a1 * b1 - a2 * b2);
+}
+// Jacobian row for gradient g wrt lp, scaled by sr
+__device__ __forceinline__ void start_row(const StartFrame& F, const V3& g, double sr, double* j) {
+  const V3 t = crossd(F.Rp, g);
+  V3 h{2.0 * t.x, 2.0 * t.y, 2.0 * t.z};
+  if (F.m1 != 0.0 || F.m2 != 0.0 || F.m0 != 1.0) {
+    const V3 hk = crossd(h, F.k), hkk = crossd(hk, F.k);
+    h = V3{F.m0 * h.x + F.m1 * hk.x + F.m2 * hkk.x, F.m0 * h.y + F.m1 * hk.y + F.m2 * hkk.y, F.m0 * h.z + F.m1 * hk.z + F.m2 * hkk.z};
+  }
+  j[0] = h.x * sr; j[1] = h.y * sr; j[2] = h.z * sr;
+  j[3] = F.s * g.x * sr; j[4] = F.s * g.y * sr; j[5] = F.s * g.z * sr;
+}
+
+__device__ __forceinline__ void eval_block(const BlockRec& rb, const double* x, double huber_a, double* acc) {
+  // lp = R(q)^s cp + s t   (s == 1 for every block the reference build makes: slerp(1, q) == q)
+  const V3 cp{rb.cp[0], rb.cp[1], rb.cp[2]};
+  StartFrame F;
+  const double s = rb.type == 2 ? 1.0 : rb.s;
+  if (s == 1.0) {
+    const V3 u{x[0], x[1], x[2]};
+    const double w = x[3];
+    V3 uv = crossd(u, cp);
+    uv.x += uv.x; uv.y += uv.y; uv.z += uv.z;
+    const V3 c2 = crossd(u, uv);
+    F.Rp = V3{cp.x + w * uv.x + c2.x, cp.y + w * uv.y + c2.y, cp.z + w * uv.z + c2.z};
+    F.k = V3{1.0, 0.0, 0.0}; F.m0 = 1.0; F.m1 = 0.0; F.m2 = 0.0; F.s = 1.0;
+  } else {
+    StartFrame G;                       // out of line and through its own stack copy: the de-skew path must neither grow the
+    start_frame_general(x, cp, s, G);   // common path's code nor force F into local memory
+    F = G;
+  }
+  const V3 lp{F.Rp.x + s * x[4], F.Rp.y + s * x[5], F.Rp.z + s * x[6]};
+  // d lp / d dtheta = -2 [Rp]x M  (Ceres Plus is delta_q (x) q with a half-angle delta) ; d lp / d t = s I
+  // row of J for a residual with gradient n wrt lp:  [ (2 (Rp x n))^T M , s n^T ]
   if (rb.type == 0) {
     const V3 a{rb.a[0], rb.a[1], rb.a[2]}, b{rb.b[0], rb.b[1], rb.b[2]};
     const V3 la{lp.x - a.x, lp.y - a.y, lp.z - a.z}, lb{lp.x - b.x, lp.y - b.y, lp.z - b.z};
     const V3 nu = crossd(la, lb);
-    const double idn = rb.s;  // 1 / |a - b|
+    const double idn = rb.w;  // 1 / |a - b|
     const double r[3] = {nu.x * idn, nu.y * idn, nu.z * idn};
     const V3 wv{(b.x - a.x) * idn, (b.y - a.y) * idn, (b.z - a.z) * idn};
     // d r / d lp = [wv]x ; rows: n0 = (0,-wz,wy), n1 = (wz,0,-wx), n2 = (-wy,wx,0)
@@ -89,8 +144,8 @@ __device__ __forceinline__ void eval_block(const BlockRec& rb, const double* x, 
     acc[27] += 0.5 * rho0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const V3 t = crossd(Rp, ns[k]);
-      const double j[6] = {2.0 * t.x * sr, 2.0 * t.y * sr, 2.0 * t.z * sr, ns[k].x * sr, ns[k].y * sr, ns[k].z * sr};
+      double j[6];
+      start_row(F, ns[k], sr, j);
       accumulate_row(acc, j, r[k] * sr);
     }
   } else {
@@ -105,8 +160,8 @@ __device__ __forceinline__ void eval_block(const BlockRec& rb, const double* x, 
     double rho0, sr;
     huber_rho(huber_a, r * r, rho0, sr);
     acc[27] += 0.5 * rho0;
-    const V3 t = crossd(Rp, n);
-    const double j[6] = {2.0 * t.x * sr, 2.0 * t.y * sr, 2.0 * t.z * sr, n.x * sr, n.y * sr, n.z * sr};
+    double j[6];
+    start_row(F, n, sr, j);
     accumulate_row(acc, j, r * sr);
   }
 }
@@ -476,10 +531,11 @@ __global__ void k_pack_blocks(const double* __restrict__ packed, int n, BlockRec
   BlockRec r;
   r.type = (int)p[0];
   for (int k = 0; k < 3; ++k) { r.cp[k] = p[1 + k]; r.a[k] = p[4 + k]; r.b[k] = p[7 + k]; }
-  r.s = p[10];
-  if (r.type == 0) {  // edge: the kernel wants 1/|a-b| ; s of the packed form is the (always 1) interpolation ratio
+  r.s = p[10];   // edge / plane: interpolation ratio ; plane-norm: negative_OA_dot_norm
+  r.w = 0.0;
+  if (r.type == 0) {  // edge: 1/|a-b| is precomputed for the evaluation passes
     const double ex = r.a[0] - r.b[0], ey = r.a[1] - r.b[1], ez = r.a[2] - r.b[2];
-    r.s = 1.0 / sqrt(ex * ex + ey * ey + ez * ez);
+    r.w = 1.0 / sqrt(ex * ex + ey * ey + ez * ez);
   }
   r.pad = 0;
   out[i] = r;

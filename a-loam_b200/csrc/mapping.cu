@@ -446,7 +446,8 @@ __global__ void __launch_bounds__(128) k_map_fit(const Pt4* __restrict__ corner_
 #pragma unroll
       for (int k = 0; k < 3; ++k) { out->a[k] = 0.1 * dir[k] + c[k]; out->b[k] = -0.1 * dir[k] + c[k]; }
       const double ex = out->a[0] - out->b[0], ey = out->a[1] - out->b[1], ez = out->a[2] - out->b[2];
-      out->s = 1.0 / sqrt(ex * ex + ey * ey + ez * ez);
+      out->w = 1.0 / sqrt(ex * ex + ey * ey + ez * ez);
+      out->s = 1.0;   // LidarEdgeFactor(curr_point, point_a, point_b, 1.0), laserMapping.cpp:618
       out->type = 0;
       if (fo) { fo[1] = 0.0; for (int k = 0; k < 3; ++k) { fo[2 + k] = out->a[k]; fo[5 + k] = out->b[k]; } fo[8] = 0.0; }
     } else {
@@ -465,6 +466,7 @@ __global__ void __launch_bounds__(128) k_map_fit(const Pt4* __restrict__ corner_
 #pragma unroll
       for (int k = 0; k < 3; ++k) { out->a[k] = nv[k]; out->b[k] = 0.0; }
       out->s = neg_oa;
+      out->w = 0.0;
       out->type = 2;
       if (fo) { fo[1] = 2.0; for (int k = 0; k < 3; ++k) { fo[2 + k] = nv[k]; fo[5 + k] = 0.0; } fo[8] = neg_oa; }
     }

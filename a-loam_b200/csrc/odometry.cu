@@ -218,17 +218,28 @@ __device__ __forceinline__ float safe_radius_sq(float rho_q, int k) {
 struct D3 { double x, y, z; };
 __device__ __forceinline__ D3 cross3(const D3& a, const D3& b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 
-// laserOdometry.cpp:111-129 with DISTORTION == 0: slerp(1, q) == q exactly; Eigen q*v = v + w*uv + u x uv, uv = 2 u x v
-__device__ __forceinline__ void transform_to_start(const double* pose, float px, float py, float pz, float& ox, float& oy, float& oz) {
-  const D3 u{pose[0], pose[1], pose[2]};
-  const double w = pose[3];
+// laserOdometry.cpp:111-129.  s == 1 (DISTORTION 0): slerp(1, q) == q exactly; otherwise q_point_last = slerp(s, q) and
+// t_point_last = s t.  Eigen q*v = v + w*uv + u x uv, uv = 2 u x v; double math, rounded to float on store (:125-127).
+__device__ __forceinline__ void transform_to_start(const double* pose, double s, float px, float py, float pz, float& ox, float& oy, float& oz) {
+  double qs[4] = {pose[0], pose[1], pose[2], pose[3]};
+  double ts[3] = {pose[4], pose[5], pose[6]};
+  if (s != 1.0) {
+    slerp_identity(pose, s, qs);
+    ts[0] = s * pose[4]; ts[1] = s * pose[5]; ts[2] = s * pose[6];
+  }
+  const D3 u{qs[0], qs[1], qs[2]};
+  const double w = qs[3];
   const D3 v{(double)px, (double)py, (double)pz};
   D3 uv = cross3(u, v);
   uv.x = uv.x + uv.x; uv.y = uv.y + uv.y; uv.z = uv.z + uv.z;
   const D3 c2 = cross3(u, uv);
-  ox = (float)(((v.x + w * uv.x) + c2.x) + pose[4]);
-  oy = (float)(((v.y + w * uv.y) + c2.y) + pose[5]);
-  oz = (float)(((v.z + w * uv.z) + c2.z) + pose[6]);
+  ox = (float)(((v.x + w * uv.x) + c2.x) + ts[0]);
+  oy = (float)(((v.y + w * uv.y) + c2.y) + ts[1]);
+  oz = (float)(((v.z + w * uv.z) + c2.z) + ts[2]);
+}
+// interpolation ratio of a point of the current sweep (:113-118): float intensity minus its integer part, over SCAN_PERIOD
+__device__ __forceinline__ double ratio_of(float intensity, int distortion) {
+  return distortion ? (double)(intensity - (float)(int)intensity) / 0.1 : 1.0;
 }
 
 __device__ __forceinline__ void store_none(BlockRec* b, int* corr) {
@@ -299,7 +310,8 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const __grid_constant__ Batc
   const LastCloud& L = is_corner ? corner : surf;
   const RabIndex& g = L.index;
   float qx, qy, qz;
-  transform_to_start(pose, cur.x, cur.y, cur.z, qx, qy, qz);
+  const double s_ratio = ratio_of(cur.i, prm.distortion);
+  transform_to_start(pose, s_ratio, cur.x, cur.y, cur.z, qx, qy, qz);
   const float thr = (float)prm.dist_sq_thresh;
 
   // nearest neighbour (kdtree*Last->nearestKSearch(pointSel, 1, ...), :302,390) then `< DISTANCE_SQ_THRESHOLD`
@@ -369,7 +381,8 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const __grid_constant__ Batc
       out->a[0] = a.x; out->a[1] = a.y; out->a[2] = a.z;
       out->b[0] = b.x; out->b[1] = b.y; out->b[2] = b.z;
       const double ex = (double)a.x - (double)b.x, ey = (double)a.y - (double)b.y, ez = (double)a.z - (double)b.z;
-      out->s = 1.0 / sqrt(ex * ex + ey * ey + ez * ez);  // 1 / de.norm(), lidarFactor.hpp:36-40 (the LM kernel multiplies)
+      out->w = 1.0 / sqrt(ex * ex + ey * ey + ez * ez);  // 1 / de.norm(), lidarFactor.hpp:36-40 (the LM kernel multiplies)
+      out->s = s_ratio;
       out->type = 0;
       if (co) { co[0] = closest; co[1] = j2; co[2] = -1; co[3] = 1; }
     }
@@ -386,11 +399,37 @@ __global__ void __launch_bounds__(256) k_odom_assoc(const __grid_constant__ Batc
       const double z = nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z;
       if (z > 0) { const double nn = sqrt(z); nrm.x /= nn; nrm.y /= nn; nrm.z /= nn; }
       out->b[0] = nrm.x; out->b[1] = nrm.y; out->b[2] = nrm.z;
-      out->s = 1.0;
+      out->s = s_ratio;
+      out->w = 0.0;
       out->type = 1;
       if (co) { co[0] = closest; co[1] = j2; co[2] = j3; co[3] = 1; }
     }
   }
+}
+
+// laserOdometry.cpp:133-148 TransformToEnd: undistort to the sweep start, then carry to the sweep end; the integer part of the
+// intensity is kept (dead code in the reference -- its call sites are under `if (0)`, :533-552 -- offered through aloam_transform_to_end)
+__global__ void k_transform_to_end(const Pt4* __restrict__ in, int n, const double* __restrict__ pose7, int distortion, Pt4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double pose[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) pose[k] = pose7[k];
+  const Pt4 p = in[i];
+  float ux, uy, uz;
+  transform_to_start(pose, ratio_of(p.i, distortion), p.x, p.y, p.z, ux, uy, uz);
+  // q_last_curr.inverse() = conjugate / squaredNorm (Eigen)
+  const double n2 = pose[0] * pose[0] + pose[1] * pose[1] + pose[2] * pose[2] + pose[3] * pose[3];
+  const D3 u{-pose[0] / n2, -pose[1] / n2, -pose[2] / n2};
+  const double w = pose[3] / n2;
+  const D3 v{(double)ux - pose[4], (double)uy - pose[5], (double)uz - pose[6]};
+  D3 uv = cross3(u, v);
+  uv.x = uv.x + uv.x; uv.y = uv.y + uv.y; uv.z = uv.z + uv.z;
+  const D3 c2 = cross3(u, uv);
+  Pt4 o;
+  o.x = (float)((v.x + w * uv.x) + c2.x); o.y = (float)((v.y + w * uv.y) + c2.y); o.z = (float)((v.z + w * uv.z) + c2.z);
+  o.i = (float)(int)p.i;
+  out[i] = o;
 }
 
 // exact 1-NN of arbitrary queries against a "last" cloud (aloam_knn, which = 0/1): no distance limit

@@ -65,6 +65,9 @@ typedef struct aloam_config {
   int max_points;        /* capacity of one raw scan (reference: 400000 static arrays, scanRegistration.cpp:66-69) */
   int max_map_points;    /* capacity of the uploaded submap, per cloud type (0 = mapping not used) */
   int max_batch;         /* trajectories a context can advance in lockstep (aloam_scan_stream_batch); 1..ALOAM_MAX_BATCH, default 1 */
+  int distortion;        /* 0 (reference build) or 1: #define DISTORTION of laserOdometry.cpp:59 -- per-point interpolation ratio
+                            s = (intensity - int(intensity)) / SCAN_PERIOD in TransformToStart (:113-118) and in the
+                            residual blocks (:376-379, 470-473; slerp inside the functors, lidarFactor.hpp:27-33) */
   int max_ring_points;   /* capacity of one scan ring, multiple of 32, <= ALOAM_MAX_RING_POINTS (default).  Smaller rings take
                             less shared memory per ring CTA, so more of them are resident per SM (batched streams) */
 } aloam_config;
@@ -142,6 +145,13 @@ int aloam_scan_stream_batch(aloam_ctx* ctx, const aloam_cloud_view* raws, int n_
                             double* poses, aloam_stats* stats_last);
 int aloam_reset_odometry(aloam_ctx* ctx); /* forget pose, warm start and "last" clouds (all trajectories) */
 
+/* TransformToEnd of laserOdometry.cpp:133-148 on a whole cloud: undistort every point to the sweep start with its own
+ * interpolation ratio, then carry it to the sweep end with (q_last_curr, t_last_curr); the intensity keeps only the scan id.
+ * (Dead code in the reference -- its call sites sit under `if (0)`, :533-552 -- provided because the DISTORTION build
+ * is where it belongs.)  distortion != 0 uses the per-point ratio, 0 uses s = 1.  out: view into ctx-owned pinned memory. */
+int aloam_transform_to_end(aloam_ctx* ctx, aloam_cloud_view in, const double q_last_curr[4], const double t_last_curr[3],
+                           int distortion, aloam_cloud_view* out);
+
 /* ---- fine-grained entry points (tests; or to keep Ceres in the loop) */
 /* exact k-NN replacing pcl::KdTreeFLANN::nearestKSearch: which = 0 corner_last, 1 surf_last (laserOdometry.cpp:302,390),
  * 2 corner_map, 3 surf_map (laserMapping.cpp:582,648).  idx/sqdist: queries.n x k, ascending (dist, index). */
@@ -151,6 +161,8 @@ int aloam_odometry_associate(aloam_ctx* ctx, aloam_cloud_view sharp, aloam_cloud
                              const double t[3], int* corner_corr, int* plane_corr);
 /* residual blocks are 11 doubles [type(0 edge,1 plane,2 plane-norm), cp(3), a(3), b(3), s]; for type 1 b is the unit
  * normal LidarPlaneFactor precomputes (lidarFactor.hpp:64-65), for type 2 a is the unit normal and s = negative_OA_dot_norm.
+ * For types 0 and 1 s is the functor's interpolation ratio (1.0 in the reference build; any value in [0, 1] is evaluated with the
+ * slerp of lidarFactor.hpp:27-33 and its analytic Jacobian).  include/lidarFactor.hpp packs these records (PackBlock).
  * JtJ (6x6 row-major), Jtr (6) in the tangent [dtheta(3), dt(3)] with Huber(0.1) applied, cost = sum 0.5 rho. */
 int aloam_normal_equations(aloam_ctx* ctx, const double* blocks, int n_blocks, const double x[7], double JtJ[36],
                            double Jtr[6], double* cost);

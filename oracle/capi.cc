@@ -155,6 +155,11 @@ void orc_quat_plus(const double x[4], const double d[3], double out[4]) { quat_p
 // ---------------------------------------------------------------- odometry
 void* orc_odom_create() { return new Odometry(); }
 void orc_odom_free(void* h) { delete (Odometry*)h; }
+void orc_odom_set_distortion(void* h, int on) { ((Odometry*)h)->distortion = on != 0; }
+void orc_transform_to_end(const float* in, int n, const double q[4], const double t[3], int distortion, float* out) {
+  Cloud o; transform_to_end(to_cloud(in, n), q, t, distortion != 0, &o);
+  for (int i = 0; i < n; ++i) { out[4 * i] = o[i].x; out[4 * i + 1] = o[i].y; out[4 * i + 2] = o[i].z; out[4 * i + 3] = o[i].intensity; }
+}
 void orc_odom_set_last(void* h, const float* corner, int nc, const float* surf, int ns) {
   ((Odometry*)h)->set_last(to_cloud(corner, nc), to_cloud(surf, ns));
 }

@@ -142,7 +142,7 @@ double evaluate(const std::vector<ResidualBlock>& blocks, const double x[7], dou
     double Jl[18];
     if (!want_j) {
       functor<double>(rb, x, x + 4, r);  // AutoDiffCostFunction::Evaluate with jacobians == NULL: plain doubles
-    } else if (autodiff) {
+    } else if (autodiff || (rb.type != FACTOR_PLANE_NORM && rb.s != 1.0)) {   // the closed form below is written for s == 1
       typedef Jet<7> J7;
       J7 q[4], t[3], rr[3];
       for (int i = 0; i < 4; ++i) q[i] = J7(x[i], i);

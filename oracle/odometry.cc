@@ -1,5 +1,5 @@
 // ORACLE (test infrastructure) -- scan-to-scan registration of laserOdometry.cpp:
-//   :111-129  TransformToStart (DISTORTION 0 => s = 1; double math, rounded to float on store)
+//   :111-129  TransformToStart (DISTORTION 0 => s = 1, DISTORTION 1 => per-point ratio; double math, rounded to float on store)
 //   :278-501  2 x { corner association (:299-384), plane association (:387-483), ceres::Solve (:494-499) }
 //   :504-505  pose integration            :554-568  swap "last" clouds, rebuild both kd-trees
 // All squared distances in the ring-window scans are float expressions (operands are float members; only the
@@ -13,9 +13,17 @@ namespace {
 const double DISTANCE_SQ_THRESHOLD = 25;  // laserOdometry.cpp:65
 const double NEARBY_SCAN = 2.5;           // :66
 
-// :111-129 with DISTORTION == 0
-inline PointXYZI transform_to_start(const PointXYZI& pi, const Quat& q_last_curr, const Vec3& t_last_curr) {
-  const double s = 1.0;
+const double SCAN_PERIOD = 0.1;           // :64
+
+// interpolation ratio (:113-118,376-379): float intensity minus its integer part (float arithmetic), divided by the double
+inline double ratio_of(const PointXYZI& pi, bool distortion) {
+  if (distortion) return (pi.intensity - int(pi.intensity)) / SCAN_PERIOD;
+  return 1.0;
+}
+
+// :111-129
+inline PointXYZI transform_to_start(const PointXYZI& pi, const Quat& q_last_curr, const Vec3& t_last_curr, bool distortion) {
+  const double s = ratio_of(pi, distortion);
   Quat q_point_last = slerp(Quat{0, 0, 0, 1}, s, q_last_curr);
   Vec3 t_point_last{s * t_last_curr.x, s * t_last_curr.y, s * t_last_curr.z};
   Vec3 point{pi.x, pi.y, pi.z};
@@ -49,7 +57,7 @@ void Odometry::associate(const Cloud& sharp, const Cloud& flat, const double qv[
   int nn_idx; float nn_d;
 
   for (int i = 0; i < (int)sharp.size(); ++i) {  // :299
-    PointXYZI sel = transform_to_start(sharp[i], q, t);
+    PointXYZI sel = transform_to_start(sharp[i], q, t, distortion);
     const float qq[3] = {sel.x, sel.y, sel.z};
     if (tree_corner.knn(qq, 1, &nn_idx, &nn_d) < 1) continue;  // (PCL would return 0 neighbours on an empty tree)
     int closest = -1, second = -1;
@@ -76,13 +84,13 @@ void Odometry::associate(const Cloud& sharp, const Cloud& flat, const double qv[
         const double cp[3] = {sharp[i].x, sharp[i].y, sharp[i].z};
         const double a[3] = {corner_last[closest].x, corner_last[closest].y, corner_last[closest].z};
         const double b[3] = {corner_last[second].x, corner_last[second].y, corner_last[second].z};
-        blocks->push_back(make_edge(cp, a, b, 1.0));
+        blocks->push_back(make_edge(cp, a, b, ratio_of(sharp[i], distortion)));
       }
     }
   }
 
   for (int i = 0; i < (int)flat.size(); ++i) {  // :387
-    PointXYZI sel = transform_to_start(flat[i], q, t);
+    PointXYZI sel = transform_to_start(flat[i], q, t, distortion);
     const float qq[3] = {sel.x, sel.y, sel.z};
     if (tree_surf.knn(qq, 1, &nn_idx, &nn_d) < 1) continue;
     if (!(nn_d < DISTANCE_SQ_THRESHOLD)) continue;
@@ -109,7 +117,7 @@ void Odometry::associate(const Cloud& sharp, const Cloud& flat, const double qv[
         const double a[3] = {surf_last[closest].x, surf_last[closest].y, surf_last[closest].z};
         const double b[3] = {surf_last[m2].x, surf_last[m2].y, surf_last[m2].z};
         const double c[3] = {surf_last[m3].x, surf_last[m3].y, surf_last[m3].z};
-        blocks->push_back(make_plane(cp, a, b, c, 1.0));
+        blocks->push_back(make_plane(cp, a, b, c, ratio_of(flat[i], distortion)));
       }
     }
   }
@@ -134,6 +142,21 @@ void Odometry::register_scan(const Cloud& sharp, const Cloud& flat, double q[4],
     for (int i = 0; i < 3; ++i) t[i] = x[4 + i];
     summaries.push_back(S);
     times.solve_ms += now_ms() - t0;
+  }
+}
+
+void transform_to_end(const Cloud& in, const double qv[4], const double tv[3], bool distortion, Cloud* out) {
+  const Quat q{qv[0], qv[1], qv[2], qv[3]};
+  const Vec3 t{tv[0], tv[1], tv[2]};
+  out->resize(in.size());
+  for (size_t i = 0; i < in.size(); ++i) {
+    const PointXYZI un = transform_to_start(in[i], q, t, distortion);          // :136-137 (rounded to float, as the PointType temp)
+    const Vec3 d{(double)un.x - t.x, (double)un.y - t.y, (double)un.z - t.z};
+    const Vec3 e = rotate(qinv(q), d);                                           // :140
+    PointXYZI po;
+    po.x = (float)e.x; po.y = (float)e.y; po.z = (float)e.z;
+    po.intensity = (float)int(in[i].intensity);                                  // :147 remove distortion time info
+    (*out)[i] = po;
   }
 }
 

@@ -114,12 +114,17 @@ class Odometry {
   void associate(const Cloud& sharp, const Cloud& flat, const double q[4], const double t[3],
                  std::vector<Correspondence>* corner_corr, std::vector<Correspondence>* plane_corr,
                  std::vector<ResidualBlock>* blocks) const;
+  // #define DISTORTION (laserOdometry.cpp:59): 0 in the reference build; 1 = per-point interpolation ratio
+  // s = (intensity - int(intensity)) / SCAN_PERIOD in TransformToStart (:115-116) and in the residual blocks (:376-379,470-473)
+  bool distortion = false;
   Cloud corner_last, surf_last;
   KdTree tree_corner, tree_surf;
   OdomTimes times;
   std::vector<SolveSummary> summaries;
   int last_corner_corr = 0, last_plane_corr = 0;
 };
+// laserOdometry.cpp:133-148 TransformToEnd (dead code in the reference: its only call sites sit under `if (0)`, :533-552)
+void transform_to_end(const Cloud& in, const double q_last_curr[4], const double t_last_curr[3], bool distortion, Cloud* out);
 // laserOdometry.cpp:504-505
 void integrate_pose(double q_w[4], double t_w[3], const double q_last_curr[4], const double t_last_curr[3]);
 

@@ -63,6 +63,8 @@ def lib():
         L.orc_quat_plus.argtypes = [_f64p, _f64p, _f64p]
         L.orc_odom_create.restype = C.c_void_p
         L.orc_odom_free.argtypes = [C.c_void_p]
+        L.orc_odom_set_distortion.argtypes = [C.c_void_p, C.c_int]
+        L.orc_transform_to_end.argtypes = [_f32p, C.c_int, _f64p, _f64p, C.c_int, _f32p]
         L.orc_odom_set_last.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, C.c_int]
         L.orc_odom_associate.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, C.c_int, _f64p, _f64p, _i32p, _i32p, _i32p, _i32p, _f64p, _i32p]
         L.orc_odom_register.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, C.c_int, _f64p, _f64p, C.c_int, C.c_int, C.c_int, C.c_double, _f64p, _f64p, _i32p]
@@ -238,8 +240,10 @@ def quat_plus(q, d):
 
 
 class Odometry:
-    def __init__(self):
+    def __init__(self, distortion=False):
         self.h = lib().orc_odom_create()
+        if distortion:
+            lib().orc_odom_set_distortion(self.h, 1)     # laserOdometry.cpp:59 #define DISTORTION 1
 
     def set_last(self, corner, surf):
         corner, surf = _cloud(corner), _cloud(surf)
@@ -273,6 +277,15 @@ class Odometry:
         if getattr(self, "h", None):
             lib().orc_odom_free(self.h)
             self.h = None
+
+
+def transform_to_end(cloud, q, t, distortion=True):
+    """laserOdometry.cpp:133-148 (dead code in the reference: only called under `if (0)`)"""
+    cloud = _cloud(cloud)
+    out = np.zeros_like(cloud)
+    lib().orc_transform_to_end(_fp(cloud), cloud.shape[0], _dp(np.ascontiguousarray(q, np.float64)), _dp(np.ascontiguousarray(t, np.float64)),
+                               int(distortion), _fp(out))
+    return out
 
 
 def integrate_pose(q_w, t_w, q, t):
