@@ -14,7 +14,7 @@ SO_PATH = os.path.join(_HERE, "libaloam_b200.so")
 _LIB = None
 
 OK = 0
-FLAG_FEW_CORRESPONDENCES, FLAG_MAP_TOO_THIN, FLAG_INITIALISED_ONLY = 1, 2, 4
+FLAG_FEW_CORRESPONDENCES, FLAG_MAP_TOO_THIN, FLAG_INITIALISED_ONLY, FLAG_CUBE_OVERFLOW = 1, 2, 4, 8
 BLOCK_DOUBLES = 11
 
 EXPORTED_SYMBOLS = [
@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "aloam_odometry_set_last", "aloam_odometry_register", "aloam_map_upload", "aloam_mapping_register",
     "aloam_voxel_filter", "aloam_scan_to_pose", "aloam_scan_to_pose_device", "aloam_reset_odometry", "aloam_knn",
     "aloam_odometry_associate", "aloam_normal_equations", "aloam_solve", "aloam_debug_features", "aloam_mapping_associate",
-    "aloam_comm_unique_id", "aloam_comm_init", "aloam_scan_stream", "aloam_scan_stream_batch", "aloam_transform_to_end", "aloam_mapper_reset", "aloam_mapper_step", "aloam_profile_enable", "aloam_profile_read", "aloam_launch_count",
+    "aloam_comm_unique_id", "aloam_comm_init", "aloam_scan_stream", "aloam_scan_stream_batch", "aloam_scan_stream_mapped", "aloam_transform_to_end", "aloam_mapper_reset", "aloam_mapper_step", "aloam_profile_enable", "aloam_profile_read", "aloam_launch_count",
 ]
 
 
@@ -89,6 +89,7 @@ def lib():
         L.aloam_reset_odometry.argtypes = [C.c_void_p]
         L.aloam_scan_stream.argtypes = [C.c_void_p, C.POINTER(cv), C.c_int, C.c_int, dp, C.POINTER(Stats)]
         L.aloam_scan_stream_batch.argtypes = [C.c_void_p, C.POINTER(cv), C.c_int, C.c_int, C.c_int, dp, C.POINTER(Stats)]
+        L.aloam_scan_stream_mapped.argtypes = [C.c_void_p, C.POINTER(cv), C.c_int, C.c_int, dp, dp, C.POINTER(Stats)]
         L.aloam_transform_to_end.argtypes = [C.c_void_p, cv, dp, dp, C.c_int, C.POINTER(cv)]
         L.aloam_knn.argtypes = [C.c_void_p, C.c_int, cv, C.c_int, ip, fp]
         L.aloam_odometry_associate.argtypes = [C.c_void_p, cv, cv, dp, dp, ip, ip]
@@ -308,6 +309,17 @@ class Aloam:
         st = Stats()
         _check(lib().aloam_scan_stream(self._h, views, n, int(device_resident), _dp(poses), C.byref(st)))
         return poses, st
+
+    def scan_stream_mapped(self, ptrs, counts, device_resident, stride=4):
+        """aloam_scan_stream_mapped: odometry + scan-to-map of every scan on the device; returns (odom poses, map poses), (n, 7) each"""
+        n = len(ptrs)
+        views = (CloudView * n)()
+        for i in range(n):
+            views[i] = CloudView(C.cast(C.c_void_p(int(ptrs[i])), C.POINTER(C.c_float)), int(counts[i]), stride)
+        odom = np.zeros((n, 7)); mapped = np.zeros((n, 7))
+        st = Stats()
+        _check(lib().aloam_scan_stream_mapped(self._h, views, n, int(device_resident), _dp(odom), _dp(mapped), C.byref(st)))
+        return odom, mapped
 
     def scan_stream_batch(self, ptrs, counts, device_resident, stride=4):
         """aloam_scan_stream_batch: ptrs / counts are (n_scans, batch) arrays of addresses / point counts (scan-major);

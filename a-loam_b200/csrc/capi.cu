@@ -83,7 +83,7 @@ int aloam_destroy(aloam_ctx* c) {
   if (c->h_poses) cudaFreeHost(c->h_poses);
   if (c->h_scan_nfull) cudaFreeHost(c->h_scan_nfull);
   for (Lane& L : c->lanes) free_lane(L);
-  void* dev[] = {c->d_poses, c->d_scan_nfull, c->d_curv, c->d_label, c->d_out28, c->d_packed, c->d_err, c->d_query, c->d_knn_idx, c->d_knn_d};
+  void* dev[] = {c->d_poses, c->d_map_poses, c->d_scan_nfull, c->d_curv, c->d_label, c->d_out28, c->d_packed, c->d_err, c->d_query, c->d_knn_idx, c->d_knn_d};
   for (void* p : dev) if (p) cudaFree(p);
   aloam_map_free_impl(c);
   { void* vp[] = {c->d_vox_keys[0], c->d_vox_keys[1], c->d_vox_vals[0], c->d_vox_vals[1], c->d_vox_hist, c->d_vox_offs, c->d_vox_misc}; for (void* p : vp) if (p) cudaFree(p); }
@@ -102,6 +102,8 @@ int aloam_destroy(aloam_ctx* c) {
   delete c;
   return ALOAM_OK;
 }
+
+int aloam_mapper_reset(aloam_ctx* c);
 
 int aloam_reset_odometry(aloam_ctx* c) {
   if (!c) return ALOAM_ERR_INVALID_ARG;
@@ -153,7 +155,7 @@ int aloam_create(const aloam_config* cfg_in, aloam_ctx** out) {
   for (cudaEvent_t& e : c->ev_mapdone) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (cudaEvent_t& e : c->ev_h2d) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (cudaEvent_t& e : c->ev_rawfree) TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  TRY(halloc(&c->h_poses, (size_t)kMaxStreamScans * 7)); TRY(dalloc(&c->d_poses, (size_t)kMaxStreamScans * 7));
+  TRY(halloc(&c->h_poses, (size_t)kMaxStreamScans * 14)); TRY(dalloc(&c->d_poses, (size_t)kMaxStreamScans * 7)); TRY(dalloc(&c->d_map_poses, (size_t)kMaxStreamScans * 7));
   TRY(halloc(&c->h_scan_nfull, (size_t)kMaxStreamScans)); TRY(dalloc(&c->d_scan_nfull, (size_t)kMaxStreamScans));
   TRY(dalloc(&c->d_curv, mp)); TRY(dalloc(&c->d_label, mp));
   c->lanes.resize(c->n_lanes);
@@ -526,7 +528,9 @@ int aloam_scan_to_pose_device(aloam_ctx* c, const float* d_raw, int n, double q_
 // (main stream) and the host->device copies of scan k+2 (s_h2d) -- the overlap the reference gets from its three ROS
 // processes.  Every launch covers all nb trajectories.  Results are identical to calling aloam_scan_to_pose once per scan
 // and trajectory.  raws / poses are scan-major: entry k * nb + b.
-static int scan_stream_impl(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, int nb, int device_resident, double* poses, aloam_stats* stats_last) {
+static int scan_stream_impl(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, int nb, int device_resident, double* poses, aloam_stats* stats_last,
+                            double* map_poses = nullptr) {
+  if (map_poses && (nb != 1 || !c || c->cfg.max_map_points <= 0)) return ALOAM_ERR_INVALID_ARG;
   if (!c || !raws || !poses || n_scans < 1 || nb < 1 || nb > c->n_lanes || (long long)n_scans * nb > kMaxStreamScans) return ALOAM_ERR_INVALID_ARG;
   for (int k = 0; k < n_scans * nb; ++k) {
     int rc = check_view(raws[k]); if (rc) return rc;
@@ -536,6 +540,7 @@ static int scan_stream_impl(aloam_ctx* c, const aloam_cloud_view* raws, int n_sc
     if (raws[k].stride_floats != raws[k - k % nb].stride_floats) return ALOAM_ERR_INVALID_ARG;   // one stride per step
   }
   CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  if (map_poses && !c->mapper) { int rc = aloam_mapper_reset(c); if (rc) return rc; }   // creates the cube store
   StreamGuard guard(c);
   cudaStream_t s_main = c->stream;
   const auto host_t0 = std::chrono::steady_clock::now();
@@ -554,7 +559,7 @@ static int scan_stream_impl(aloam_ctx* c, const aloam_cloud_view* raws, int n_sc
   // everything issued on the main stream before this call (reset, earlier calls) is ordered before the side streams.
   // Waiting on an event that was never recorded, or whose work finished in an earlier call, is a no-op -- so the
   // per-scan waits below need no "first iterations" special cases.
-  for (cudaStream_t s : {c->s_h2d, c->s_exa, c->s_ext, c->s_idx}) STREAM_TRY(cudaStreamWaitEvent(s, c->ev0, 0));
+  for (cudaStream_t s : {c->s_h2d, c->s_exa, c->s_ext, c->s_idx, c->s_map}) STREAM_TRY(cudaStreamWaitEvent(s, c->ev0, 0));
   const float* d_raw[ALOAM_MAX_BATCH];
   int ns[ALOAM_MAX_BATCH];
   for (int k = 0; k < n_scans; ++k) {
@@ -597,6 +602,7 @@ static int scan_stream_impl(aloam_ctx* c, const aloam_cloud_view* raws, int n_sc
     c->stream = c->s_idx;
     STREAM_TRY(cudaStreamWaitEvent(c->s_idx, c->ev_b[b], 0));
     STREAM_TRY(cudaStreamWaitEvent(c->s_idx, c->ev_odo[(f + 1) % kFeatSlots], 0));
+    STREAM_TRY(cudaStreamWaitEvent(c->s_idx, c->ev_mapdone[cur], 0));   // the scan-to-map stage of frame f - kFeatSlots has read this slot
     rc = run_features_b2(c, nb, b, cur, false);
     if (rc) return fail(rc);
     STREAM_TRY(cudaEventRecord(c->ev_cmp[b], c->s_idx));
@@ -612,6 +618,19 @@ static int scan_stream_impl(aloam_ctx* c, const aloam_cloud_view* raws, int n_sc
     if (f > 0) run_register(c, nb, cur, last, kFusedSharpSlots, kFusedFlatSlots, true, false, slots);
     else for (int l = 0; l < nb; ++l) STREAM_TRY(cudaMemcpyAsync(slots + (size_t)l * 7, c->lanes[l].d_world, 56, cudaMemcpyDeviceToDevice, s_main));
     STREAM_TRY(cudaEventRecord(c->ev_odo[cur], s_main));
+    if (map_poses) {
+      // ---- scan-to-map on s_map (laserMapping.cpp process()): the scan's less-sharp / less-flat clouds and its odometry pose go
+      //      to the mapping stage on the device -- what the reference ships through /laser_cloud_corner_last, /laser_cloud_surf_last
+      //      and /laser_odom_to_init (laserOdometry.cpp:570-591 -> laserMapping.cpp:278-288) never leaves HBM
+      STREAM_TRY(cudaStreamWaitEvent(c->s_map, c->ev_odo[cur], 0));
+      c->stream = c->s_map;
+      const FeatBuf& fc = c->lanes[0].feat[cur];
+      rc = mapper_step_device(c, fc.less_sharp, fc.counts + 1, 64 * kMaxLessSharpPerRing, fc.less_flat, fc.counts + 3, std::min(nmax, c->max_points),
+                              c->d_poses + (size_t)k * 7, c->d_map_poses + (size_t)k * 7);
+      if (rc) return fail(rc);
+      STREAM_TRY(cudaEventRecord(c->ev_mapdone[cur], c->s_map));
+      c->stream = s_main;
+    }
     c->cur = cur;
     c->frame++;
   }
@@ -620,6 +639,10 @@ static int scan_stream_impl(aloam_ctx* c, const aloam_cloud_view* raws, int n_sc
       std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count() / n_scans);
   const size_t total = (size_t)n_scans * nb;
   STREAM_TRY(cudaMemcpyAsync(c->h_poses, c->d_poses, total * 56, cudaMemcpyDeviceToHost, s_main));
+  if (map_poses) {
+    STREAM_TRY(cudaStreamWaitEvent(s_main, c->ev_mapdone[c->cur], 0));
+    STREAM_TRY(cudaMemcpyAsync(c->h_poses + (size_t)kMaxStreamScans * 7, c->d_map_poses, total * 56, cudaMemcpyDeviceToHost, s_main));
+  }
   for (int l = 0; l < nb; ++l) {
     STREAM_TRY(cudaMemcpyAsync(c->h_summary + 4 * l, c->lanes[l].d_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, s_main));
     STREAM_TRY(cudaMemcpyAsync(c->h_sc + 3 * l, c->lanes[l].d_sc, 3 * sizeof(ScanScalars), cudaMemcpyDeviceToHost, s_main));
@@ -638,6 +661,7 @@ static int scan_stream_impl(aloam_ctx* c, const aloam_cloud_view* raws, int n_sc
   for (size_t i = 0; i < total; ++i)
     if (c->h_scan_nfull[i] <= 0) return fail(ALOAM_ERR_EMPTY_CLOUD);   // scanRegistration.cpp:136-137 left nothing of this scan
   std::memcpy(poses, c->h_poses, total * 56);
+  if (map_poses) std::memcpy(map_poses, c->h_poses + (size_t)kMaxStreamScans * 7, total * 56);
   float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   if (stats_last) {
     for (int l = 0; l < nb; ++l) {
@@ -650,6 +674,12 @@ static int scan_stream_impl(aloam_ctx* c, const aloam_cloud_view* raws, int n_sc
 
 int aloam_scan_stream(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, int device_resident, double* poses, aloam_stats* stats_last) {
   return scan_stream_impl(c, raws, n_scans, 1, device_resident, poses, stats_last);
+}
+
+int aloam_scan_stream_mapped(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, int device_resident, double* odom_poses, double* map_poses,
+                             aloam_stats* stats_last) {
+  if (!map_poses) return ALOAM_ERR_INVALID_ARG;
+  return scan_stream_impl(c, raws, n_scans, 1, device_resident, odom_poses, stats_last, map_poses);
 }
 
 int aloam_scan_stream_batch(aloam_ctx* c, const aloam_cloud_view* raws, int n_scans, int batch, int device_resident, double* poses,

@@ -95,6 +95,7 @@ struct aloam_ctx {
               ev_a[2] = {}, ev_b[2] = {}, ev_cmp[2] = {};
   double* h_poses = nullptr;     // pinned [kMaxStreamScans][7]
   double* d_poses = nullptr;     // device [kMaxStreamScans][7]: per-(scan, lane) world poses of a stream call (one D2H at the end)
+  double* d_map_poses = nullptr; // device [kMaxStreamScans][7]: map-refined poses (aloam_scan_stream_mapped)
   int* h_scan_nfull = nullptr;   // pinned [kMaxStreamScans]
   // pinned host mirrors
   Pt4* h_out[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -179,6 +180,11 @@ inline void launch_lm(aloam_ctx* c, bool pdl, const BlockRec* blocks, const int*
 }  // namespace
 // sharded LM (comm.cu): per evaluation one kernel for the local blocks, one exchange of 32 doubles, one step kernel
 void launch_lm_sharded(aloam_ctx* c, const aloam::BlockRec* blocks, const int* d_n, double* pose, const aloam::LmParams& lp, aloam::LmSummary* summary);
+void vox_seg_filter(aloam_ctx* c, const aloam::SegFilter& f, aloam::SegBuffers& b, int S_upper, int n_upper, int per_seg_upper);
+int vox_seg_alloc(aloam::SegBuffers& b, size_t cap);
+void vox_seg_free(aloam::SegBuffers& b);
+int mapper_step_device(aloam_ctx* c, const Pt4* d_corner_last, const int* d_nc, int n_upper_c, const Pt4* d_surf_last, const int* d_ns, int n_upper_s,
+                       const double* d_odom7, double* d_out7);
 void map_index_build(aloam_ctx* c, const Pt4* d_corner, const Pt4* d_surf, int n_upper);
 void map_register_device(aloam_ctx* c, const Pt4* d_corner_stack, const Pt4* d_surf_stack, const int* d_counts3, int nq_upper, double* d_pose, bool want_fits);
 namespace {

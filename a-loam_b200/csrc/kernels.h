@@ -106,6 +106,22 @@ __global__ void k_map_fit(const Pt4* corner_stack, const Pt4* surf_stack, const 
                           double* fits);
 __global__ void k_map_knn(MapCloud map, const Pt4* queries, int nq, int k, int* idx, float* sqd);
 
+// ---- voxel.cu: segmented, device-resident pcl::VoxelGrid (the scan-stack filters and the per-cube re-filter of the mapping loop)
+#define ALOAM_MAX_SEGS 160
+struct SegDesc { const Pt4* src; const int* n_in; float leaf; Pt4* dst; int* n_out; };
+struct SegFilter {
+  const SegDesc* seg;   // [n_seg] device
+  const int* n_seg;     // device
+  int* off;             // [MAX_SEGS + 1] compact offsets of the segments
+  int* rank0;           // [MAX_SEGS + 1] voxels before each segment
+  int* bbox;            // [MAX_SEGS][6] ordered-int min / max
+  int* total;           // points over all segments
+  int* err;             // sticky error word (bit 0: a segment needs more than idx_bits index bits)
+  int idx_bits;         // bits of the voxel index inside a segment
+};
+struct SegBuffers { unsigned* keys[2] = {nullptr, nullptr}; int* vals[2] = {nullptr, nullptr}; int *hist = nullptr, *offs = nullptr, *block_heads = nullptr, *heads_total = nullptr;
+                    Pt4* tmp = nullptr; size_t cap = 0; };
+
 // ---- lm.cu
 struct LmParams {
   int max_iters;

@@ -50,9 +50,11 @@ __global__ void k_vox_keys(const Pt4* __restrict__ pts, int n, VoxParams vp, uns
   vals[i] = i;
 }
 
-__global__ void __launch_bounds__(VT) k_radix_hist(const unsigned* __restrict__ keys, int n, int shift, int* __restrict__ hist) {
+__global__ void __launch_bounds__(VT) k_radix_hist(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr, int shift, int* __restrict__ hist) {
   __shared__ int s_h[256];
   const int tid = threadIdx.x;
+  const int n = *n_ptr;
+  if (blockIdx.x * VCH >= n) return;   // grids are sized by a host upper bound; the live size is on the device
   s_h[tid] = 0;
   __syncthreads();
 #pragma unroll
@@ -65,7 +67,8 @@ __global__ void __launch_bounds__(VT) k_radix_hist(const unsigned* __restrict__ 
 }
 
 // one CTA, 1024 threads: thread (bin = t >> 2, quarter = t & 3) ; offsets are digit-major over all blocks
-__global__ void __launch_bounds__(1024) k_radix_scan(const int* __restrict__ hist, int nblocks, int* __restrict__ offsets) {
+__global__ void __launch_bounds__(1024) k_radix_scan(const int* __restrict__ hist, const int* __restrict__ n_ptr, int* __restrict__ offsets) {
+  const int nblocks = (*n_ptr + VCH - 1) / VCH;
   __shared__ int s_tot[256];
   __shared__ int s_start[257];
   const int t = threadIdx.x, bin = t >> 2, q = t & 3;
@@ -94,11 +97,13 @@ __global__ void __launch_bounds__(1024) k_radix_scan(const int* __restrict__ his
   for (int b = b0; b < b1; ++b) { offsets[b * 256 + bin] = running; running += hist[b * 256 + bin]; }
 }
 
-__global__ void __launch_bounds__(VT) k_radix_scatter(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in, int n,
+__global__ void __launch_bounds__(VT) k_radix_scatter(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in, const int* __restrict__ n_ptr,
                                                       int shift, const int* __restrict__ offsets, unsigned* __restrict__ keys_out,
                                                       int* __restrict__ vals_out) {
   __shared__ int s_cnt[VIT * (VT / 32)][256];   // [slot = it*8 + warp][digit] -> exclusive prefix over slots
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int n = *n_ptr;
+  if (blockIdx.x * VCH >= n) return;
   for (int k = tid; k < VIT * (VT / 32) * 256; k += VT) (&s_cnt[0][0])[k] = 0;
   __syncthreads();
   int dig[VIT], rank[VIT];
@@ -129,7 +134,9 @@ __global__ void __launch_bounds__(VT) k_radix_scatter(const unsigned* __restrict
 }
 
 // number of voxel heads (first element of each run of equal keys) per block of VCH sorted elements
-__global__ void __launch_bounds__(VT) k_vox_heads(const unsigned* __restrict__ keys, int n, int* __restrict__ block_heads) {
+__global__ void __launch_bounds__(VT) k_vox_heads(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr, int* __restrict__ block_heads) {
+  const int n = *n_ptr;
+  if (blockIdx.x * VCH >= n) return;
   __shared__ int s_c;
   if (threadIdx.x == 0) s_c = 0;
   __syncthreads();
@@ -146,7 +153,8 @@ __global__ void __launch_bounds__(VT) k_vox_heads(const unsigned* __restrict__ k
   if (threadIdx.x == 0) block_heads[blockIdx.x] = s_c;
 }
 
-__global__ void __launch_bounds__(1024) k_vox_blockscan(int* __restrict__ block_heads, int nblocks, int* __restrict__ total) {
+__global__ void __launch_bounds__(1024) k_vox_blockscan(int* __restrict__ block_heads, const int* __restrict__ n_ptr, int* __restrict__ total) {
+  const int nblocks = (*n_ptr + VCH - 1) / VCH;
   __shared__ int s_w[32];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int per = (nblocks + 1023) / 1024;
@@ -171,7 +179,9 @@ __global__ void __launch_bounds__(1024) k_vox_blockscan(int* __restrict__ block_
 
 // every head sums its run in sorted order (float, like pcl::CentroidPoint) and writes voxel number (block offset + local rank)
 __global__ void __launch_bounds__(VT) k_vox_emit(const Pt4* __restrict__ pts, const unsigned* __restrict__ keys, const int* __restrict__ vals,
-                                                 int n, const int* __restrict__ block_offsets, Pt4* __restrict__ out) {
+                                                 const int* __restrict__ n_ptr, const int* __restrict__ block_offsets, Pt4* __restrict__ out) {
+  const int n = *n_ptr;
+  if (blockIdx.x * VCH >= n) return;
   __shared__ int s_w[VT / 32];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int base = blockIdx.x * VCH + tid * VIT;   // this thread owns VIT consecutive sorted slots
@@ -209,9 +219,238 @@ __global__ void __launch_bounds__(VT) k_vox_emit(const Pt4* __restrict__ pts, co
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Segmented, device-resident form: S independent clouds ("segments", each with its own leaf size) are filtered by ONE
+// sequence of launches -- the two scan stacks of a mapping frame (laserMapping.cpp:543-549), or all valid cubes of the map
+// after insertion (:787-801, up to 75 corner + 75 surf cubes).  Sizes live in device memory; nothing here synchronises
+// with the host.  Key = segment << idx_bits | voxel index (PCL's index inside the segment's own bounding box), so one
+// stable LSD radix sort orders every segment by voxel and keeps the segments apart; everything else is the single-cloud
+// algorithm above, per segment: same bounding-box rule, same float centroid accumulation in sorted order.
+// A segment whose index range overflows int (PCL: "leaf size is too small", input returned unchanged) or idx_bits keeps its
+// points as they are (key = position).
+
+__global__ void __launch_bounds__(256) k_seg_prep(SegFilter f) {
+  __shared__ int s_w[8];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int S = *f.n_seg;
+  const int n = t < S ? max(0, *f.seg[t].n_in) : 0;
+  int incl = n;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int v = 0; v < w; ++v) base += s_w[v];
+  if (t <= ALOAM_MAX_SEGS) f.off[t] = 0;
+  __syncthreads();
+  if (t < S) f.off[t] = base + incl - n;
+  if (t == S - 1 || (S == 0 && t == 0)) {
+    const int total = S == 0 ? 0 : base + incl;
+    for (int v = max(S, 0); v <= ALOAM_MAX_SEGS; ++v) f.off[v] = total;
+    *f.total = total;
+  }
+  if (t < ALOAM_MAX_SEGS) {
+    f.bbox[6 * t + 0] = INT_MAX; f.bbox[6 * t + 1] = INT_MAX; f.bbox[6 * t + 2] = INT_MAX;
+    f.bbox[6 * t + 3] = INT_MIN; f.bbox[6 * t + 4] = INT_MIN; f.bbox[6 * t + 5] = INT_MIN;
+  }
+}
+
+// grid (chunks, segments)
+__global__ void __launch_bounds__(256) k_seg_bbox(SegFilter f) {
+  const int sgm = blockIdx.y;
+  if (sgm >= *f.n_seg) return;
+  const SegDesc d = f.seg[sgm];
+  const int n = *d.n_in;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  bool any = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const Pt4 p = d.src[i];
+    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    any = true;
+  }
+  if (!__any_sync(0xffffffffu, any)) return;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], dd));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], dd));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&f.bbox[6 * sgm + a], f2ord(lo[a])); atomicMax(&f.bbox[6 * sgm + 3 + a], f2ord(hi[a])); }
+  }
+}
+
+// grid (chunks, segments): keys / vals in the compact order (segment after segment)
+__global__ void __launch_bounds__(256) k_seg_keys(SegFilter f, unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int sgm = blockIdx.y;
+  if (sgm >= *f.n_seg) return;
+  const SegDesc d = f.seg[sgm];
+  const int n = *d.n_in;
+  if (n <= 0) return;
+  const int off = f.off[sgm];
+  float mn[3], mx[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { mn[a] = ord2f(f.bbox[6 * sgm + a]); mx[a] = ord2f(f.bbox[6 * sgm + 3 + a]); }
+  const float inv = 1.0f / d.leaf;
+  long long dxyz[3]; int min_b[3], div_b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    dxyz[a] = (long long)((mx[a] - mn[a]) * inv) + 1;
+    min_b[a] = (int)floorf(mn[a] * inv);
+    div_b[a] = (int)floorf(mx[a] * inv) - min_b[a] + 1;
+  }
+  const unsigned long long cells = (unsigned long long)div_b[0] * (unsigned long long)div_b[1] * (unsigned long long)div_b[2];
+  const bool pass = dxyz[0] * dxyz[1] * dxyz[2] > (long long)INT_MAX || cells > (1ull << f.idx_bits);
+  if (pass && blockIdx.x == 0 && threadIdx.x == 0 && cells > (1ull << f.idx_bits) && !(dxyz[0] * dxyz[1] * dxyz[2] > (long long)INT_MAX)) atomicOr(f.err, 1);
+  const unsigned hi_bits = (unsigned)sgm << f.idx_bits;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned idx;
+    if (pass) idx = (unsigned)i;
+    else {
+      const Pt4 p = d.src[i];
+      const int i0 = (int)(floorf(p.x * inv) - (float)min_b[0]);
+      const int i1 = (int)(floorf(p.y * inv) - (float)min_b[1]);
+      const int i2 = (int)(floorf(p.z * inv) - (float)min_b[2]);
+      idx = (unsigned)(i0 + i1 * div_b[0] + i2 * div_b[0] * div_b[1]);
+    }
+    keys[off + i] = hi_bits | idx;
+    vals[off + i] = off + i;
+  }
+}
+
+// heads before the first sorted slot of every segment, and the filtered size of every segment (one warp per segment)
+__global__ void __launch_bounds__(1024) k_seg_rank0(SegFilter f, const unsigned* __restrict__ keys, const int* __restrict__ block_offsets) {
+  __shared__ int s_r[ALOAM_MAX_SEGS + 1];
+  const int S = *f.n_seg, total = *f.total;
+  const int lane = threadIdx.x & 31;
+  for (int sgm = threadIdx.x >> 5; sgm <= S; sgm += blockDim.x >> 5) {
+    const int pos = sgm == S ? total : f.off[sgm];
+    int r;
+    if (pos >= total) {
+      // all heads: block offset of the last block + its heads
+      const int lb = total > 0 ? (total - 1) / VCH : 0;
+      int cnt = 0;
+      for (int i = lb * VCH + lane; i < total; i += 32) cnt += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+#pragma unroll
+      for (int dd = 16; dd > 0; dd >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, dd);
+      r = total > 0 ? block_offsets[lb] + cnt : 0;
+    } else {
+      const int b = pos / VCH;
+      int cnt = 0;
+      for (int i = b * VCH + lane; i < pos; i += 32) cnt += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+#pragma unroll
+      for (int dd = 16; dd > 0; dd >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, dd);
+      r = block_offsets[b] + cnt;
+    }
+    if (lane == 0) s_r[sgm] = r;
+  }
+  __syncthreads();
+  for (int sgm = threadIdx.x; sgm <= S; sgm += blockDim.x) f.rank0[sgm] = s_r[sgm];
+  for (int sgm = threadIdx.x; sgm < S; sgm += blockDim.x) *f.seg[sgm].n_out = s_r[sgm + 1] - s_r[sgm];
+}
+
+// every head sums its run in sorted order (float, like pcl::CentroidPoint); output slot = off[segment] + rank inside the segment
+__global__ void __launch_bounds__(VT) k_seg_emit(SegFilter f, const unsigned* __restrict__ keys, const int* __restrict__ vals,
+                                                 const int* __restrict__ block_offsets, Pt4* __restrict__ tmp) {
+  const int n = *f.total;
+  if (blockIdx.x * VCH >= n) return;
+  __shared__ int s_w[VT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int base = blockIdx.x * VCH + tid * VIT;
+  int heads = 0;
+  bool is_head[VIT];
+#pragma unroll
+  for (int k = 0; k < VIT; ++k) {
+    const int i = base + k;
+    is_head[k] = i < n && (i == 0 || keys[i] != keys[i - 1]);
+    heads += is_head[k] ? 1 : 0;
+  }
+  int incl = heads;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int v = 0; v < w; ++v) wbase += s_w[v];
+  int rank = block_offsets[blockIdx.x] + wbase + incl - heads;
+#pragma unroll
+  for (int k = 0; k < VIT; ++k) {
+    if (!is_head[k]) continue;
+    const int i = base + k;
+    const unsigned key = keys[i];
+    const int sgm = (int)(key >> f.idx_bits);
+    const int off = f.off[sgm];
+    const Pt4* __restrict__ src = f.seg[sgm].src;
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int cnt = 0;
+    for (int j = i; j < n && keys[j] == key; ++j) {
+      const Pt4 p = src[vals[j] - off];
+      sx += p.x; sy += p.y; sz += p.z; si += p.i;
+      ++cnt;
+    }
+    const float nf = (float)cnt;
+    Pt4 o; o.x = sx / nf; o.y = sy / nf; o.z = sz / nf; o.i = si / nf;
+    tmp[off + (rank - f.rank0[sgm])] = o;
+    ++rank;
+  }
+}
+
+// grid (chunks, segments): filtered points back to their destination (which may be the source slab itself)
+__global__ void __launch_bounds__(256) k_seg_writeback(SegFilter f, const Pt4* __restrict__ tmp) {
+  const int sgm = blockIdx.y;
+  if (sgm >= *f.n_seg) return;
+  const SegDesc d = f.seg[sgm];
+  const int m = f.rank0[sgm + 1] - f.rank0[sgm];
+  const int off = f.off[sgm];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) d.dst[i] = tmp[off + i];
+}
+
 }  // namespace aloam
 
 using namespace aloam;
+
+// one segmented filter pass; S_upper / n_upper are host bounds for grid sizing (segments, total points), bits = idx_bits + segment bits
+void vox_seg_filter(aloam_ctx* c, const SegFilter& f, SegBuffers& b, int S_upper, int n_upper, int per_seg_upper) {
+  const int nblk = std::max(1, (n_upper + VCH - 1) / VCH);
+  const int chunks = std::max(1, std::min((per_seg_upper + 255) / 256, 64));
+  int seg_bits = 0; while ((1 << seg_bits) < std::max(S_upper, 1)) ++seg_bits;
+  const int bits = f.idx_bits + seg_bits;
+  LAUNCH(c, KID_VOXEL, k_seg_prep, 1, 256, 0, f);
+  LAUNCH(c, KID_VOXEL, k_seg_bbox, dim3(chunks, S_upper), 256, 0, f);
+  LAUNCH(c, KID_VOXEL, k_seg_keys, dim3(chunks, S_upper), 256, 0, f, b.keys[0], b.vals[0]);
+  int cur = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    LAUNCH(c, KID_VOXEL, k_radix_hist, nblk, VT, 0, b.keys[cur], f.total, shift, b.hist);
+    LAUNCH(c, KID_VOXEL, k_radix_scan, 1, 1024, 0, b.hist, f.total, b.offs);
+    LAUNCH(c, KID_VOXEL, k_radix_scatter, nblk, VT, 0, b.keys[cur], b.vals[cur], f.total, shift, b.offs, b.keys[cur ^ 1], b.vals[cur ^ 1]);
+    cur ^= 1;
+  }
+  LAUNCH(c, KID_VOXEL, k_vox_heads, nblk, VT, 0, b.keys[cur], f.total, b.block_heads);
+  LAUNCH(c, KID_VOXEL, k_vox_blockscan, 1, 1024, 0, b.block_heads, f.total, b.heads_total);
+  LAUNCH(c, KID_VOXEL, k_seg_rank0, 1, 1024, 0, f, b.keys[cur], b.block_heads);
+  LAUNCH(c, KID_VOXEL, k_seg_emit, nblk, VT, 0, f, b.keys[cur], b.vals[cur], b.block_heads, b.tmp);
+  LAUNCH(c, KID_VOXEL, k_seg_writeback, dim3(chunks, S_upper), 256, 0, f, b.tmp);
+}
+
+int vox_seg_alloc(SegBuffers& b, size_t cap) {
+  const size_t nb = (cap + VCH - 1) / VCH + 1;
+  b.cap = cap;
+  if (cudaMalloc((void**)&b.keys[0], cap * 4) != cudaSuccess || cudaMalloc((void**)&b.keys[1], cap * 4) != cudaSuccess ||
+      cudaMalloc((void**)&b.vals[0], cap * 4) != cudaSuccess || cudaMalloc((void**)&b.vals[1], cap * 4) != cudaSuccess ||
+      cudaMalloc((void**)&b.hist, nb * 256 * 4) != cudaSuccess || cudaMalloc((void**)&b.offs, nb * 256 * 4) != cudaSuccess ||
+      cudaMalloc((void**)&b.block_heads, nb * 4) != cudaSuccess || cudaMalloc((void**)&b.heads_total, 16) != cudaSuccess ||
+      cudaMalloc((void**)&b.tmp, cap * sizeof(Pt4)) != cudaSuccess)
+    return ALOAM_ERR_CUDA;
+  return ALOAM_OK;
+}
+void vox_seg_free(SegBuffers& b) {
+  void* ps[] = {b.keys[0], b.keys[1], b.vals[0], b.vals[1], b.hist, b.offs, b.block_heads, b.heads_total, b.tmp};
+  for (void* p : ps) if (p) cudaFree(p);
+  b = SegBuffers();
+}
+
 
 extern "C" int aloam_voxel_filter_impl(aloam_ctx* c, aloam_cloud_view in, float leaf, aloam_cloud_view* out) {
   if (!c || !out || !(leaf > 0.f)) return ALOAM_ERR_INVALID_ARG;
@@ -235,10 +474,12 @@ extern "C" int aloam_voxel_filter_impl(aloam_ctx* c, aloam_cloud_view in, float 
   Pt4* d_in = c->d_query;        // staging buffers that already exist in the context
   Pt4* d_out = c->lanes[0].d_full[0];
   rc = upload_cloud(c, in, d_in, c->max_points); if (rc) return rc;
-  int* mm6 = c->d_vox_misc; int* d_total = c->d_vox_misc + 8; int* block_heads = c->d_vox_misc + 64;
+  int* mm6 = c->d_vox_misc; int* d_total = c->d_vox_misc + 8; int* d_n = c->d_vox_misc + 9; int* block_heads = c->d_vox_misc + 64;
   const int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
   std::memcpy(c->h_ints + 32, init, sizeof(init));
+  c->h_ints[38] = n;
   CUDA_CHECK_RET(cudaMemcpyAsync(mm6, c->h_ints + 32, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(d_n, c->h_ints + 38, 4, cudaMemcpyHostToDevice, c->stream));
   LAUNCH(c, KID_VOXEL, k_vox_bbox, std::min((n + 255) / 256, 592), 256, 0, d_in, n, mm6);
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints + 40, mm6, 24, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
@@ -270,15 +511,15 @@ extern "C" int aloam_voxel_filter_impl(aloam_ctx* c, aloam_cloud_view in, float 
   int bits = 1; while (bits < 32 && (1ull << bits) < cells) ++bits;
   int cur = 0;
   for (int shift = 0; shift < bits; shift += 8) {
-    LAUNCH(c, KID_VOXEL, k_radix_hist, nblk, VT, 0, c->d_vox_keys[cur], n, shift, c->d_vox_hist);
-    LAUNCH(c, KID_VOXEL, k_radix_scan, 1, 1024, 0, c->d_vox_hist, nblk, c->d_vox_offs);
-    LAUNCH(c, KID_VOXEL, k_radix_scatter, nblk, VT, 0, c->d_vox_keys[cur], c->d_vox_vals[cur], n, shift, c->d_vox_offs, c->d_vox_keys[cur ^ 1],
+    LAUNCH(c, KID_VOXEL, k_radix_hist, nblk, VT, 0, c->d_vox_keys[cur], d_n, shift, c->d_vox_hist);
+    LAUNCH(c, KID_VOXEL, k_radix_scan, 1, 1024, 0, c->d_vox_hist, d_n, c->d_vox_offs);
+    LAUNCH(c, KID_VOXEL, k_radix_scatter, nblk, VT, 0, c->d_vox_keys[cur], c->d_vox_vals[cur], d_n, shift, c->d_vox_offs, c->d_vox_keys[cur ^ 1],
            c->d_vox_vals[cur ^ 1]);
     cur ^= 1;
   }
-  LAUNCH(c, KID_VOXEL, k_vox_heads, nblk, VT, 0, c->d_vox_keys[cur], n, block_heads);
-  LAUNCH(c, KID_VOXEL, k_vox_blockscan, 1, 1024, 0, block_heads, nblk, d_total);
-  LAUNCH(c, KID_VOXEL, k_vox_emit, nblk, VT, 0, d_in, c->d_vox_keys[cur], c->d_vox_vals[cur], n, block_heads, d_out);
+  LAUNCH(c, KID_VOXEL, k_vox_heads, nblk, VT, 0, c->d_vox_keys[cur], d_n, block_heads);
+  LAUNCH(c, KID_VOXEL, k_vox_blockscan, 1, 1024, 0, block_heads, d_n, d_total);
+  LAUNCH(c, KID_VOXEL, k_vox_emit, nblk, VT, 0, d_in, c->d_vox_keys[cur], c->d_vox_vals[cur], d_n, block_heads, d_out);
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints + 48, d_total, 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
   CUDA_CHECK_RET(cudaGetLastError());

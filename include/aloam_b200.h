@@ -46,6 +46,7 @@ extern "C" {
 #define ALOAM_FLAG_FEW_CORRESPONDENCES 1
 #define ALOAM_FLAG_MAP_TOO_THIN 2
 #define ALOAM_FLAG_INITIALISED_ONLY 4 /* first frame: laserOdometry.cpp:267-271 */
+#define ALOAM_FLAG_CUBE_OVERFLOW 8    /* map cube store: a cube slab (16 k corner / 64 k surf points) or the slab pool was full; the overflow was dropped */
 
 typedef struct aloam_ctx aloam_ctx;
 
@@ -143,6 +144,14 @@ int aloam_scan_stream(aloam_ctx* ctx, const aloam_cloud_view* raws, int n_scans,
  * counter (the first scan of a fresh / reset context only initialises, laserOdometry.cpp:267-271). */
 int aloam_scan_stream_batch(aloam_ctx* ctx, const aloam_cloud_view* raws, int n_scans, int batch, int device_resident,
                             double* poses, aloam_stats* stats_last);
+/* the whole pipeline of the three reference nodes in one call: as aloam_scan_stream, and every scan's
+ * less-sharp / less-flat clouds and odometry pose are handed ON THE DEVICE to the scan-to-map stage (one aloam_mapper_step
+ * per scan, on its own stream, overlapping the odometry of the following scans) -- what the reference ships over
+ * /laser_cloud_corner_last, /laser_cloud_surf_last and /laser_odom_to_init (laserOdometry.cpp:570-591 ->
+ * laserMapping.cpp:278-288, 142-152).  odom_poses / map_poses: n_scans x 7 doubles (q xyzw, t): laser_odom_to_init and
+ * aft_mapped_to_init.  Identical to calling aloam_scan_to_pose + aloam_mapper_step per scan.  Needs cfg.max_map_points > 0. */
+int aloam_scan_stream_mapped(aloam_ctx* ctx, const aloam_cloud_view* raws, int n_scans, int device_resident, double* odom_poses,
+                             double* map_poses, aloam_stats* stats_last);
 int aloam_reset_odometry(aloam_ctx* ctx); /* forget pose, warm start and "last" clouds (all trajectories) */
 
 /* TransformToEnd of laserOdometry.cpp:133-148 on a whole cloud: undistort every point to the sweep start with its own
@@ -179,14 +188,17 @@ int aloam_mapping_associate(aloam_ctx* ctx, aloam_cloud_view corner_stack, aloam
                             const double x[7], double* fits);
 
 /* ---- map cube store + the mapping loop around it (laserMapping.cpp:74-108,142-163,309-550,736-801).
- * The 21 x 21 x 11 ring buffer of 50 m cubes lives in device memory (fixed-capacity slabs, created on first use: 6.4 GB).
- * aloam_mapper_step is one frame of alaserMapping's process(): pose hand-off from the odometry (transformAssociateToMap),
- * ring-buffer shift, gather of the <= 75 valid cubes (device to device), stack filters at line_res / plane_res,
- * optimisation against the gathered submap (skipped while it is thinner than 10 corner / 50 surf points), transformUpdate,
- * insertion of the registered stacks and per-cube VoxelGrid of the valid cubes.  corner_last / surf_last are the
- * less-sharp / less-flat clouds of the scan (what /laser_cloud_corner_last and /laser_cloud_surf_last carry); the
- * odometry pose is q_wodom_curr / t_wodom_curr; the refined pose is returned.  ALOAM_ERR_CAPACITY: a cube holds more
- * than 16 k corner / 64 k surf points, or the submap exceeds cfg.max_map_points. */
+ * The 21 x 21 x 11 ring buffer of 50 m cubes lives in device memory: a pool of fixed-capacity slabs (1024 per cloud type,
+ * 16 k corner / 64 k surf points each, 1.3 GB, created on first use) handed to cubes on their first insertion.
+ * aloam_mapper_step is one frame of alaserMapping's process(), entirely on the device with one synchronisation at the end:
+ * pose hand-off from the odometry (transformAssociateToMap), ring-buffer shift, gather of the <= 75 valid cubes (device
+ * to device), stack filters at line_res / plane_res, optimisation against the gathered submap (skipped while it is thinner
+ * than 10 corner / 50 surf points), transformUpdate, insertion of the registered stacks and per-cube VoxelGrid of the valid
+ * cubes.  corner_last / surf_last are the less-sharp / less-flat clouds of the scan (what /laser_cloud_corner_last and
+ * /laser_cloud_surf_last carry); the odometry pose is q_wodom_curr / t_wodom_curr; the refined pose is returned.
+ * The call never fails half-way: a full cube slab, an exhausted pool or a submap beyond cfg.max_map_points drop the
+ * overflow and set ALOAM_FLAG_CUBE_OVERFLOW in stats->flags; argument errors are reported before any state changes.
+ * cfg.max_map_points must be > 0. */
 int aloam_mapper_reset(aloam_ctx* ctx);
 int aloam_mapper_step(aloam_ctx* ctx, aloam_cloud_view corner_last, aloam_cloud_view surf_last,
                       const double q_wodom_curr[4], const double t_wodom_curr[3], double q_w_curr[4], double t_w_curr[3],
