@@ -286,10 +286,11 @@ __global__ void __launch_bounds__(1024) k_cube_insert(const Pt4* __restrict__ wo
         int start = 0, slab = -1;
         if (mine >= 0 && lane == leader) {
           slab = slab_of[mine];
-          if (slab < 0) {   // first point of an empty cube: take a slab from the pool
+          if (slab < 0) {   // first point of an empty cube: take a slab from the pool (several group leaders of one warp may do so at once)
             int* top = ty == 0 ? &S->free_top : &S->free_top2;
-            if (*top < kPool) { slab = S->free_list[ty][*top]; *top = *top + 1; slab_of[mine] = slab; cnt[slab] = 0; }
-            else atomicOr(&S->err, 4);
+            const int idx = atomicAdd(top, 1);
+            if (idx < kPool) { slab = S->free_list[ty][idx]; slab_of[mine] = slab; cnt[slab] = 0; }
+            else { atomicSub(top, 1); atomicOr(&S->err, 4); }
           }
           start = s_end[mine];
           s_end[mine] = start + __popc(grp);
@@ -360,7 +361,7 @@ int ensure_mapper(aloam_ctx* c) {
 SegFilter make_filter(Mapper* m, int idx_bits) {
   SegFilter f;
   f.seg = m->d_segs; f.n_seg = m->d_nseg; f.off = m->d_off; f.rank0 = m->d_rank0; f.bbox = m->d_bbox; f.total = m->d_total;
-  f.err = &m->d_state->err; f.idx_bits = idx_bits;
+  f.err = &m->d_state->err; f.idx_bits = idx_bits; f.seg0 = 0; f.seg_cap = ALOAM_MAX_SEGS;
   return f;
 }
 
@@ -399,7 +400,7 @@ int mapper_step_device(aloam_ctx* c, const Pt4* d_corner_last, const int* d_nc, 
   // ---- stack filters (:541-550): one segmented pass for both clouds
   LAUNCH(c, KID_VOXEL, k_seg_two, 1, 32, 0, m->d_segs, m->d_nseg, d_corner_last, d_nc, c->cfg.line_res, c->d_stack_corner, &S->stack_counts[0], d_surf_last, d_ns,
          c->cfg.plane_res, c->d_stack_surf, &S->stack_counts[1]);
-  vox_seg_filter(c, make_filter(m, 30), m->buf, 2, n_upper_c + n_upper_s, std::max(n_upper_c, n_upper_s));
+  vox_seg_filter(c, make_filter(m, 31), m->buf, 2, n_upper_c + n_upper_s, std::max(n_upper_c, n_upper_s));
   LAUNCH(c, KID_CUBES, k_mapper_prep, 1, 32, 0, S);
   // ---- optimisation (:554-733)
   const int nq_upper = std::min(n_upper_c + n_upper_s, 2 * c->max_points);
@@ -414,7 +415,11 @@ int mapper_step_device(aloam_ctx* c, const Pt4* d_corner_last, const int* d_nc, 
   }
   // ---- per-cube re-filter of the valid cubes (:770-801): one segmented pass over <= 150 cubes, in place
   LAUNCH(c, KID_CUBES, k_seg_cubes, 1, 256, 0, S, m->d_segs, m->d_nseg, m->d_pts[0], m->d_pts[1], m->cap[0], m->cap[1], c->cfg.line_res, c->cfg.plane_res);
-  vox_seg_filter(c, make_filter(m, 21), m->buf, 2 * 75, (int)std::min(m->buf.cap, (size_t)2 * m->max_sub + (size_t)2 * c->max_points), m->cap[1]);
+  // index bits of a 50 m cube at the finer leaf: (50 / leaf + 3)^3 voxels at most (PCL itself gives up beyond 2^31)
+  int cube_bits = 1;
+  { const double side = std::floor(50.0 / std::min(c->cfg.line_res, c->cfg.plane_res)) + 3.0; const double cells = side * side * side;
+    while (cube_bits < 31 && (double)(1ull << cube_bits) < cells) ++cube_bits; }
+  vox_seg_filter(c, make_filter(m, cube_bits), m->buf, 2 * 75, (int)std::min(m->buf.cap, (size_t)2 * m->max_sub + (size_t)2 * c->max_points), m->cap[1]);
   CUDA_CHECK_RET(cudaGetLastError());
   return ALOAM_OK;
 }

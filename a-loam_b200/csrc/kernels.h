@@ -118,6 +118,7 @@ struct SegFilter {
   int* total;           // points over all segments
   int* err;             // sticky error word (bit 0: a segment needs more than idx_bits index bits)
   int idx_bits;         // bits of the voxel index inside a segment
+  int seg0, seg_cap;    // this pass handles segments seg0 .. seg0 + seg_cap - 1 (as many as fit beside idx_bits in a 32-bit key)
 };
 struct SegBuffers { unsigned* keys[2] = {nullptr, nullptr}; int* vals[2] = {nullptr, nullptr}; int *hist = nullptr, *offs = nullptr, *block_heads = nullptr, *heads_total = nullptr;
                     Pt4* tmp = nullptr; size_t cap = 0; };

@@ -230,11 +230,13 @@ __global__ void __launch_bounds__(VT) k_vox_emit(const Pt4* __restrict__ pts, co
 // A segment whose index range overflows int (PCL: "leaf size is too small", input returned unchanged) or idx_bits keeps its
 // points as they are (key = position).
 
+__device__ __forceinline__ int seg_count(const SegFilter& f) { return min(max(*f.n_seg - f.seg0, 0), f.seg_cap); }
+
 __global__ void __launch_bounds__(256) k_seg_prep(SegFilter f) {
   __shared__ int s_w[8];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int S = *f.n_seg;
-  const int n = t < S ? max(0, *f.seg[t].n_in) : 0;
+  const int S = seg_count(f);
+  const int n = t < S ? max(0, *f.seg[f.seg0 + t].n_in) : 0;
   int incl = n;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
@@ -259,8 +261,8 @@ __global__ void __launch_bounds__(256) k_seg_prep(SegFilter f) {
 // grid (chunks, segments)
 __global__ void __launch_bounds__(256) k_seg_bbox(SegFilter f) {
   const int sgm = blockIdx.y;
-  if (sgm >= *f.n_seg) return;
-  const SegDesc d = f.seg[sgm];
+  if (sgm >= seg_count(f)) return;
+  const SegDesc d = f.seg[f.seg0 + sgm];
   const int n = *d.n_in;
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   bool any = false;
@@ -285,8 +287,8 @@ __global__ void __launch_bounds__(256) k_seg_bbox(SegFilter f) {
 // grid (chunks, segments): keys / vals in the compact order (segment after segment)
 __global__ void __launch_bounds__(256) k_seg_keys(SegFilter f, unsigned* __restrict__ keys, int* __restrict__ vals) {
   const int sgm = blockIdx.y;
-  if (sgm >= *f.n_seg) return;
-  const SegDesc d = f.seg[sgm];
+  if (sgm >= seg_count(f)) return;
+  const SegDesc d = f.seg[f.seg0 + sgm];
   const int n = *d.n_in;
   if (n <= 0) return;
   const int off = f.off[sgm];
@@ -302,8 +304,10 @@ __global__ void __launch_bounds__(256) k_seg_keys(SegFilter f, unsigned* __restr
     div_b[a] = (int)floorf(mx[a] * inv) - min_b[a] + 1;
   }
   const unsigned long long cells = (unsigned long long)div_b[0] * (unsigned long long)div_b[1] * (unsigned long long)div_b[2];
-  const bool pass = dxyz[0] * dxyz[1] * dxyz[2] > (long long)INT_MAX || cells > (1ull << f.idx_bits);
-  if (pass && blockIdx.x == 0 && threadIdx.x == 0 && cells > (1ull << f.idx_bits) && !(dxyz[0] * dxyz[1] * dxyz[2] > (long long)INT_MAX)) atomicOr(f.err, 1);
+  const bool pcl_overflow = dxyz[0] * dxyz[1] * dxyz[2] > (long long)INT_MAX;   // PCL: "leaf size is too small", input returned unchanged
+  const bool key_overflow = !pcl_overflow && cells > (1ull << f.idx_bits);       // cannot be encoded: flagged, points kept as they are
+  const bool pass = pcl_overflow || key_overflow;
+  if (key_overflow && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(f.err, 1);
   const unsigned hi_bits = (unsigned)sgm << f.idx_bits;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     unsigned idx;
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(256) k_seg_keys(SegFilter f, unsigned* __restr
 // heads before the first sorted slot of every segment, and the filtered size of every segment (one warp per segment)
 __global__ void __launch_bounds__(1024) k_seg_rank0(SegFilter f, const unsigned* __restrict__ keys, const int* __restrict__ block_offsets) {
   __shared__ int s_r[ALOAM_MAX_SEGS + 1];
-  const int S = *f.n_seg, total = *f.total;
+  const int S = seg_count(f), total = *f.total;
   const int lane = threadIdx.x & 31;
   for (int sgm = threadIdx.x >> 5; sgm <= S; sgm += blockDim.x >> 5) {
     const int pos = sgm == S ? total : f.off[sgm];
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(1024) k_seg_rank0(SegFilter f, const unsigned*
   }
   __syncthreads();
   for (int sgm = threadIdx.x; sgm <= S; sgm += blockDim.x) f.rank0[sgm] = s_r[sgm];
-  for (int sgm = threadIdx.x; sgm < S; sgm += blockDim.x) *f.seg[sgm].n_out = s_r[sgm + 1] - s_r[sgm];
+  for (int sgm = threadIdx.x; sgm < S; sgm += blockDim.x) *f.seg[f.seg0 + sgm].n_out = s_r[sgm + 1] - s_r[sgm];
 }
 
 // every head sums its run in sorted order (float, like pcl::CentroidPoint); output slot = off[segment] + rank inside the segment
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(VT) k_seg_emit(SegFilter f, const unsigned* __
     const unsigned key = keys[i];
     const int sgm = (int)(key >> f.idx_bits);
     const int off = f.off[sgm];
-    const Pt4* __restrict__ src = f.seg[sgm].src;
+    const Pt4* __restrict__ src = f.seg[f.seg0 + sgm].src;
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
     int cnt = 0;
     for (int j = i; j < n && keys[j] == key; ++j) {
@@ -400,8 +404,8 @@ __global__ void __launch_bounds__(VT) k_seg_emit(SegFilter f, const unsigned* __
 // grid (chunks, segments): filtered points back to their destination (which may be the source slab itself)
 __global__ void __launch_bounds__(256) k_seg_writeback(SegFilter f, const Pt4* __restrict__ tmp) {
   const int sgm = blockIdx.y;
-  if (sgm >= *f.n_seg) return;
-  const SegDesc d = f.seg[sgm];
+  if (sgm >= seg_count(f)) return;
+  const SegDesc d = f.seg[f.seg0 + sgm];
   const int m = f.rank0[sgm + 1] - f.rank0[sgm];
   const int off = f.off[sgm];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) d.dst[i] = tmp[off + i];
@@ -411,27 +415,34 @@ __global__ void __launch_bounds__(256) k_seg_writeback(SegFilter f, const Pt4* _
 
 using namespace aloam;
 
-// one segmented filter pass; S_upper / n_upper are host bounds for grid sizing (segments, total points), bits = idx_bits + segment bits
-void vox_seg_filter(aloam_ctx* c, const SegFilter& f, SegBuffers& b, int S_upper, int n_upper, int per_seg_upper) {
+// segmented filter over up to S_upper segments; n_upper / per_seg_upper are host bounds for grid sizing (total points, points of
+// one segment).  A 32-bit key holds f.idx_bits index bits and the segment number: when S_upper segments do not fit beside the
+// index, the segments are processed in windows of 2^(32 - idx_bits).
+void vox_seg_filter(aloam_ctx* c, const SegFilter& f_in, SegBuffers& b, int S_upper, int n_upper, int per_seg_upper) {
   const int nblk = std::max(1, (n_upper + VCH - 1) / VCH);
   const int chunks = std::max(1, std::min((per_seg_upper + 255) / 256, 64));
-  int seg_bits = 0; while ((1 << seg_bits) < std::max(S_upper, 1)) ++seg_bits;
-  const int bits = f.idx_bits + seg_bits;
-  LAUNCH(c, KID_VOXEL, k_seg_prep, 1, 256, 0, f);
-  LAUNCH(c, KID_VOXEL, k_seg_bbox, dim3(chunks, S_upper), 256, 0, f);
-  LAUNCH(c, KID_VOXEL, k_seg_keys, dim3(chunks, S_upper), 256, 0, f, b.keys[0], b.vals[0]);
-  int cur = 0;
-  for (int shift = 0; shift < bits; shift += 8) {
-    LAUNCH(c, KID_VOXEL, k_radix_hist, nblk, VT, 0, b.keys[cur], f.total, shift, b.hist);
-    LAUNCH(c, KID_VOXEL, k_radix_scan, 1, 1024, 0, b.hist, f.total, b.offs);
-    LAUNCH(c, KID_VOXEL, k_radix_scatter, nblk, VT, 0, b.keys[cur], b.vals[cur], f.total, shift, b.offs, b.keys[cur ^ 1], b.vals[cur ^ 1]);
-    cur ^= 1;
+  const int win = (int)std::min<long long>(1ll << std::max(0, 32 - f_in.idx_bits), ALOAM_MAX_SEGS);
+  for (int s0 = 0; s0 < S_upper; s0 += win) {
+    SegFilter f = f_in;
+    f.seg0 = s0; f.seg_cap = std::min(win, S_upper - s0);
+    int seg_bits = 0; while ((1 << seg_bits) < f.seg_cap) ++seg_bits;
+    const int bits = f.idx_bits + seg_bits;
+    LAUNCH(c, KID_VOXEL, k_seg_prep, 1, 256, 0, f);
+    LAUNCH(c, KID_VOXEL, k_seg_bbox, dim3(chunks, f.seg_cap), 256, 0, f);
+    LAUNCH(c, KID_VOXEL, k_seg_keys, dim3(chunks, f.seg_cap), 256, 0, f, b.keys[0], b.vals[0]);
+    int cur = 0;
+    for (int shift = 0; shift < bits; shift += 8) {
+      LAUNCH(c, KID_VOXEL, k_radix_hist, nblk, VT, 0, b.keys[cur], f.total, shift, b.hist);
+      LAUNCH(c, KID_VOXEL, k_radix_scan, 1, 1024, 0, b.hist, f.total, b.offs);
+      LAUNCH(c, KID_VOXEL, k_radix_scatter, nblk, VT, 0, b.keys[cur], b.vals[cur], f.total, shift, b.offs, b.keys[cur ^ 1], b.vals[cur ^ 1]);
+      cur ^= 1;
+    }
+    LAUNCH(c, KID_VOXEL, k_vox_heads, nblk, VT, 0, b.keys[cur], f.total, b.block_heads);
+    LAUNCH(c, KID_VOXEL, k_vox_blockscan, 1, 1024, 0, b.block_heads, f.total, b.heads_total);
+    LAUNCH(c, KID_VOXEL, k_seg_rank0, 1, 1024, 0, f, b.keys[cur], b.block_heads);
+    LAUNCH(c, KID_VOXEL, k_seg_emit, nblk, VT, 0, f, b.keys[cur], b.vals[cur], b.block_heads, b.tmp);
+    LAUNCH(c, KID_VOXEL, k_seg_writeback, dim3(chunks, f.seg_cap), 256, 0, f, b.tmp);
   }
-  LAUNCH(c, KID_VOXEL, k_vox_heads, nblk, VT, 0, b.keys[cur], f.total, b.block_heads);
-  LAUNCH(c, KID_VOXEL, k_vox_blockscan, 1, 1024, 0, b.block_heads, f.total, b.heads_total);
-  LAUNCH(c, KID_VOXEL, k_seg_rank0, 1, 1024, 0, f, b.keys[cur], b.block_heads);
-  LAUNCH(c, KID_VOXEL, k_seg_emit, nblk, VT, 0, f, b.keys[cur], b.vals[cur], b.block_heads, b.tmp);
-  LAUNCH(c, KID_VOXEL, k_seg_writeback, dim3(chunks, S_upper), 256, 0, f, b.tmp);
 }
 
 int vox_seg_alloc(SegBuffers& b, size_t cap) {

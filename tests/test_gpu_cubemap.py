@@ -62,4 +62,71 @@ def test_mapping_loop_over_a_trajectory(aloam, orc, synth, scans):
         # the poses agree to ~1e-8, so a transformed point can land on the other side of a voxel boundary: sizes may
         # differ by a handful of points, not more
         assert abs(sg["total_corner"] - so["total_corner"]) <= 5 and abs(sg["total_surf"] - so["total_surf"]) <= 20
+        # cube CONTENTS after the optimisation: same voxels in the same order, centroids equal to float rounding of a 1e-8 pose
+        # difference (a cube whose size differs had a point cross a voxel / cube boundary and is skipped)
+        same = differ = 0
+        for idx in so["valid"]:
+            for which in (0, 1):
+                a, b = c.mapper_cube(which, idx), cm.cube(which, idx)
+                if a.shape != b.shape:
+                    differ += 1
+                    continue
+                same += 1
+                if len(a):
+                    assert np.abs(a[:, :3] - b[:, :3]).max() < 2e-5 and np.abs(a[:, 3] - b[:, 3]).max() < 1e-4, (k, idx, which)
+        assert same >= 1 and differ <= 4
+    c.close()
+
+
+def test_stream_with_mapping_equals_per_scan_calls_and_oracle(aloam, orc, synth, scans):
+    """aloam_scan_stream_mapped (odometry -> scan-to-map hand-off on the device) == aloam_scan_to_pose +
+    aloam_mapper_step per scan, and both follow the oracle's ascanRegistration | alaserOdometry | alaserMapping chain"""
+    import torch
+    ns, _, mr = synth.SENSORS["VLP-16"][:3]
+    raws = [scans("VLP-16", k, n_az=900) for k in range(6)]
+    maxn = max(r.shape[0] for r in raws)
+    c = aloam.Aloam(n_scans=16, max_points=maxn + 1024, max_map_points=400000)
+    dev = [torch.from_numpy(r).cuda() for r in raws]
+    # split in two calls: the mapper state carries over
+    o1, m1 = c.scan_stream_mapped([d.data_ptr() for d in dev[:4]], [r.shape[0] for r in raws[:4]], True)
+    o2, m2 = c.scan_stream_mapped([r.ctypes.data for r in raws[4:]], [r.shape[0] for r in raws[4:]], False)
+    odom, mapped = np.concatenate([o1, o2]), np.concatenate([m1, m2])
+    c.close()
+    # per-scan calls
+    c2 = aloam.Aloam(n_scans=16, max_points=maxn + 1024, max_map_points=400000)
+    c2.mapper_reset()
+    cm = orc.CubeMap()
+    od = orc.Odometry()
+    q = np.array([0, 0, 0, 1.0]); t = np.zeros(3); qw = q.copy(); tw = t.copy()
+    for k, raw in enumerate(raws):
+        gq, gt, _ = c2.scan_to_pose(raw)
+        assert np.array_equal(np.concatenate([gq, gt]), odom[k])
+        f = c2.extract_features(raw)
+        mq, mt, _ = c2.mapper_step(f["less_sharp"], f["less_flat"], gq, gt)
+        assert np.array_equal(np.concatenate([mq, mt]), mapped[k]), k
+        fo = orc.Features(raw, ns, mr)
+        if k > 0:
+            q, t, _ = od.register(fo.sharp, fo.flat, q, t)
+            qw, tw = orc.integrate_pose(qw, tw, q, t)
+        od.set_last(fo.less_sharp, fo.less_flat)
+        pose, info = cm.step(fo.less_sharp, fo.less_flat, qw, tw, 0.2, 0.4)
+        assert np.abs(mapped[k, 4:] - pose[4:]).max() < 1e-4 and rot_angle(mapped[k, :4], pose[:4]) < 1e-4
+    c2.close()
+
+
+def test_slab_overflow_is_flagged_not_fatal(aloam):
+    """a cube that receives more points than a slab holds keeps running: the overflow is dropped and flagged (the
+    reference's cubes grow without bound between re-filters)"""
+    rng = np.random.default_rng(3)
+    c = aloam.Aloam(n_scans=16, max_points=3000, max_map_points=20000, line_res=0.01, plane_res=0.01)   # slab capacity = 3000
+    c.mapper_reset()
+    ident = np.array([0, 0, 0, 1.0])
+    flags = 0
+    for k in range(3):
+        corner = (rng.uniform(-10, 10, size=(5, 4))).astype(np.float32)
+        surf = (rng.uniform(-20, 20, size=(2500, 4)) * [1, 1, 0.2, 0]).astype(np.float32)     # all inside the centre cube
+        q, t, st = c.mapper_step(corner, surf, ident, np.zeros(3))
+        flags |= st["flags"]
+    assert flags & aloam.FLAG_CUBE_OVERFLOW
+    assert c.mapper_state()["total_surf"] == 3000
     c.close()
