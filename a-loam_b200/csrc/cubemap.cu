@@ -132,6 +132,8 @@ __device__ void rotate_line(MapperState* S, int axis, bool towards_high, int u, 
 
 // transformAssociateToMap (:142-146), centre cube + shift (:314-509), valid cubes (:511-529), gather offsets
 __global__ void __launch_bounds__(1024) k_mapper_begin(MapperState* S, const double* __restrict__ odom7, int max_sub) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   __shared__ int s_ctr[3], s_cen[3];
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -170,32 +172,45 @@ __global__ void __launch_bounds__(1024) k_mapper_begin(MapperState* S, const dou
       __syncthreads();
     }
   }
+  __shared__ int s_valid[kMaxValid], s_n[2][kMaxValid], s_nv;
   if (tid == 0) {
     for (int a = 0; a < 3; ++a) { S->cen[a] = s_cen[a]; S->ctr[a] = s_ctr[a]; }
     int nv = 0;
     for (int i = s_ctr[0] - 2; i <= s_ctr[0] + 2; ++i)
       for (int j = s_ctr[1] - 2; j <= s_ctr[1] + 2; ++j)
         for (int k = s_ctr[2] - 1; k <= s_ctr[2] + 1; ++k)
-          if (i >= 0 && i < CW && j >= 0 && j < CH && k >= 0 && k < CD) S->valid[nv++] = cube_index(i, j, k);
+          if (i >= 0 && i < CW && j >= 0 && j < CH && k >= 0 && k < CD) s_valid[nv++] = cube_index(i, j, k);
+    s_nv = nv;
     S->n_valid = nv;
-    for (int ty = 0; ty < 2; ++ty) {
-      int off = 0;
-      for (int v = 0; v < nv; ++v) {
-        S->sub_off[ty][v] = off;
-        const int s = S->slab_of[ty][S->valid[v]];
-        int n = s < 0 ? 0 : S->cnt[ty][s];
-        if (off + n > max_sub) { n = max_sub - off; S->err |= 8; }   // submap capacity: truncated, flagged
-        off += n;
-      }
-      S->sub_off[ty][nv] = off;
-      S->n_sub[ty] = off;
+  }
+  __syncthreads();
+  const int nv = s_nv;
+  if (tid < 2 * nv) {   // the counts of the valid cubes, all loads in flight at once
+    const int ty = tid >= nv, v = ty ? tid - nv : tid;
+    const int s = S->slab_of[ty][s_valid[v]];
+    s_n[ty][v] = s < 0 ? 0 : S->cnt[ty][s];
+    if (ty == 0) S->valid[v] = s_valid[v];
+  }
+  __syncthreads();
+  if (tid < 2) {
+    const int ty = tid;
+    int off = 0;
+    for (int v = 0; v < nv; ++v) {
+      S->sub_off[ty][v] = off;
+      int n = s_n[ty][v];
+      if (off + n > max_sub) { n = max_sub - off; atomicOr(&S->err, 8); }   // submap capacity: truncated, flagged
+      off += n;
     }
+    S->sub_off[ty][nv] = off;
+    S->n_sub[ty] = off;
   }
 }
 
 // grid (valid cubes, 2 types): slab -> submap (:531-539), device to device
 __global__ void __launch_bounds__(256) k_mapper_gather(const MapperState* __restrict__ S, const Pt4* __restrict__ p0, const Pt4* __restrict__ p1,
                                                        int cap0, int cap1, Pt4* __restrict__ sub0, Pt4* __restrict__ sub1) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const int v = blockIdx.x, ty = blockIdx.y;
   if (v >= S->n_valid) return;
   const int s = S->slab_of[ty][S->valid[v]];
@@ -209,6 +224,8 @@ __global__ void __launch_bounds__(256) k_mapper_gather(const MapperState* __rest
 // segment descriptors of the two scan-stack filters (:543-549)
 __global__ void k_seg_two(SegDesc* segs, int* n_seg, const Pt4* c_in, const int* nc, float c_leaf, Pt4* c_out, int* nc_out, const Pt4* s_in, const int* ns,
                           float s_leaf, Pt4* s_out, int* ns_out) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     segs[0] = SegDesc{c_in, nc, c_leaf, c_out, nc_out};
     segs[1] = SegDesc{s_in, ns, s_leaf, s_out, ns_out};
@@ -218,6 +235,8 @@ __global__ void k_seg_two(SegDesc* segs, int* n_seg, const Pt4* c_in, const int*
 
 // after the stack filters: the map-too-thin test of :554 (on the gathered submap) -> number of queries the registration sees
 __global__ void k_mapper_prep(MapperState* S) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   if (threadIdx.x || blockIdx.x) return;
   const int total = S->stack_counts[0] + S->stack_counts[1];
   S->stack_counts[3] = total;
@@ -228,6 +247,8 @@ __global__ void k_mapper_prep(MapperState* S) {
 
 // transformUpdate (:148-152) ; refined pose out
 __global__ void k_mapper_update(MapperState* S, double* __restrict__ out7) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   if (threadIdx.x || blockIdx.x) return;
   const Qd qw{S->x[0], S->x[1], S->x[2], S->x[3]};
   const Qd qo{S->q_wodom[0], S->q_wodom[1], S->q_wodom[2], S->q_wodom[3]};
@@ -243,6 +264,8 @@ __global__ void k_mapper_update(MapperState* S, double* __restrict__ out7) {
 // pointAssociateToMap (:154-163) in double, stored as float, then the cube of the stored point (:741-758)
 __global__ void k_cube_ids(const Pt4* __restrict__ stack, const int* __restrict__ n_ptr, const MapperState* __restrict__ S, Pt4* __restrict__ world,
                            int* __restrict__ cube) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const int n = *n_ptr;
   const double ux = S->x[0], uy = S->x[1], uz = S->x[2], w = S->x[3], tx = S->x[4], ty = S->x[5], tz = S->x[6];
   const int c0 = S->cen[0], c1 = S->cen[1], c2 = S->cen[2];
@@ -268,16 +291,20 @@ __global__ void k_cube_ids(const Pt4* __restrict__ stack, const int* __restrict_
 // advances the cube's running end in shared memory -- and takes a slab from the free list when the cube had none.
 __global__ void __launch_bounds__(1024) k_cube_insert(const Pt4* __restrict__ world, const int* __restrict__ cube, const int* __restrict__ n_ptr,
                                                       MapperState* S, int ty, Pt4* __restrict__ pts, int cap) {
-  __shared__ int s_end[NCUBE];
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
+  __shared__ int s_end[NCUBE];    // running end of every cube
+  __shared__ int s_slab[NCUBE];   // cube -> slab (the warps' turns must not wait on global memory)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = *n_ptr;
   int* slab_of = S->slab_of[ty];
   int* cnt = S->cnt[ty];
-  for (int c = tid; c < NCUBE; c += blockDim.x) { const int s = slab_of[c]; s_end[c] = s < 0 ? 0 : cnt[s]; }
+  for (int c = tid; c < NCUBE; c += blockDim.x) { const int s = slab_of[c]; s_slab[c] = s; s_end[c] = s < 0 ? 0 : cnt[s]; }
   __syncthreads();
   for (int base = 0; base < n; base += 1024) {
     const int i = base + tid;
     const int mine = i < n ? cube[i] : -1;
+    const Pt4 p = i < n ? world[i] : Pt4{0.f, 0.f, 0.f, 0.f};
     const int warps = min(32, (n - base + 31) / 32);
     for (int w = 0; w < warps; ++w) {
       if (warp == w) {
@@ -285,11 +312,11 @@ __global__ void __launch_bounds__(1024) k_cube_insert(const Pt4* __restrict__ wo
         const int leader = __ffs(grp) - 1;
         int start = 0, slab = -1;
         if (mine >= 0 && lane == leader) {
-          slab = slab_of[mine];
+          slab = s_slab[mine];
           if (slab < 0) {   // first point of an empty cube: take a slab from the pool (several group leaders of one warp may do so at once)
             int* top = ty == 0 ? &S->free_top : &S->free_top2;
             const int idx = atomicAdd(top, 1);
-            if (idx < kPool) { slab = S->free_list[ty][idx]; slab_of[mine] = slab; cnt[slab] = 0; }
+            if (idx < kPool) { slab = S->free_list[ty][idx]; s_slab[mine] = slab; }
             else { atomicSub(top, 1); atomicOr(&S->err, 4); }
           }
           start = s_end[mine];
@@ -299,18 +326,20 @@ __global__ void __launch_bounds__(1024) k_cube_insert(const Pt4* __restrict__ wo
         slab = __shfl_sync(0xffffffffu, slab, leader);
         if (mine >= 0 && slab >= 0) {
           const int pos = start + __popc(grp & ((1u << lane) - 1u));
-          if (pos < cap) pts[(size_t)slab * cap + pos] = world[i];
+          if (pos < cap) pts[(size_t)slab * cap + pos] = p;
           else atomicOr(&S->err, 2);   // slab full: the overflow is dropped (flagged), the frame goes on
         }
       }
       __syncthreads();
     }
   }
-  for (int c = tid; c < NCUBE; c += blockDim.x) { const int s = slab_of[c]; if (s >= 0) cnt[s] = min(s_end[c], cap); }
+  for (int c = tid; c < NCUBE; c += blockDim.x) { const int s = s_slab[c]; if (s >= 0) { slab_of[c] = s; cnt[s] = min(s_end[c], cap); } }
 }
 
 // segment descriptors of the per-cube re-filter (:770-801): every valid cube that has a slab, corner cubes then surf cubes, in place
 __global__ void __launch_bounds__(256) k_seg_cubes(MapperState* S, SegDesc* segs, int* n_seg, Pt4* p0, Pt4* p1, int cap0, int cap1, float leaf0, float leaf1) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const int t = threadIdx.x, nv = S->n_valid;
   if (t < 2 * nv) {
     const int ty = t >= nv, v = ty ? t - nv : t;
@@ -391,30 +420,30 @@ int mapper_step_device(aloam_ctx* c, const Pt4* d_corner_last, const int* d_nc, 
     aloam_cloud_view none{nullptr, 0, 4};
     rc = aloam_map_upload_impl(c, none, none); if (rc) return rc;
   }
-  LAUNCH(c, KID_CUBES, k_mapper_begin, 1, 1024, 0, S, d_odom7, m->max_sub);
-  LAUNCH(c, KID_CUBES, k_mapper_gather, dim3(kMaxValid, 2), 256, 0, (const MapperState*)S, (const Pt4*)m->d_pts[0], (const Pt4*)m->d_pts[1], m->cap[0], m->cap[1],
+  launch_ex(c, KID_CUBES, k_mapper_begin, dim3(1), dim3(1024), 0, 1, true, S, d_odom7, m->max_sub);
+  launch_ex(c, KID_CUBES, k_mapper_gather, dim3(dim3(kMaxValid, 2)), dim3(256), 0, 1, true, (const MapperState*)S, (const Pt4*)m->d_pts[0], (const Pt4*)m->d_pts[1], m->cap[0], m->cap[1],
          m->d_sub[0], m->d_sub[1]);
-  LAUNCH(c, KID_MAP_GRID, k_grid_setup, 1, 32, 0, c->map_corner.grid, (const int*)&S->n_sub[0], c->map_surf.grid, (const int*)&S->n_sub[1]);
+  launch_ex(c, KID_MAP_GRID, k_grid_setup, dim3(1), dim3(32), 0, 1, true, c->map_corner.grid, (const int*)&S->n_sub[0], c->map_surf.grid, (const int*)&S->n_sub[1]);
   map_index_build(c, m->d_sub[0], m->d_sub[1], m->max_sub);
   c->have_map = true;
   // ---- stack filters (:541-550): one segmented pass for both clouds
-  LAUNCH(c, KID_VOXEL, k_seg_two, 1, 32, 0, m->d_segs, m->d_nseg, d_corner_last, d_nc, c->cfg.line_res, c->d_stack_corner, &S->stack_counts[0], d_surf_last, d_ns,
+  launch_ex(c, KID_VOXEL, k_seg_two, dim3(1), dim3(32), 0, 1, true, m->d_segs, m->d_nseg, d_corner_last, d_nc, c->cfg.line_res, c->d_stack_corner, &S->stack_counts[0], d_surf_last, d_ns,
          c->cfg.plane_res, c->d_stack_surf, &S->stack_counts[1]);
   vox_seg_filter(c, make_filter(m, 31), m->buf, 2, n_upper_c + n_upper_s, std::max(n_upper_c, n_upper_s));
-  LAUNCH(c, KID_CUBES, k_mapper_prep, 1, 32, 0, S);
+  launch_ex(c, KID_CUBES, k_mapper_prep, dim3(1), dim3(32), 0, 1, true, S);
   // ---- optimisation (:554-733)
   const int nq_upper = std::min(n_upper_c + n_upper_s, 2 * c->max_points);
   map_register_device(c, c->d_stack_corner, c->d_stack_surf, S->stack_counts, nq_upper, S->x, false);
-  LAUNCH(c, KID_CUBES, k_mapper_update, 1, 32, 0, S, d_out7);
+  launch_ex(c, KID_CUBES, k_mapper_update, dim3(1), dim3(32), 0, 1, true, S, d_out7);
   // ---- insertion (:736-767)
   const Pt4* stacks[2] = {c->d_stack_corner, c->d_stack_surf};
   const int ups[2] = {n_upper_c, n_upper_s};
   for (int t = 0; t < 2; ++t) {
-    LAUNCH(c, KID_CUBES, k_cube_ids, std::max(1, std::min((ups[t] + 255) / 256, 148 * 4)), 256, 0, stacks[t], (const int*)&S->stack_counts[t], (const MapperState*)S, m->d_world, m->d_cube);
-    LAUNCH(c, KID_CUBES, k_cube_insert, 1, 1024, 0, (const Pt4*)m->d_world, (const int*)m->d_cube, (const int*)&S->stack_counts[t], S, t, m->d_pts[t], m->cap[t]);
+    launch_ex(c, KID_CUBES, k_cube_ids, dim3(std::max(1, std::min((ups[t] + 255) / 256, 148 * 4))), dim3(256), 0, 1, true, stacks[t], (const int*)&S->stack_counts[t], (const MapperState*)S, m->d_world, m->d_cube);
+    launch_ex(c, KID_CUBES, k_cube_insert, dim3(1), dim3(1024), 0, 1, true, (const Pt4*)m->d_world, (const int*)m->d_cube, (const int*)&S->stack_counts[t], S, t, m->d_pts[t], m->cap[t]);
   }
   // ---- per-cube re-filter of the valid cubes (:770-801): one segmented pass over <= 150 cubes, in place
-  LAUNCH(c, KID_CUBES, k_seg_cubes, 1, 256, 0, S, m->d_segs, m->d_nseg, m->d_pts[0], m->d_pts[1], m->cap[0], m->cap[1], c->cfg.line_res, c->cfg.plane_res);
+  launch_ex(c, KID_CUBES, k_seg_cubes, dim3(1), dim3(256), 0, 1, true, S, m->d_segs, m->d_nseg, m->d_pts[0], m->d_pts[1], m->cap[0], m->cap[1], c->cfg.line_res, c->cfg.plane_res);
   // index bits of a 50 m cube at the finer leaf: (50 / leaf + 3)^3 voxels at most (PCL itself gives up beyond 2^31)
   int cube_bits = 1;
   { const double side = std::floor(50.0 / std::min(c->cfg.line_res, c->cfg.plane_res)) + 3.0; const double cells = side * side * side;

@@ -62,6 +62,8 @@ unsigned grid_mask_for(int n, unsigned cap_slots) {
 
 // device-resident sizes -> GridDyn (the mapping loop gathers the submap on the device; its size never visits the host)
 __global__ void k_grid_setup(GridTable a, const int* __restrict__ na, GridTable b, const int* __restrict__ nb) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     a.dyn->n = *na; a.dyn->mask = min(table_mask_for(*na), a.cap_slots - 1); a.dyn->cursor = 0; a.dyn->owned = 0;
     b.dyn->n = *nb; b.dyn->mask = min(table_mask_for(*nb), b.cap_slots - 1); b.dyn->cursor = 0; b.dyn->owned = 0;
@@ -69,6 +71,8 @@ __global__ void k_grid_setup(GridTable a, const int* __restrict__ na, GridTable 
 }
 
 __global__ void k_grid_clear(GridTable a, GridTable b) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
   const uint4 empty = make_uint4(~0u, ~0u, 0u, 0u);
   const int ma = (int)a.dyn->mask, mb = (int)b.dyn->mask;
@@ -79,6 +83,8 @@ __global__ void k_grid_clear(GridTable a, GridTable b) {
 // blockIdx.y selects the cloud (0 = a, 1 = b)
 __global__ void k_grid_insert(GridTable a, const Pt4* __restrict__ pa, GridTable b, const Pt4* __restrict__ pb, int shard_rank,
                               int shard_count) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const GridTable& g = blockIdx.y == 0 ? a : b;
   const Pt4* __restrict__ pts = blockIdx.y == 0 ? pa : pb;
   const int n = g.dyn->n;
@@ -108,6 +114,8 @@ __global__ void k_grid_insert(GridTable a, const Pt4* __restrict__ pa, GridTable
 // atomicAdd serialises ~500k updates of a single address: 324 us for a 1M-point map, ncu r01).  Writes the cell's START
 // into the `end` word; k_grid_fill advances it to the end.
 __global__ void __launch_bounds__(256) k_grid_alloc(GridTable a, GridTable b) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   __shared__ int s_w[2][8];
   __shared__ int s_base[2];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -140,6 +148,8 @@ __global__ void __launch_bounds__(256) k_grid_alloc(GridTable a, GridTable b) {
 }
 
 __global__ void k_grid_fill(GridTable a, const Pt4* __restrict__ pa, GridTable b, const Pt4* __restrict__ pb) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const GridTable& g = blockIdx.y == 0 ? a : b;
   const Pt4* __restrict__ pts = blockIdx.y == 0 ? pa : pb;
   const int n = g.dyn->n;
@@ -556,10 +566,10 @@ void map_index_build(aloam_ctx* c, const Pt4* d_corner, const Pt4* d_surf, int n
   const int pb = std::max(1, std::min((std::max(n_upper, 1) + 255) / 256, kGridCtas));
   const unsigned slots_upper = grid_mask_for(std::max(n_upper, 1), (unsigned)c->map_slots) + 1;
   const int tb = std::max(1, std::min((int)((slots_upper + 255) / 256), kGridCtas));
-  LAUNCH(c, KID_MAP_GRID, k_grid_clear, tb, 256, 0, c->map_corner.grid, c->map_surf.grid);
-  LAUNCH(c, KID_MAP_GRID, k_grid_insert, dim3(pb, 2), 256, 0, c->map_corner.grid, d_corner, c->map_surf.grid, d_surf, c->shard_rank, c->shard_count);
-  LAUNCH(c, KID_MAP_GRID, k_grid_alloc, tb, 256, 0, c->map_corner.grid, c->map_surf.grid);
-  LAUNCH(c, KID_MAP_GRID, k_grid_fill, dim3(pb, 2), 256, 0, c->map_corner.grid, d_corner, c->map_surf.grid, d_surf);
+  launch_ex(c, KID_MAP_GRID, k_grid_clear, dim3(tb), dim3(256), 0, 1, true, c->map_corner.grid, c->map_surf.grid);
+  launch_ex(c, KID_MAP_GRID, k_grid_insert, dim3(dim3(pb, 2)), dim3(256), 0, 1, true, c->map_corner.grid, d_corner, c->map_surf.grid, d_surf, c->shard_rank, c->shard_count);
+  launch_ex(c, KID_MAP_GRID, k_grid_alloc, dim3(tb), dim3(256), 0, 1, true, c->map_corner.grid, c->map_surf.grid);
+  launch_ex(c, KID_MAP_GRID, k_grid_fill, dim3(dim3(pb, 2)), dim3(256), 0, 1, true, c->map_corner.grid, d_corner, c->map_surf.grid, d_surf);
 }
 
 // outer_iters x (5-NN + fits + LM) with the stacks, their counts {n_corner, n_surf, total} and the pose all in device memory

@@ -51,6 +51,8 @@ __global__ void k_vox_keys(const Pt4* __restrict__ pts, int n, VoxParams vp, uns
 }
 
 __global__ void __launch_bounds__(VT) k_radix_hist(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr, int shift, int* __restrict__ hist) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   __shared__ int s_h[256];
   const int tid = threadIdx.x;
   const int n = *n_ptr;
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(VT) k_radix_hist(const unsigned* __restrict__ 
 
 // one CTA, 1024 threads: thread (bin = t >> 2, quarter = t & 3) ; offsets are digit-major over all blocks
 __global__ void __launch_bounds__(1024) k_radix_scan(const int* __restrict__ hist, const int* __restrict__ n_ptr, int* __restrict__ offsets) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const int nblocks = (*n_ptr + VCH - 1) / VCH;
   __shared__ int s_tot[256];
   __shared__ int s_start[257];
@@ -100,6 +104,8 @@ __global__ void __launch_bounds__(1024) k_radix_scan(const int* __restrict__ his
 __global__ void __launch_bounds__(VT) k_radix_scatter(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in, const int* __restrict__ n_ptr,
                                                       int shift, const int* __restrict__ offsets, unsigned* __restrict__ keys_out,
                                                       int* __restrict__ vals_out) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   __shared__ int s_cnt[VIT * (VT / 32)][256];   // [slot = it*8 + warp][digit] -> exclusive prefix over slots
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int n = *n_ptr;
@@ -135,6 +141,8 @@ __global__ void __launch_bounds__(VT) k_radix_scatter(const unsigned* __restrict
 
 // number of voxel heads (first element of each run of equal keys) per block of VCH sorted elements
 __global__ void __launch_bounds__(VT) k_vox_heads(const unsigned* __restrict__ keys, const int* __restrict__ n_ptr, int* __restrict__ block_heads) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const int n = *n_ptr;
   if (blockIdx.x * VCH >= n) return;
   __shared__ int s_c;
@@ -154,6 +162,8 @@ __global__ void __launch_bounds__(VT) k_vox_heads(const unsigned* __restrict__ k
 }
 
 __global__ void __launch_bounds__(1024) k_vox_blockscan(int* __restrict__ block_heads, const int* __restrict__ n_ptr, int* __restrict__ total) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const int nblocks = (*n_ptr + VCH - 1) / VCH;
   __shared__ int s_w[32];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -233,6 +243,8 @@ __global__ void __launch_bounds__(VT) k_vox_emit(const Pt4* __restrict__ pts, co
 __device__ __forceinline__ int seg_count(const SegFilter& f) { return min(max(*f.n_seg - f.seg0, 0), f.seg_cap); }
 
 __global__ void __launch_bounds__(256) k_seg_prep(SegFilter f) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   __shared__ int s_w[8];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int S = seg_count(f);
@@ -260,6 +272,8 @@ __global__ void __launch_bounds__(256) k_seg_prep(SegFilter f) {
 
 // grid (chunks, segments)
 __global__ void __launch_bounds__(256) k_seg_bbox(SegFilter f) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const int sgm = blockIdx.y;
   if (sgm >= seg_count(f)) return;
   const SegDesc d = f.seg[f.seg0 + sgm];
@@ -286,6 +300,8 @@ __global__ void __launch_bounds__(256) k_seg_bbox(SegFilter f) {
 
 // grid (chunks, segments): keys / vals in the compact order (segment after segment)
 __global__ void __launch_bounds__(256) k_seg_keys(SegFilter f, unsigned* __restrict__ keys, int* __restrict__ vals) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const int sgm = blockIdx.y;
   if (sgm >= seg_count(f)) return;
   const SegDesc d = f.seg[f.seg0 + sgm];
@@ -324,45 +340,57 @@ __global__ void __launch_bounds__(256) k_seg_keys(SegFilter f, unsigned* __restr
   }
 }
 
-// heads before the first sorted slot of every segment, and the filtered size of every segment (one warp per segment)
-__global__ void __launch_bounds__(1024) k_seg_rank0(SegFilter f, const unsigned* __restrict__ keys, const int* __restrict__ block_offsets) {
-  __shared__ int s_r[ALOAM_MAX_SEGS + 1];
-  const int S = seg_count(f), total = *f.total;
+// heads before the first sorted slot of every segment (grid: segments + 1 CTAs of one warp; CTA s ranks slot off[s])
+__device__ __forceinline__ int seg_head_rank(const unsigned* __restrict__ keys, const int* __restrict__ block_offsets, int pos, int total) {
   const int lane = threadIdx.x & 31;
-  for (int sgm = threadIdx.x >> 5; sgm <= S; sgm += blockDim.x >> 5) {
-    const int pos = sgm == S ? total : f.off[sgm];
-    int r;
-    if (pos >= total) {
-      // all heads: block offset of the last block + its heads
-      const int lb = total > 0 ? (total - 1) / VCH : 0;
-      int cnt = 0;
-      for (int i = lb * VCH + lane; i < total; i += 32) cnt += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+  if (total <= 0) return 0;
+  const int p = min(pos, total);
+  // heads in [block start, p): for p == total the block is the last one (all of its heads count)
+  const int b = p >= total ? (total - 1) / VCH : p / VCH;
+  int cnt = 0;
+  for (int i = b * VCH + lane; i < p; i += 32) cnt += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 #pragma unroll
-      for (int dd = 16; dd > 0; dd >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, dd);
-      r = total > 0 ? block_offsets[lb] + cnt : 0;
-    } else {
-      const int b = pos / VCH;
-      int cnt = 0;
-      for (int i = b * VCH + lane; i < pos; i += 32) cnt += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
-#pragma unroll
-      for (int dd = 16; dd > 0; dd >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, dd);
-      r = block_offsets[b] + cnt;
-    }
-    if (lane == 0) s_r[sgm] = r;
+  for (int dd = 16; dd > 0; dd >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, dd);
+  return block_offsets[b] + cnt;
+}
+__global__ void __launch_bounds__(32) k_seg_rank0(SegFilter f, const unsigned* __restrict__ keys, const int* __restrict__ block_offsets) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
+  const int S = seg_count(f), total = *f.total;
+  const int sgm = blockIdx.x;
+  if (sgm > S) return;
+  const int r0 = seg_head_rank(keys, block_offsets, sgm == S ? total : f.off[sgm], total);
+  if (threadIdx.x == 0) f.rank0[sgm] = r0;
+  if (sgm < S) {   // the filtered size of this segment needs the rank of the next boundary too
+    const int r1 = seg_head_rank(keys, block_offsets, sgm + 1 == S ? total : f.off[sgm + 1], total);
+    if (threadIdx.x == 0) *f.seg[f.seg0 + sgm].n_out = r1 - r0;
   }
-  __syncthreads();
-  for (int sgm = threadIdx.x; sgm <= S; sgm += blockDim.x) f.rank0[sgm] = s_r[sgm];
-  for (int sgm = threadIdx.x; sgm < S; sgm += blockDim.x) *f.seg[f.seg0 + sgm].n_out = s_r[sgm + 1] - s_r[sgm];
 }
 
 // every head sums its run in sorted order (float, like pcl::CentroidPoint); output slot = off[segment] + rank inside the segment
 __global__ void __launch_bounds__(VT) k_seg_emit(SegFilter f, const unsigned* __restrict__ keys, const int* __restrict__ vals,
                                                  const int* __restrict__ block_offsets, Pt4* __restrict__ tmp) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const int n = *f.total;
   if (blockIdx.x * VCH >= n) return;
   __shared__ int s_w[VT / 32];
+  __shared__ Pt4 s_pts[VCH];        // the block's points in sorted order: the runs are summed from shared memory, the gather
+  __shared__ unsigned s_keys[VCH];  // through vals[] is issued once, all loads in flight
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int base = blockIdx.x * VCH + tid * VIT;
+  const int b0 = blockIdx.x * VCH;
+#pragma unroll
+  for (int k = 0; k < VIT; ++k) {
+    const int i = b0 + k * VT + tid;
+    if (i < n) {
+      const unsigned key = keys[i];
+      const int sgm = (int)(key >> f.idx_bits);
+      s_keys[k * VT + tid] = key;
+      s_pts[k * VT + tid] = f.seg[f.seg0 + sgm].src[vals[i] - f.off[sgm]];
+    }
+  }
+  __syncthreads();
+  const int base = b0 + tid * VIT;
   int heads = 0;
   bool is_head[VIT];
 #pragma unroll
@@ -379,20 +407,29 @@ __global__ void __launch_bounds__(VT) k_seg_emit(SegFilter f, const unsigned* __
   int wbase = 0;
   for (int v = 0; v < w; ++v) wbase += s_w[v];
   int rank = block_offsets[blockIdx.x] + wbase + incl - heads;
+  const int bend = min(n, b0 + VCH);
 #pragma unroll
   for (int k = 0; k < VIT; ++k) {
     if (!is_head[k]) continue;
     const int i = base + k;
-    const unsigned key = keys[i];
+    const unsigned key = s_keys[i - b0];
     const int sgm = (int)(key >> f.idx_bits);
     const int off = f.off[sgm];
-    const Pt4* __restrict__ src = f.seg[f.seg0 + sgm].src;
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
     int cnt = 0;
-    for (int j = i; j < n && keys[j] == key; ++j) {
-      const Pt4 p = src[vals[j] - off];
+    int j = i;
+    for (; j < bend && s_keys[j - b0] == key; ++j) {   // float accumulation in sorted order (pcl::CentroidPoint)
+      const Pt4 p = s_pts[j - b0];
       sx += p.x; sy += p.y; sz += p.z; si += p.i;
       ++cnt;
+    }
+    if (j == bend) {   // the run continues in the next block(s): finish it from global memory
+      const Pt4* __restrict__ src = f.seg[f.seg0 + sgm].src;
+      for (; j < n && keys[j] == key; ++j) {
+        const Pt4 p = src[vals[j] - off];
+        sx += p.x; sy += p.y; sz += p.z; si += p.i;
+        ++cnt;
+      }
     }
     const float nf = (float)cnt;
     Pt4 o; o.x = sx / nf; o.y = sy / nf; o.z = sz / nf; o.i = si / nf;
@@ -403,6 +440,8 @@ __global__ void __launch_bounds__(VT) k_seg_emit(SegFilter f, const unsigned* __
 
 // grid (chunks, segments): filtered points back to their destination (which may be the source slab itself)
 __global__ void __launch_bounds__(256) k_seg_writeback(SegFilter f, const Pt4* __restrict__ tmp) {
+  pdl_launch_dependents();
+  pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
   const int sgm = blockIdx.y;
   if (sgm >= seg_count(f)) return;
   const SegDesc d = f.seg[f.seg0 + sgm];
@@ -420,28 +459,28 @@ using namespace aloam;
 // index, the segments are processed in windows of 2^(32 - idx_bits).
 void vox_seg_filter(aloam_ctx* c, const SegFilter& f_in, SegBuffers& b, int S_upper, int n_upper, int per_seg_upper) {
   const int nblk = std::max(1, (n_upper + VCH - 1) / VCH);
-  const int chunks = std::max(1, std::min((per_seg_upper + 255) / 256, 64));
+  const int chunks = std::max(1, std::min((per_seg_upper + 255) / 256, S_upper > 8 ? 8 : 64));   // grid-stride inside a segment
   const int win = (int)std::min<long long>(1ll << std::max(0, 32 - f_in.idx_bits), ALOAM_MAX_SEGS);
   for (int s0 = 0; s0 < S_upper; s0 += win) {
     SegFilter f = f_in;
     f.seg0 = s0; f.seg_cap = std::min(win, S_upper - s0);
     int seg_bits = 0; while ((1 << seg_bits) < f.seg_cap) ++seg_bits;
     const int bits = f.idx_bits + seg_bits;
-    LAUNCH(c, KID_VOXEL, k_seg_prep, 1, 256, 0, f);
-    LAUNCH(c, KID_VOXEL, k_seg_bbox, dim3(chunks, f.seg_cap), 256, 0, f);
-    LAUNCH(c, KID_VOXEL, k_seg_keys, dim3(chunks, f.seg_cap), 256, 0, f, b.keys[0], b.vals[0]);
+    launch_ex(c, KID_VOXEL, k_seg_prep, dim3(1), dim3(256), 0, 1, true, f);
+    launch_ex(c, KID_VOXEL, k_seg_bbox, dim3(dim3(chunks, f.seg_cap)), dim3(256), 0, 1, true, f);
+    launch_ex(c, KID_VOXEL, k_seg_keys, dim3(dim3(chunks, f.seg_cap)), dim3(256), 0, 1, true, f, b.keys[0], b.vals[0]);
     int cur = 0;
     for (int shift = 0; shift < bits; shift += 8) {
-      LAUNCH(c, KID_VOXEL, k_radix_hist, nblk, VT, 0, b.keys[cur], f.total, shift, b.hist);
-      LAUNCH(c, KID_VOXEL, k_radix_scan, 1, 1024, 0, b.hist, f.total, b.offs);
-      LAUNCH(c, KID_VOXEL, k_radix_scatter, nblk, VT, 0, b.keys[cur], b.vals[cur], f.total, shift, b.offs, b.keys[cur ^ 1], b.vals[cur ^ 1]);
+      launch_ex(c, KID_VOXEL, k_radix_hist, dim3(nblk), dim3(VT), 0, 1, true, b.keys[cur], f.total, shift, b.hist);
+      launch_ex(c, KID_VOXEL, k_radix_scan, dim3(1), dim3(1024), 0, 1, true, b.hist, f.total, b.offs);
+      launch_ex(c, KID_VOXEL, k_radix_scatter, dim3(nblk), dim3(VT), 0, 1, true, b.keys[cur], b.vals[cur], f.total, shift, b.offs, b.keys[cur ^ 1], b.vals[cur ^ 1]);
       cur ^= 1;
     }
-    LAUNCH(c, KID_VOXEL, k_vox_heads, nblk, VT, 0, b.keys[cur], f.total, b.block_heads);
-    LAUNCH(c, KID_VOXEL, k_vox_blockscan, 1, 1024, 0, b.block_heads, f.total, b.heads_total);
-    LAUNCH(c, KID_VOXEL, k_seg_rank0, 1, 1024, 0, f, b.keys[cur], b.block_heads);
-    LAUNCH(c, KID_VOXEL, k_seg_emit, nblk, VT, 0, f, b.keys[cur], b.vals[cur], b.block_heads, b.tmp);
-    LAUNCH(c, KID_VOXEL, k_seg_writeback, dim3(chunks, f.seg_cap), 256, 0, f, b.tmp);
+    launch_ex(c, KID_VOXEL, k_vox_heads, dim3(nblk), dim3(VT), 0, 1, true, b.keys[cur], f.total, b.block_heads);
+    launch_ex(c, KID_VOXEL, k_vox_blockscan, dim3(1), dim3(1024), 0, 1, true, b.block_heads, f.total, b.heads_total);
+    launch_ex(c, KID_VOXEL, k_seg_rank0, dim3(f.seg_cap + 1), dim3(32), 0, 1, true, f, b.keys[cur], b.block_heads);
+    launch_ex(c, KID_VOXEL, k_seg_emit, dim3(nblk), dim3(VT), 0, 1, true, f, b.keys[cur], b.vals[cur], b.block_heads, b.tmp);
+    launch_ex(c, KID_VOXEL, k_seg_writeback, dim3(dim3(chunks, f.seg_cap)), dim3(256), 0, 1, true, f, b.tmp);
   }
 }
 

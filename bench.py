@@ -360,6 +360,85 @@ def mapping_record(args, synth, pkg, ctx_feat, rank, world, local_rank, dist, to
     return rec
 
 
+def mapped_record(args, synth, pkg, rank, world, local_rank, dist, torch, K, W, scans, counts, dev, host, oracle_odom):
+    """the three reference nodes in one call: aloam_scan_stream_mapped = extraction + odometry + scan-to-map with
+    the map cube store, every hand-off on the device.  One replica per GPU (the cube store is not sharded)."""
+    maxn = max(counts)
+    n = 1 + W + K
+    ctx = pkg.Aloam(n_scans=64, device=local_rank, max_points=maxn + 1024, max_map_points=600000)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def run(base, device_resident):
+        ctx.reset_odometry(); ctx.mapper_reset()
+        ptrs = [base[i].data_ptr() for i in range(n)]
+        o0, m0 = ctx.scan_stream_mapped(ptrs[:1 + W], counts[:1 + W], device_resident)
+        barrier()
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        o1, m1 = ctx.scan_stream_mapped(ptrs[1 + W:], counts[1 + W:n], device_resident)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        return t1 - t0, np.concatenate([o0, o1]), np.concatenate([m0, m1]), ctx.launch_count() - l0
+    secs, odom, mapped, launches = run(dev, True)
+    secs_h, _, mapped_h, _ = run(host, False)
+    # kernel breakdown of one synchronous frame (aloam_scan_to_pose + aloam_mapper_step), CUDA events around every launch
+    ctx.reset_odometry(); ctx.mapper_reset()
+    for i in range(1 + W):
+        q, t, _ = ctx.scan_to_pose_device(dev[i].data_ptr(), counts[i])
+        f = ctx.extract_features(scans[i]); ctx.mapper_step(f["less_sharp"], f["less_flat"], q, t)
+    ctx.profile_enable(True)
+    sync_s = 0.0
+    for i in range(1 + W, 1 + W + min(K, 5)):
+        q, t, _ = ctx.scan_to_pose_device(dev[i].data_ptr(), counts[i])
+        f = ctx.extract_features(scans[i])
+        t0 = time.perf_counter(); ctx.mapper_step(f["less_sharp"], f["less_flat"], q, t); sync_s += time.perf_counter() - t0
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    st = ctx.mapper_state()
+    tt = torch.tensor([secs, secs_h], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    secs, secs_h = float(tt[0]), float(tt[1])
+    rec = None
+    if rank == 0:
+        import pyoracle as orc
+        nf = min(K, 5)
+        per_kernel = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / nf, "ms_per_step": v[0] / nf} for k, v in prof.items()
+                      if k in ("k_cube_store", "k_voxel", "k_map_grid(4 launches)", "k_map_knn5", "k_map_fit", "k_lm_solve")}
+        # oracle mapping loop on the oracle's odometry poses over the first frames (kd-tree builds make it slow)
+        n_chk = min(n, 1 + W + 4)
+        cm = orc.CubeMap()
+        ns, _, mr = synth.SENSORS[SENSOR][:3]
+        ref = []
+        t0 = time.perf_counter()
+        for k in range(n_chk):
+            fo = orc.Features(scans[k], ns, mr)
+            pose, _ = cm.step(fo.less_sharp, fo.less_flat, oracle_odom[k, :4], oracle_odom[k, 4:], 0.4, 0.8)
+            ref.append(pose)
+        cpu_s = (time.perf_counter() - t0) / n_chk
+        rm, rr, mm, mr_ = pose_rmse(mapped[1:n_chk], np.array(ref)[1:])
+        rec = {"metric": "scans/sec", "value": K * world / secs, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * secs / K,
+               "scaling": "weak (replicas)",
+               "config": {"workload": "HDL-64 stream through all three stages: extraction + scan-to-scan odometry + scan-to-map against the growing map cube store "
+                                      "(aloam_scan_stream_mapped; gather of <= 75 cubes, index build, 2 x (5-NN + fits + LM), insertion, per-cube VoxelGrid, all on the device)",
+                          "map_points_after_run": int(st["total_corner"] + st["total_surf"])},
+               "e2e": {"value": K * world / secs_h, "unit": "scans/s", "h2d_bytes_per_step": 16 * int(np.mean(counts)), "d2h_bytes_per_step": 112},
+               "gpu_launches": launches,
+               "mapper_step_sync_ms": 1e3 * sync_s / nf, "per_kernel_mapper_step": per_kernel,
+               "host_equals_device_path": bool(np.array_equal(mapped, mapped_h)),
+               "map_pose_rmse_vs_oracle_m": rm, "map_pose_rmse_vs_oracle_rad": rr, "map_pose_max_vs_oracle_m": mm, "scans_checked": n_chk - 1,
+               "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "scans/s", "cores": 1, "kind": "port",
+                                "sample": "%d frames of the oracle's alaserMapping loop alone (extraction and odometry not included): kd-tree builds + 2 x (5-NN + fits + LM) "
+                                          "+ insertion + per-cube VoxelGrid" % n_chk}}
+    ctx.close()
+    return rec
+
+
 def batch_record(args, synth, pkg, rank, world, local_rank, dist, torch, K, W):
     """BASELINE configs[4]: HDL-32 32x2200, B trajectories in flight in ONE context / ONE host thread (shared launches)."""
     if not hasattr(pkg.Aloam, "scan_stream_batch"):
@@ -444,6 +523,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mapping", action="store_true", help="skip the scan-to-map sub-record (configs[2] / [3])")
     ap.add_argument("--no-batch", action="store_true", help="skip the batched-stream sub-record (configs[4])")
+    ap.add_argument("--no-mapped", action="store_true", help="skip the full three-stage stream (odometry + map cube store)")
     args = ap.parse_args()
     K, W = max(args.steps, 1), max(args.warmup, 3)   # never fewer than 3 untimed warm-up steps
     rank = int(os.environ.get("RANK", "0"))
@@ -577,9 +657,19 @@ def main():
 
     mapping = None if args.no_mapping else mapping_record(args, synth, pkg, ctx, rank, world, local_rank, dist, torch, K, W)
     batch = None if args.no_batch else batch_record(args, synth, pkg, rank, world, local_rank, dist, torch, K, W)
-
+    # pose RMSE of the K timed scans of the first repeat against the CPU oracle on the same scans (BASELINE.json metric)
+    n_chk = 1 + W + K
+    oposes = None
     if rank == 0:
         import pyoracle as orc
+        tot_cpu, t_ext, t_odo, oposes = cpu_odometry_sequential(orc, synth, scans[:n_chk])
+    mapped = None
+    if not args.no_mapped:
+        if world > 1:   # every rank feeds its oracle-independent run; only rank 0 holds the oracle poses
+            pass
+        mapped = mapped_record(args, synth, pkg, rank, world, local_rank, dist, torch, K, W, scans, counts, dev, host, oposes)
+
+    if rank == 0:
         feats = ctx.extract_features(scans[1 + W])
         n_raw = counts[1 + W]
         n_full = feats["full"].shape[0]
@@ -607,9 +697,7 @@ def main():
                     "note": "single ~2 MB scans are latency/occupancy bound, not HBM bound (SURVEY.md 8d): frac is expected << 1; per_kernel is "
                             "measured with CUDA events around every launch of the K timed steps of the synchronous API (launches_per_step = launches / K)"}
 
-        # pose RMSE of the K timed scans of the first repeat against the CPU oracle on the same scans (BASELINE.json metric)
-        n_chk = 1 + W + K
-        tot, t_ext, t_odo, oposes = cpu_odometry_sequential(orc, synth, scans[:n_chk])
+        tot = tot_cpu
         rm, rr, mm, mr_ = pose_rmse(poses_dev[1 + W:n_chk], oposes[1 + W:])
         rm_e, rr_e, _, _ = pose_rmse(poses_e2e[1 + W:n_chk], oposes[1 + W:])
         cpu_baseline = None
@@ -641,7 +729,7 @@ def main():
                                "e2e_path_rmse_vs_oracle_m": rm_e, "e2e_path_rmse_vs_oracle_rad": rr_e,
                                "device_vs_host_path_identical": bool(np.array_equal(poses_dev, poses_e2e)),
                                "t_w_stream_vs_sync_maxabs": float(np.abs(poses_dev[W + K, 4:] - pose_sync[4:]).max())},
-                "mapping": mapping, "batch": batch}
+                "mapping": mapping, "batch": batch, "mapped_stream": mapped}
         emit(line)
     ctx.close()
     if world > 1:
