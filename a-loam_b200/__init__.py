@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "aloam_odometry_set_last", "aloam_odometry_register", "aloam_map_upload", "aloam_mapping_register",
     "aloam_voxel_filter", "aloam_scan_to_pose", "aloam_scan_to_pose_device", "aloam_reset_odometry", "aloam_knn",
     "aloam_odometry_associate", "aloam_normal_equations", "aloam_solve", "aloam_debug_features", "aloam_mapping_associate",
-    "aloam_comm_unique_id", "aloam_comm_init", "aloam_scan_stream", "aloam_scan_stream_batch", "aloam_scan_stream_mapped", "aloam_transform_to_end", "aloam_mapper_reset", "aloam_mapper_step", "aloam_profile_enable", "aloam_profile_read", "aloam_launch_count",
+    "aloam_comm_unique_id", "aloam_comm_init", "aloam_comm_uses_peer_memory", "aloam_map_upload_sharded", "aloam_scan_stream", "aloam_scan_stream_batch", "aloam_scan_stream_mapped", "aloam_transform_to_end", "aloam_mapper_reset", "aloam_mapper_step", "aloam_profile_enable", "aloam_profile_read", "aloam_launch_count",
 ]
 
 
@@ -78,6 +78,7 @@ def lib():
         L.aloam_odometry_set_last.argtypes = [C.c_void_p, cv, cv]
         L.aloam_odometry_register.argtypes = [C.c_void_p, cv, cv, dp, dp, C.POINTER(Stats)]
         L.aloam_map_upload.argtypes = [C.c_void_p, cv, cv]
+        L.aloam_map_upload_sharded.argtypes = [C.c_void_p, cv, cv]
         L.aloam_mapping_register.argtypes = [C.c_void_p, cv, cv, dp, C.POINTER(Stats)]
         L.aloam_voxel_filter.argtypes = [C.c_void_p, cv, C.c_float, C.POINTER(cv)]
         L.aloam_mapper_reset.argtypes = [C.c_void_p]
@@ -210,6 +211,17 @@ class Aloam:
         b, kb = _view(surf_map)
         _check(lib().aloam_map_upload(self._h, a, b))
 
+    def map_upload_sharded(self, corner_map, surf_map):
+        """the whole submap in, this rank's shard (owned x-slabs + halo) cut out on the device and indexed"""
+        a, ka = _view(corner_map)
+        b, kb = _view(surf_map)
+        _check(lib().aloam_map_upload_sharded(self._h, a, b))
+
+    def map_upload_sharded_ptr(self, corner_ptr, n_corner, surf_ptr, n_surf, stride=4):
+        a = CloudView(C.cast(C.c_void_p(int(corner_ptr)), C.POINTER(C.c_float)), int(n_corner), stride)
+        b = CloudView(C.cast(C.c_void_p(int(surf_ptr)), C.POINTER(C.c_float)), int(n_surf), stride)
+        _check(lib().aloam_map_upload_sharded(self._h, a, b))
+
     def map_upload_ptr(self, corner_ptr, n_corner, surf_ptr, n_surf, stride=4):
         """aloam_map_upload on raw addresses (pinned host memory or device memory; the library infers the copy kind)"""
         a = CloudView(C.cast(C.c_void_p(int(corner_ptr)), C.POINTER(C.c_float)), int(n_corner), stride)
@@ -267,6 +279,10 @@ class Aloam:
 
     def comm_init(self, rank, world, unique_id):
         _check(lib().aloam_comm_init(self._h, rank, world, C.create_string_buffer(bytes(unique_id), 128)))
+
+    def comm_uses_peer_memory(self):
+        lib().aloam_comm_uses_peer_memory.argtypes = [C.c_void_p]
+        return bool(lib().aloam_comm_uses_peer_memory(self._h))
 
     def voxel_filter(self, cloud, leaf):
         a, ka = _view(cloud)

@@ -17,6 +17,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -30,6 +31,7 @@ bool load_nccl() {
   g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) return false;
@@ -38,12 +40,28 @@ bool load_nccl() {
 }
 }  // namespace
 
+// peer-memory exchange state of a context (see PeerX, kernels.h)
+struct PeerState {
+  PeerX px = {};
+  void* own = nullptr;                 // this rank's mailbox allocation (boxes, flags, counter, totals, error word)
+  void* opened[ALOAM_MAX_RANKS] = {};  // peers' mailboxes mapped into this process (cudaIpcOpenMemHandle)
+};
+
 void launch_lm_sharded(aloam_ctx* c, const BlockRec* blocks, const int* d_n, double* pose, const LmParams& lp, LmSummary* summary) {
+  if (c->peer) {
+    // ONE launch per solve: the cluster kernel of the single-GPU path with the all-reduce of every evaluation done inside it
+    // over NVLink peer memory; early termination ends the solve on every rank at the same evaluation
+    PeerState* ps = static_cast<PeerState*>(c->peer);
+    Batch<LmArgs> b = {};
+    b.a[0] = LmArgs{blocks, d_n, 0, pose, summary, nullptr, nullptr};
+    launch_lm_batch(c, true, b, 1, lp, 0, 0, &ps->px);
+    return;
+  }
   const int evals = 1 + lp.max_iters;
   double* local = c->d_lm_tot + 32;
   for (int e = 0; e < evals; ++e) {
     const int first = e == 0, last = e == evals - 1;
-    prof_begin(c, KID_LM_SOLVE);
+    prof_begin(c, KID_LM_SHARD);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kLmCluster); cfg.blockDim = dim3(ALOAM_LM_THREADS); cfg.dynamicSmemBytes = lm_dynamic_smem_bytes(); cfg.stream = c->stream;
     cudaLaunchAttribute at[1];
@@ -54,8 +72,61 @@ void launch_lm_sharded(aloam_ctx* c, const BlockRec* blocks, const int* d_n, dou
     prof_end(c);
     ncclResult_t r = g_nccl.AllReduce(local, c->d_lm_tot, 32, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream);
     if (r != ncclSuccess) fprintf(stderr, "[aloam_b200] ncclAllReduce failed: %s\n", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
-    LAUNCH(c, KID_LM_SOLVE, k_lm_tr_shard, 1, 32, 0, c->d_lm_state, (const double*)c->d_lm_tot, pose, first, last, lp, summary);
+    LAUNCH(c, KID_LM_SHARD, k_lm_tr_shard, 1, 32, 0, c->d_lm_state, (const double*)c->d_lm_tot, pose, first, last, lp, summary);
   }
+}
+
+// Maps every rank's mailbox into every other rank (CUDA IPC handles exchanged with one ncclAllGather).  Returns false (and leaves
+// the NCCL path in place) when peer access is not available or ALOAM_NO_PEER is set.
+static bool peer_setup(aloam_ctx* c, int rank, int world) {
+  if (getenv("ALOAM_NO_PEER") || world > ALOAM_MAX_RANKS || !g_nccl.AllGather) return false;
+  PeerState* ps = new (std::nothrow) PeerState();
+  if (!ps) return false;
+  const size_t box_bytes = (size_t)2 * world * 32 * sizeof(double), flag_bytes = (size_t)2 * world * sizeof(unsigned);
+  const size_t total = box_bytes + flag_bytes + 64 + 2 * 32 * sizeof(double) + 64;
+  bool ok = cudaMalloc(&ps->own, total) == cudaSuccess && cudaMemset(ps->own, 0, total) == cudaSuccess;
+  cudaIpcMemHandle_t mine;
+  ok = ok && cudaIpcGetMemHandle(&mine, ps->own) == cudaSuccess;
+  cudaIpcMemHandle_t* d_all = nullptr;
+  std::vector<cudaIpcMemHandle_t> all(world);
+  ok = ok && cudaMalloc((void**)&d_all, sizeof(mine) * (world + 1)) == cudaSuccess;
+  // every rank must take part in the gather even if its own setup failed: a zeroed handle marks the failure
+  if (!ok) std::memset(&mine, 0, sizeof(mine));
+  bool gathered = false;
+  if (d_all) {
+    cudaMemcpyAsync(d_all + world, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream);
+    if (g_nccl.AllGather(d_all + world, d_all, sizeof(mine), ncclChar, (ncclComm_t)c->comm, c->stream) == ncclSuccess &&
+        cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * world, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+        cudaStreamSynchronize(c->stream) == cudaSuccess)
+      gathered = true;
+    cudaFree(d_all);
+  }
+  ok = ok && gathered;
+  const cudaIpcMemHandle_t zero = {};
+  for (int r = 0; r < world && ok; ++r) {
+    void* base = ps->own;
+    if (r != rank) {
+      if (!std::memcmp(&all[r], &zero, sizeof(zero)) || cudaIpcOpenMemHandle(&ps->opened[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+      base = ps->opened[r];
+    }
+    ps->px.box[r] = reinterpret_cast<double*>(base);
+    ps->px.flag[r] = reinterpret_cast<unsigned*>(static_cast<char*>(base) + box_bytes);
+  }
+  if (!ok) {
+    cudaGetLastError();
+    for (void* p : ps->opened) if (p) cudaIpcCloseMemHandle(p);
+    if (ps->own) cudaFree(ps->own);
+    delete ps;
+    fprintf(stderr, "[aloam_b200] peer-memory exchange unavailable on rank %d: the sharded LM uses ncclAllReduce\n", rank);
+    return false;
+  }
+  char* own = static_cast<char*>(ps->own);
+  ps->px.seq = reinterpret_cast<unsigned long long*>(own + box_bytes + flag_bytes);
+  ps->px.gtot = reinterpret_cast<double*>(own + box_bytes + flag_bytes + 64);
+  ps->px.err = reinterpret_cast<int*>(own + box_bytes + flag_bytes + 64 + 2 * 32 * sizeof(double));
+  ps->px.rank = rank; ps->px.world = world;
+  c->peer = ps;
+  return true;
 }
 
 // sum of two ints over the ranks, in place (global submap sizes for the thin-map test, mapping.cu)
@@ -70,6 +141,13 @@ extern "C" {
 
 void aloam_comm_free_impl(aloam_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
+  if (c->peer) {
+    PeerState* ps = static_cast<PeerState*>(c->peer);
+    for (void* p : ps->opened) if (p) cudaIpcCloseMemHandle(p);
+    if (ps->own) cudaFree(ps->own);
+    delete ps;
+    c->peer = nullptr;
+  }
   if (c->d_lm_tot) cudaFree(c->d_lm_tot);
   if (c->d_lm_state) cudaFree(c->d_lm_state);
   c->d_lm_tot = nullptr; c->d_lm_state = nullptr;
@@ -103,8 +181,29 @@ int aloam_comm_init(aloam_ctx* c, int rank, int world, const char id128[128]) {
   if (!c->d_lm_tot) CUDA_CHECK_RET(cudaMalloc((void**)&c->d_lm_tot, 64 * sizeof(double)));
   if (!c->d_lm_state) CUDA_CHECK_RET(cudaMalloc(&c->d_lm_state, lm_state_bytes()));
   c->shard_rank = rank; c->shard_count = world;
+  // the 256-byte exchange of every LM evaluation goes through NVLink peer memory inside the solve kernel when the ranks can map
+  // each other's memory (all ranks decide alike: the outcome of the handle exchange is the same everywhere ... see below)
+  const bool mine_ok = peer_setup(c, rank, world);
+  // agree on the path: one rank without peer access forces everybody onto NCCL
+  int* d_flag = nullptr;
+  CUDA_CHECK_RET(cudaMalloc((void**)&d_flag, 2 * sizeof(int)));
+  int h[2] = {mine_ok ? 0 : 1, 0};
+  CUDA_CHECK_RET(cudaMemcpyAsync(d_flag, h, 8, cudaMemcpyHostToDevice, c->stream));
+  if (g_nccl.AllReduce(d_flag, d_flag, 2, ncclInt32, ncclSum, (ncclComm_t)c->comm, c->stream) != ncclSuccess) { cudaFree(d_flag); return ALOAM_ERR_COMM; }
+  CUDA_CHECK_RET(cudaMemcpyAsync(h, d_flag, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  cudaFree(d_flag);
+  if (h[0] != 0 && c->peer) {   // somebody failed: drop the peer path here too
+    PeerState* ps = static_cast<PeerState*>(c->peer);
+    for (void* p : ps->opened) if (p) cudaIpcCloseMemHandle(p);
+    if (ps->own) cudaFree(ps->own);
+    delete ps;
+    c->peer = nullptr;
+  }
   return ALOAM_OK;
 }
+
+int aloam_comm_uses_peer_memory(aloam_ctx* c) { return c && c->peer ? 1 : 0; }
 
 int aloam_shard_slab_cells(void) { return 8; }   // ownership: slab = floor((cell_x + 2^20) / 8), owner = slab mod world
 

@@ -166,8 +166,10 @@ void launch_ex(aloam_ctx* c, int kid, K kernel, dim3 grid, dim3 block, size_t sm
 
 // the LM kernel runs as one thread-block cluster per trajectory (distributed-shared-memory reduction, see lm.cu)
 constexpr int kLmCluster = 8;
-inline void launch_lm_batch(aloam_ctx* c, bool pdl, const Batch<LmArgs>& args, int lanes, const LmParams& lp, int mode, int integrate) {
-  launch_ex(c, KID_LM_SOLVE, k_lm_solve, dim3(kLmCluster, lanes), dim3(ALOAM_LM_THREADS), lm_dynamic_smem_bytes(), kLmCluster, pdl, args, lp, mode, integrate);
+inline void launch_lm_batch(aloam_ctx* c, bool pdl, const Batch<LmArgs>& args, int lanes, const LmParams& lp, int mode, int integrate, const PeerX* px = nullptr) {
+  PeerX none = {};
+  launch_ex(c, KID_LM_SOLVE, k_lm_solve, dim3(kLmCluster, lanes), dim3(ALOAM_LM_THREADS), lm_dynamic_smem_bytes(), kLmCluster, pdl, args, lp, mode, integrate,
+            px ? *px : none);
 }
 // single solve: blocks, n (device pointer or host value), pose in / out
 inline void launch_lm(aloam_ctx* c, bool pdl, const BlockRec* blocks, const int* n_ptr, int n_host, double* x7, const LmParams& lp, LmSummary* summary,

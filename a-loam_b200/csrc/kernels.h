@@ -143,7 +143,20 @@ struct LmSummary {
 // mode 0: full trust-region solve, x updated in place ; mode 1: one evaluation, out28 = [JtJ upper 21, g 6, cost]
 // integrate != 0 : after the solve compose the world pose (laserOdometry.cpp:504-505): world7 <- world7 (+) x
 struct LmArgs { const BlockRec* blocks; const int* n_blocks_ptr; int n_blocks_host; double* x7; LmSummary* summary; double* out28; double* world7; };
-__global__ void k_lm_solve(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate);   // grid (8, lanes), clusters of 8 along x
+// Sharded solve over NVLink peer memory (multi-GPU scan-to-map, comm.cu): every rank's LM cluster pushes its 32 partial sums
+// into a mailbox in EVERY rank's memory (peer stores through NVSwitch), raises a flag there, waits for the flags of all ranks
+// in its own mailbox and adds the contributions in rank order -- the all-reduce of the normal equations happens INSIDE the
+// solve kernel, one launch per solve, no kernel boundary around the 256-byte exchange.  world <= 1: no exchange.
+#define ALOAM_MAX_RANKS 16
+struct PeerX {
+  double* box[ALOAM_MAX_RANKS];             // mailbox of rank r: [2 parities][world][32] doubles (peer-mapped device memory)
+  unsigned* flag[ALOAM_MAX_RANKS];          // flags of rank r:   [2 parities][world]
+  unsigned long long* seq;                  // this rank's evaluation counter (device), identical on all ranks by construction
+  double* gtot;                             // [2][32] this rank's summed totals (local)
+  int* err;                                 // set to 1 when a peer did not answer in time
+  int rank, world;
+};
+__global__ void k_lm_solve(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate, PeerX px);   // grid (8, lanes), clusters of 8 along x
 // sharded solve: per-evaluation kernels around an ncclAllReduce (see lm.cu, comm.cu)
 size_t lm_state_bytes();
 size_t lm_dynamic_smem_bytes();   // dynamic shared memory of k_lm_solve / k_lm_eval_shard (opt-in > 48 KB)

@@ -541,7 +541,39 @@ __global__ void k_pack_blocks(const double* __restrict__ packed, int n, BlockRec
   out[i] = r;
 }
 
-__global__ void __launch_bounds__(NT, 1) k_lm_solve(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate) {
+// all-reduce of the cluster totals over the ranks through peer memory (see PeerX in kernels.h).  Called by every thread of the
+// cluster after cluster_evaluate; on return `tot` holds the sum over all ranks, bit-identical on every rank (rank-order sum).
+template <typename Cluster>
+__device__ __forceinline__ void peer_allreduce(Cluster& cluster, const PeerX& px, unsigned long long seq, double* tot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int par = (int)(seq & 1ull);
+  const unsigned tag = (unsigned)seq;
+  if (cluster.block_rank() == 0 && warp == 0) {
+    const double mine = tot[lane];
+    for (int r = 0; r < px.world; ++r) px.box[r][(par * px.world + px.rank) * 32 + lane] = mine;   // peer stores (NVLink)
+    __threadfence_system();
+    __syncwarp();
+    if (lane < px.world) *reinterpret_cast<volatile unsigned*>(px.flag[lane] + par * px.world + px.rank) = tag;
+    if (lane < px.world) {
+      const volatile unsigned* f = px.flag[px.rank] + par * px.world + lane;
+      const long long t0 = clock64();
+      while (*f != tag) {
+        if (clock64() - t0 > 4000000000ll) { *px.err = 1; break; }   // ~2 s: a peer is gone; never hang the GPU
+      }
+    }
+    __syncwarp();
+    __threadfence_system();
+    double sum = 0.0;
+    const volatile double* in = px.box[px.rank] + (size_t)par * px.world * 32;
+    for (int r = 0; r < px.world; ++r) sum += in[r * 32 + lane];
+    px.gtot[par * 32 + lane] = sum;
+    __threadfence();
+  }
+  cluster.sync();
+  if (warp == 0) { tot[lane] = *reinterpret_cast<const volatile double*>(px.gtot + par * 32 + lane); __syncwarp(); }
+}
+
+__global__ void __launch_bounds__(NT, 1) k_lm_solve(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate, PeerX px) {
   // one cluster (8 CTAs along x) per trajectory of the batch: blockIdx.y selects it
   const LmArgs& A = B.a[blockIdx.y];
   const BlockRec* __restrict__ blocks = A.blocks;
@@ -577,10 +609,12 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const __grid_constant__ Batc
   // one evaluation site (the evaluation body is large; duplicating it costs instruction-cache misses)
   bool first = true;
   long long cyc_eval = 0, cyc_tr = 0;
+  const unsigned long long seq0 = px.world > 1 ? *px.seq : 0ull;
   do {
     const long long c0 = clock64();
     double* tot = s_tot[first ? 0 : 1 - T.acc_buf];
     cluster_evaluate(cluster, blocks, n, rb0, first ? s_x : T.xc, prm.huber_a, s_red, s_part, s_in, tot, pass);
+    if (px.world > 1) peer_allreduce(cluster, px, seq0 + (unsigned long long)pass, tot);   // pass was advanced: tags start at seq0 + 1
     const long long c1 = clock64();
     cyc_eval += c1 - c0;
     if (first && mode == 1) {
@@ -597,6 +631,7 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const __grid_constant__ Batc
     cyc_tr += clock64() - c1;
   } while (T.go);
   if (writer) {
+    if (px.world > 1) *px.seq = seq0 + (unsigned long long)pass;
     tr_finish(T, x7, summary);
     summary->cyc_total = clock64() - clk0;
     summary->cyc_eval = cyc_eval;

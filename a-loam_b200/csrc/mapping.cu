@@ -164,6 +164,65 @@ __global__ void k_grid_fill(GridTable a, const Pt4* __restrict__ pa, GridTable b
   }
 }
 
+// ---- device-side shard split: keeps the points of a cloud that fall in this rank's x-slabs or within one
+// cell of them (the halo), in their original order -- a stable stream compaction in three launches (per-block counts, scan of
+// the block counts, scatter).  `base` (device) is the number of points already kept by earlier chunks of the same cloud.
+__device__ __forceinline__ bool in_shard(float x, float inv_cs, int rank, int world) {
+  const int cx = cell_of(x, inv_cs);
+  return owner_of(cx, world) == rank || owner_of(cx - 1, world) == rank || owner_of(cx + 1, world) == rank;
+}
+__global__ void __launch_bounds__(256) k_shard_count(const float* __restrict__ pts, int stride, int n, float inv_cs, int rank, int world, int* __restrict__ block_cnt) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const bool keep = i < n && in_shard(pts[(size_t)i * stride], inv_cs, rank, world);
+  const int c = __syncthreads_count(keep);
+  if (threadIdx.x == 0) block_cnt[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(1024) k_shard_scan(int* __restrict__ block_cnt, int nblocks, int* __restrict__ base_total) {
+  __shared__ int s_w[32];
+  __shared__ int s_carry;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) s_carry = *base_total;
+  __syncthreads();
+  for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+    const int b = b0 + t;
+    const int v = b < nblocks ? block_cnt[b] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    int wb = 0;
+    for (int k = 0; k < w; ++k) wb += s_w[k];
+    const int carry = s_carry;
+    if (b < nblocks) block_cnt[b] = carry + wb + incl - v;
+    __syncthreads();
+    if (t == 1023) s_carry = carry + wb + incl;
+    __syncthreads();
+  }
+  if (t == 0) *base_total = s_carry;
+}
+__global__ void __launch_bounds__(256) k_shard_scatter(const float* __restrict__ pts, int stride, int n, float inv_cs, int rank, int world,
+                                                       const int* __restrict__ block_off, Pt4* __restrict__ out, int cap, int* __restrict__ err) {
+  __shared__ int s_w[8];
+  const int i = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  Pt4 p = {0.f, 0.f, 0.f, 0.f};
+  bool keep = false;
+  if (i < n) {
+    const float* q = pts + (size_t)i * stride;
+    p.x = q[0]; p.y = q[1]; p.z = q[2]; p.i = q[3];
+    keep = in_shard(p.x, inv_cs, rank, world);
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) s_w[w] = __popc(bal);
+  __syncthreads();
+  int wb = 0;
+  for (int k = 0; k < w; ++k) wb += s_w[k];
+  if (keep) {
+    const int pos = block_off[blockIdx.x] + wb + __popc(bal & ((1u << lane) - 1u));
+    if (pos < cap) out[pos] = p; else atomicOr(err, 1);
+  }
+}
+
 namespace {
 
 __device__ __forceinline__ int warp_incl_scan(int v) {
@@ -638,6 +697,62 @@ int aloam_map_upload_impl(aloam_ctx* c, aloam_cloud_view corner_map, aloam_cloud
   CUDA_CHECK_RET(cudaGetLastError());
   if (c->shard_count > 1) { c->map_global_n[0] = c->h_ints[80]; c->map_global_n[1] = c->h_ints[81]; }
   prof_collect(c);
+  c->have_map = true;
+  return ALOAM_OK;
+}
+
+// aloam_map_upload for a rank of a sharded job that holds the WHOLE submap: the split into owned slabs + halo happens on the
+// device (host views are streamed through in chunks), then the usual index build
+int aloam_map_upload_sharded(aloam_ctx* c, aloam_cloud_view corner_map, aloam_cloud_view surf_map) {
+  if (!c) return ALOAM_ERR_INVALID_ARG;
+  int rc = check_view(corner_map); if (rc) return rc;
+  rc = check_view(surf_map); if (rc) return rc;
+  CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
+  if (c->cfg.max_map_points <= 0) return ALOAM_ERR_CAPACITY;
+  rc = ensure_map_buffers(c); if (rc) return rc;
+  const aloam_cloud_view views[2] = {corner_map, surf_map};
+  // host views go through the stack staging buffer (max_points x 16 bytes), a chunk at a time
+  const float inv_cs = c->map_corner.grid.inv_cs;
+  int* d_cnt = c->d_stack_counts;    // [0], [1]: points kept per cloud ; [2]: error word
+  CUDA_CHECK_RET(cudaMemsetAsync(d_cnt, 0, 16, c->stream));
+  int* d_blocks = reinterpret_cast<int*>(c->d_nbr);   // scratch for the block counts (unused outside a registration)
+  for (int t = 0; t < 2; ++t) {
+    const aloam_cloud_view v = views[t];
+    const bool on_device = v.n > 0 && is_device_ptr(v.data);
+    const int chunk = std::max(1, c->max_points * 4 / std::max(v.stride_floats, 4));
+    for (int off = 0; off < v.n; off += on_device ? v.n : chunk) {
+      const int m = on_device ? v.n : std::min(chunk, v.n - off);
+      const float* src;
+      int stride = v.stride_floats;
+      if (on_device) src = v.data;
+      else {
+        CUDA_CHECK_RET(cudaMemcpyAsync(c->d_stack_corner, v.data + (size_t)off * v.stride_floats, (size_t)m * v.stride_floats * 4, cudaMemcpyHostToDevice, c->stream));
+        src = reinterpret_cast<const float*>(c->d_stack_corner);
+      }
+      const int nb = (m + 255) / 256;
+      if ((size_t)nb * 4 > (size_t)2 * c->max_points * 5 * sizeof(float4)) return ALOAM_ERR_CAPACITY;
+      LAUNCH(c, KID_MAP_GRID, k_shard_count, nb, 256, 0, src, stride, m, inv_cs, c->shard_rank, c->shard_count, d_blocks);
+      LAUNCH(c, KID_MAP_GRID, k_shard_scan, 1, 1024, 0, d_blocks, nb, d_cnt + t);
+      LAUNCH(c, KID_MAP_GRID, k_shard_scatter, nb, 256, 0, src, stride, m, inv_cs, c->shard_rank, c->shard_count, (const int*)d_blocks, c->d_map_pts[t], c->max_map, d_cnt + 2);
+    }
+  }
+  LAUNCH(c, KID_MAP_GRID, k_grid_setup, 1, 32, 0, c->map_corner.grid, (const int*)d_cnt, c->map_surf.grid, (const int*)(d_cnt + 1));
+  map_index_build(c, c->d_map_pts[0], c->d_map_pts[1], c->max_map);
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints + 84, d_cnt, 12, cudaMemcpyDeviceToHost, c->stream));
+  if (c->shard_count > 1) {
+    int* d_two = d_cnt + 2;   // reuse after the error word has been copied out (stream order)
+    CUDA_CHECK_RET(cudaMemcpyAsync(d_two, &c->map_corner.grid.dyn->owned, 4, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_CHECK_RET(cudaMemcpyAsync(d_two + 1, &c->map_surf.grid.dyn->owned, 4, cudaMemcpyDeviceToDevice, c->stream));
+    rc = comm_allreduce_int2(c, d_two); if (rc) return rc;
+    CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints + 80, d_two, 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK_RET(cudaGetLastError());
+  prof_collect(c);
+  if (c->h_ints[86]) return ALOAM_ERR_CAPACITY;   // the shard does not fit cfg.max_map_points
+  c->map_n[0] = c->h_ints[84]; c->map_n[1] = c->h_ints[85];
+  c->map_global_n[0] = c->shard_count > 1 ? c->h_ints[80] : c->map_n[0];
+  c->map_global_n[1] = c->shard_count > 1 ? c->h_ints[81] : c->map_n[1];
   c->have_map = true;
   return ALOAM_OK;
 }

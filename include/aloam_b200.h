@@ -218,6 +218,13 @@ int aloam_mapper_debug_cube(aloam_ctx* ctx, int which, int cube_index, aloam_clo
 int aloam_comm_unique_id(char out128[128]);
 int aloam_comm_init(aloam_ctx* ctx, int rank, int world, const char id128[128]);
 int aloam_shard_slab_cells(void);
+/* as aloam_map_upload, for a rank that holds the WHOLE submap (host or device memory): the rank's shard -- its x-slabs plus the
+ * one-cell halo -- is cut out on the device (stable compaction), then indexed.  cfg.max_map_points must hold the shard. */
+int aloam_map_upload_sharded(aloam_ctx* ctx, aloam_cloud_view corner_map, aloam_cloud_view surf_map);
+/* 1 when the ranks exchange the normal equations through NVLink peer memory INSIDE the LM kernel (one launch per solve; CUDA IPC
+ * mailboxes set up by aloam_comm_init), 0 when they use ncclAllReduce between per-evaluation kernels (no peer access, or the
+ * environment variable ALOAM_NO_PEER is set -- kept for A/B measurements). */
+int aloam_comm_uses_peer_memory(aloam_ctx* ctx);
 
 /* ---- measurement hooks (bench.py): per-kernel CUDA-event timing on the ctx stream, and a launch counter */
 int aloam_profile_enable(aloam_ctx* ctx, int on);

@@ -51,14 +51,24 @@ def main():
         idb = torch.tensor(list(pkg.Aloam.comm_unique_id()), dtype=torch.uint8, device="cuda")
     dist.broadcast(idb, 0)
     ctx.comm_init(rank, world, bytes(idb.cpu().tolist()))
+    path = "NVLink peer memory inside the LM kernel" if ctx.comm_uses_peer_memory() else "ncclAllReduce between per-evaluation kernels"
     ctx.map_upload(shard.shard_cloud(cmap, rank, world), shard.shard_cloud(smap, rank, world))
     x_sh, st_sh = ctx.mapping_register(cs, ss, x0)
+    # the same with the split done on the device from the whole map (aloam_map_upload_sharded), host and device views
+    ctx.map_upload_sharded(cmap, smap)
+    x_dv, _ = ctx.mapping_register(cs, ss, x0)
+    dc, dsf = torch.from_numpy(np.ascontiguousarray(cmap)).cuda(), torch.from_numpy(np.ascontiguousarray(smap)).cuda()
+    ctx.map_upload_sharded_ptr(dc.data_ptr(), dc.shape[0], dsf.data_ptr(), dsf.shape[0])
+    x_dd, _ = ctx.mapping_register(cs, ss, x0)
+    split_ok = bool(np.array_equal(x_dv, x_sh) and np.array_equal(x_dd, x_sh))
     dt = float(np.abs(x_sh[4:] - x_ref[4:]).max()); dq = float(abs(abs(float(x_sh[:4] @ x_ref[:4])) - 1.0))
     counts = torch.tensor([st_sh["n_corner_corr"], st_sh["n_plane_corr"]], device="cuda")
+    if rank == 0:
+        print("exchange path: %s; device-side split equals host split: %s" % (path, split_ok), flush=True)
     print("rank %d/%d: shard map %d+%d of %d+%d pts, blocks total %s (unsharded %d+%d), |dt| %.3e, 1-|dq| %.3e, lm_iters %d vs %d"
           % (rank, world, int(shard.shard_mask(cmap, rank, world).sum()), int(shard.shard_mask(smap, rank, world).sum()), len(cmap), len(smap),
              counts.tolist(), st_ref["n_corner_corr"], st_ref["n_plane_corr"], dt, dq, st_sh["lm_iters"], st_ref["lm_iters"]), flush=True)
-    ok = dt < 1e-9 and dq < 1e-12 and st_sh["lm_iters"] == st_ref["lm_iters"] and counts.tolist() == [st_ref["n_corner_corr"], st_ref["n_plane_corr"]]
+    ok = dt < 1e-9 and dq < 1e-12 and st_sh["lm_iters"] == st_ref["lm_iters"] and counts.tolist() == [st_ref["n_corner_corr"], st_ref["n_plane_corr"]] and split_ok
     # all ranks must hold the identical pose
     xs = torch.tensor(x_sh, device="cuda"); lo = xs.clone(); hi = xs.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
