@@ -82,7 +82,7 @@ static bool peer_setup(aloam_ctx* c, int rank, int world) {
   if (getenv("ALOAM_NO_PEER") || world > ALOAM_MAX_RANKS || !g_nccl.AllGather) return false;
   PeerState* ps = new (std::nothrow) PeerState();
   if (!ps) return false;
-  const size_t box_bytes = (size_t)2 * world * 32 * sizeof(double), flag_bytes = (size_t)2 * world * sizeof(unsigned);
+  const size_t box_bytes = (size_t)2 * world * 32 * 2 * sizeof(unsigned long long), flag_bytes = (size_t)2 * world * sizeof(unsigned);
   const size_t total = box_bytes + flag_bytes + 64 + 2 * 32 * sizeof(double) + 64;
   bool ok = cudaMalloc(&ps->own, total) == cudaSuccess && cudaMemset(ps->own, 0, total) == cudaSuccess;
   cudaIpcMemHandle_t mine;

@@ -149,8 +149,8 @@ struct LmArgs { const BlockRec* blocks; const int* n_blocks_ptr; int n_blocks_ho
 // solve kernel, one launch per solve, no kernel boundary around the 256-byte exchange.  world <= 1: no exchange.
 #define ALOAM_MAX_RANKS 16
 struct PeerX {
-  double* box[ALOAM_MAX_RANKS];             // mailbox of rank r: [2 parities][world][32] doubles (peer-mapped device memory)
-  unsigned* flag[ALOAM_MAX_RANKS];          // flags of rank r:   [2 parities][world]
+  double* box[ALOAM_MAX_RANKS];             // mailbox of rank r: [2 parities][world][32][2] 8-byte words {payload half, tag} (peer-mapped device memory)
+  unsigned* flag[ALOAM_MAX_RANKS];          // (unused by the low-latency protocol)
   unsigned long long* seq;                  // this rank's evaluation counter (device), identical on all ranks by construction
   double* gtot;                             // [2][32] this rank's summed totals (local)
   int* err;                                 // set to 1 when a peer did not answer in time

@@ -543,29 +543,35 @@ __global__ void k_pack_blocks(const double* __restrict__ packed, int n, BlockRec
 
 // all-reduce of the cluster totals over the ranks through peer memory (see PeerX in kernels.h).  Called by every thread of the
 // cluster after cluster_evaluate; on return `tot` holds the sum over all ranks, bit-identical on every rank (rank-order sum).
+// Low-latency protocol: every 8-byte word carries 4 bytes of payload and the 4-byte tag of the evaluation (8-byte stores are
+// atomic over NVLink), so the receiver polls the data words themselves -- no memory fence and no separate flag: one one-way
+// NVLink latency per exchange.  Mailboxes are double-buffered by the parity of the tag: a rank can run at most one evaluation
+// ahead of a peer (it needs the peer's contribution to finish the next one).
 template <typename Cluster>
 __device__ __forceinline__ void peer_allreduce(Cluster& cluster, const PeerX& px, unsigned long long seq, double* tot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int par = (int)(seq & 1ull);
-  const unsigned tag = (unsigned)seq;
+  const unsigned long long tag = (seq & 0xffffffffull) << 32;
   if (cluster.block_rank() == 0 && warp == 0) {
-    const double mine = tot[lane];
-    for (int r = 0; r < px.world; ++r) px.box[r][(par * px.world + px.rank) * 32 + lane] = mine;   // peer stores (NVLink)
-    __threadfence_system();
-    __syncwarp();
-    if (lane < px.world) *reinterpret_cast<volatile unsigned*>(px.flag[lane] + par * px.world + px.rank) = tag;
-    if (lane < px.world) {
-      const volatile unsigned* f = px.flag[px.rank] + par * px.world + lane;
-      const long long t0 = clock64();
-      while (*f != tag) {
-        if (clock64() - t0 > 4000000000ll) { *px.err = 1; break; }   // ~2 s: a peer is gone; never hang the GPU
-      }
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[lane]);
+    const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
+    const size_t slot = ((size_t)(par * px.world + px.rank) * 32 + lane) * 2;
+    for (int r = 0; r < px.world; ++r) {   // peer stores (NVLink); my own mailbox too, so that the sum below is uniform
+      volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(px.box[r]) + slot;
+      dst[0] = w0; dst[1] = w1;
     }
-    __syncwarp();
-    __threadfence_system();
     double sum = 0.0;
-    const volatile double* in = px.box[px.rank] + (size_t)par * px.world * 32;
-    for (int r = 0; r < px.world; ++r) sum += in[r * 32 + lane];
+    const long long t0 = clock64();
+    for (int r = 0; r < px.world; ++r) {
+      const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(px.box[px.rank]) + ((size_t)(par * px.world + r) * 32 + lane) * 2;
+      unsigned long long a, b;
+      for (;;) {
+        a = src[0]; b = src[1];
+        if ((a >> 32) == (tag >> 32) && (b >> 32) == (tag >> 32)) break;
+        if (clock64() - t0 > 4000000000ll) { *px.err = 1; a = b = 0; break; }   // ~2 s: a peer is gone; never hang the GPU
+      }
+      sum += __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+    }
     px.gtot[par * 32 + lane] = sum;
     __threadfence();
   }

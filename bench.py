@@ -260,19 +260,22 @@ def mapping_record(args, synth, pkg, ctx_feat, rank, world, local_rank, dist, to
     cmap, smap = synth.build_map(feats, total_pts)
     my_c, my_s = shard.shard_cloud(cmap, rank, world), shard.shard_cloud(smap, rank, world)
     m_loc = len(my_c) + len(my_s)
-    ctx = pkg.Aloam(n_scans=64, device=local_rank, max_points=200000, max_map_points=max(len(my_c), len(my_s)) + 1024)
+    def make_ctx():
+        cx = pkg.Aloam(n_scans=64, device=local_rank, max_points=200000, max_map_points=max(len(my_c), len(my_s)) + 1024)
+        if world > 1:
+            idb = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idb = torch.tensor(list(pkg.Aloam.comm_unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(idb, 0)
+            cx.comm_init(rank, world, bytes(idb.cpu().tolist()))
+        return cx
+    ctx = make_ctx()
     stacks = []
     for k in synth.MAP_QUERY_SCANS[:Wm + Km]:
         f = ctx_feat.extract_features(synth.scan(SENSOR, k))
         q, t = synth.pose(k)
         x0 = np.concatenate([q, t + np.array([0.05, -0.04, 0.02])])
-        stacks.append((ctx.voxel_filter(f["less_sharp"], 0.4), ctx.voxel_filter(f["less_flat"], 0.8), x0, k))
-    if world > 1:
-        idb = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idb = torch.tensor(list(pkg.Aloam.comm_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idb, 0)
-        ctx.comm_init(rank, world, bytes(idb.cpu().tolist()))
+        stacks.append((ctx_feat.voxel_filter(f["less_sharp"], 0.4), ctx_feat.voxel_filter(f["less_flat"], 0.8), x0, k))
 
     def barrier():
         torch.cuda.synchronize()
@@ -283,7 +286,8 @@ def mapping_record(args, synth, pkg, ctx_feat, rank, world, local_rank, dist, to
     pin_c, pin_s = torch.from_numpy(my_c).pin_memory(), torch.from_numpy(my_s).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # 2 x L2
 
-    def run(host, profile=False):
+    def run(host, profile=False, ctx=None):
+        ctx = ctx or ctx_main
         mc, ms = (pin_c, pin_s) if host else (dev_c, dev_s)
         step_s = []
         poses = []
@@ -306,11 +310,25 @@ def mapping_record(args, synth, pkg, ctx_feat, rank, world, local_rank, dist, to
             dist.all_reduce(ts, op=dist.ReduceOp.MAX)     # every step: the slowest rank
         return float(ts.sum()), poses, launches, st
 
+    ctx_main = ctx
     secs, poses, launches, st = run(False)
     secs_host, poses_host, _, _ = run(True)
     run(False, profile=True)
     prof = ctx.profile_read()
     ctx.profile_enable(False)
+    exchange = "none (1 GPU)"
+    nccl_ab = None
+    if world > 1:
+        exchange = ("NVLink peer memory inside the LM kernel: every rank pushes its 32 partial sums into every rank's mailbox and sums in rank order; one launch per solve"
+                    if ctx.comm_uses_peer_memory() else "ncclAllReduce(32 f64) between per-evaluation kernels")
+        # A/B: the same steps with the NCCL exchange (1 + 4 evaluations x (kernel, ncclAllReduce, kernel) per solve)
+        os.environ["ALOAM_NO_PEER"] = "1"
+        ctx_b = make_ctx()
+        del os.environ["ALOAM_NO_PEER"]
+        secs_b, poses_b, launches_b, _ = run(False, ctx=ctx_b)
+        nccl_ab = {"value": Km / secs_b, "unit": "scans/s", "ms_per_step": 1e3 * secs_b / Km, "gpu_launches": launches_b,
+                   "same_poses_as_peer_path_1e-9": bool(all(np.abs(a - b).max() < 1e-9 for a, b in zip(poses, poses_b)))}
+        ctx_b.close()
     rec = None
     if rank == 0:
         import pyoracle as orc
@@ -343,9 +361,9 @@ def mapping_record(args, synth, pkg, ctx_feat, rank, world, local_rank, dist, to
                "scaling": "weak", "config": {"workload": "HDL-64 scan-to-map (BASELINE.json configs[%d]): %d-point synthetic voxel map (%d corner + %d surf) inside the "
                                                          "250x250x150 m submap volume, %s; per step the rank's shard (%d points) is re-indexed and the scan registered with "
                                                          "2 outer x <=4 inner LM iterations" % (2 if world == 1 else 3, total_pts, len(cmap), len(smap),
-                                                         "1 GPU" if world == 1 else "x-slab shards + 1-cell halo over %d GPUs, one ncclAllReduce(32 f64) per LM evaluation" % world, m_loc),
+                                                         "1 GPU" if world == 1 else "x-slab shards + 1-cell halo over %d GPUs, one all-reduce of the 32 normal-equation sums per LM evaluation" % world, m_loc),
                                             "stack_points": nq, "l2": "256 MB written between steps (shard + index fit in L2 otherwise)"},
-               "gpu_launches": launches,
+               "gpu_launches": launches, "exchange": exchange, "ncclAllReduce_path": nccl_ab,
                "e2e": {"value": Km / secs_host, "unit": "scans/s", "ms_per_step": 1e3 * secs_host / Km, "h2d_bytes_per_step": 16 * m_loc + 16 * nq, "d2h_bytes_per_step": 56 + 4 * 560,
                        "api": "aloam_map_upload + aloam_mapping_register with the shard and the stacks in host memory"},
                "roofline": roofs, "per_kernel": per_kernel,
