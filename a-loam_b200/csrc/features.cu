@@ -336,14 +336,14 @@ __device__ __forceinline__ void warp_sort_segment(const float* curv, int sp, int
   }
 }
 
-// the whole CTA (256 threads) sorts P = 256*E voxel keys ; key_of(i) supplies the key of slot i ; result in keys[0..P)
-template <int E, typename KeyOf>
+// the whole CTA (NT threads) sorts P = NT*E voxel keys ; key_of(i) supplies the key of slot i ; result in keys[0..P)
+template <int E, int NT, typename KeyOf>
 __device__ __forceinline__ void cta_sort_keys(unsigned long long* keys, KeyOf&& key_of) {
   const int t = threadIdx.x;
   unsigned long long v[E];
 #pragma unroll
   for (int s2 = 0; s2 < E; ++s2) v[s2] = key_of(t * E + s2);
-  hybrid_bitonic<E, 256>(v, keys);
+  hybrid_bitonic<E, NT>(v, keys);
 #pragma unroll
   for (int s2 = 0; s2 < E; ++s2) keys[t * E + s2] = v[s2];
   __syncthreads();
@@ -399,21 +399,38 @@ __device__ __forceinline__ void pick_segment(const float* curv, const unsigned c
   };
   n_less = 0; n_flat = 0;
   // ---- largest curvature first (:291-344): eligible = !picked && c > 0.1 ; ties -> larger index (top of the sorted run)
+  // The local scan is written as independent operations (a max tree, then "highest slot equal to the maximum" from a bit
+  // mask) instead of a 12-deep dependent compare / select chain: the warp runs alone on its scheduler, so instruction-level
+  // parallelism is the only latency hiding there is.  An eligible curvature is > 0.1, i.e. its bit pattern is non-zero,
+  // so a warp maximum of 0 means "nobody eligible" and no separate vote is needed.  (A 64-bit shuffle butterfly instead of
+  // the two REDUX was measured: 2.2x slower.)
   unsigned el = 0;
 #pragma unroll
   for (int s2 = 0; s2 < NS; ++s2) if ((double)c[s2] > 0.1) el |= 1u << s2;
   el &= valid;
+  unsigned cb[NS];
+#pragma unroll
+  for (int s2 = 0; s2 < NS; ++s2) cb[s2] = __float_as_uint(c[s2]);
   for (;;) {
     const unsigned e = el & ~pk;
-    unsigned bb = 0; int bs = -1;
+    unsigned kk[NS];
 #pragma unroll
-    for (int s2 = 0; s2 < NS; ++s2) {
-      const unsigned cb = __float_as_uint(c[s2]);
-      if (((e >> s2) & 1u) && cb >= bb) { bb = cb; bs = s2; }   // later slot = larger position wins a tie inside a lane
+    for (int s2 = 0; s2 < NS; ++s2) kk[s2] = ((e >> s2) & 1u) ? cb[s2] : 0u;
+    unsigned t[NS];
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) t[s2] = kk[s2];
+#pragma unroll
+    for (int w2 = 1; w2 < NS; w2 <<= 1) {
+#pragma unroll
+      for (int s2 = 0; s2 + w2 < NS; s2 += 2 * w2) t[s2] = max(t[s2], t[s2 + w2]);
     }
-    if (!__any_sync(0xffffffffu, bs >= 0)) break;
-    const unsigned mx = __reduce_max_sync(0xffffffffu, bs >= 0 ? bb : 0u);
-    const int cand = (bs >= 0 && bb == mx) ? (sp + bs * 32 + lane) : -1;
+    const unsigned bb = t[0];
+    const unsigned mx = __reduce_max_sync(0xffffffffu, bb);
+    if (mx == 0u) break;
+    unsigned mm = 0;
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) mm |= (kk[s2] == mx) ? (1u << s2) : 0u;
+    const int cand = mm ? (sp + (31 - __clz(mm)) * 32 + lane) : -1;   // later slot = larger position wins a tie inside a lane
     const int win = __reduce_max_sync(0xffffffffu, cand);
     if (n_less >= 20) break;          // the 21st eligible point ends the walk unpicked (:312-315)
     const unsigned char r = fb[win];
@@ -428,15 +445,24 @@ __device__ __forceinline__ void pick_segment(const float* curv, const unsigned c
   el &= valid;
   for (;;) {
     const unsigned e = el & ~pk;
-    unsigned bb = 0xffffffffu; int bs = -1;
+    unsigned kk[NS];
 #pragma unroll
-    for (int s2 = 0; s2 < NS; ++s2) {
-      const unsigned cb = __float_as_uint(c[s2]);
-      if (((e >> s2) & 1u) && cb < bb) { bb = cb; bs = s2; }    // earlier slot = smaller position wins a tie inside a lane
+    for (int s2 = 0; s2 < NS; ++s2) kk[s2] = ((e >> s2) & 1u) ? cb[s2] : 0xffffffffu;   // curvatures are finite: their bits are below 0x7f800000
+    unsigned t[NS];
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) t[s2] = kk[s2];
+#pragma unroll
+    for (int w2 = 1; w2 < NS; w2 <<= 1) {
+#pragma unroll
+      for (int s2 = 0; s2 + w2 < NS; s2 += 2 * w2) t[s2] = min(t[s2], t[s2 + w2]);
     }
-    if (!__any_sync(0xffffffffu, bs >= 0)) break;
-    const unsigned mn = __reduce_min_sync(0xffffffffu, bs >= 0 ? bb : 0xffffffffu);
-    const int cand = (bs >= 0 && bb == mn) ? (sp + bs * 32 + lane) : 0x7fffffff;
+    const unsigned bb = t[0];
+    const unsigned mn = __reduce_min_sync(0xffffffffu, bb);
+    if (mn == 0xffffffffu) break;
+    unsigned mm = 0;
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) mm |= (kk[s2] == mn) ? (1u << s2) : 0u;
+    const int cand = mm ? (sp + (__ffs(mm) - 1) * 32 + lane) : 0x7fffffff;   // earlier slot = smaller position wins a tie inside a lane
     const int win = __reduce_min_sync(0xffffffffu, cand);
     if (lane == 0) flat[n_flat] = (unsigned short)win;
     ++n_flat;
@@ -450,13 +476,16 @@ __device__ __forceinline__ void pick_segment(const float* curv, const unsigned c
 __device__ long long g_dbg_cycles[65 * 8];   // per-ring phase time stamps (clock64) of the last k_ring_features launch
 
 // dynamic shared memory layout (bytes), maxr = ring capacity of the context (multiple of 32, <= ALOAM_MAX_RING), P = sort width
-// (next power of two >= maxr, >= 512):  pts 16*maxr | keys 8*P | curv 4*maxr | label maxr | gap 4*(maxr/32+2) | picked same | fb maxr
+// (next power of two >= maxr, >= 1024):  pts 16*maxr | keys 8*P | curv 4*maxr | label maxr | gap 4*(maxr/32+2) | picked same | fb maxr
 // The smaller the ring capacity the more CTAs are resident per SM (2048: 65 KB -> 3 per SM; 4096: 131 KB -> 1 per SM),
 // which is what a batch of trajectories needs.
-__host__ __device__ inline int sort_width(int maxr) { int p = 512; while (p < maxr) p <<= 1; return p; }
+__host__ __device__ inline int sort_width(int maxr) { int p = 1024; while (p < maxr) p <<= 1; return p; }
 size_t ring_features_smem_bytes(int maxr) { return (size_t)maxr * (16 + 4 + 1 + 1) + (size_t)sort_width(maxr) * 8 + 2 * 4 * (maxr / 32 + 2) + 64; }
 
-__global__ void __launch_bounds__(256) k_ring_features(const __grid_constant__ Batch<RingFeatArgs> B, int n_scans, float leaf, int MAXR) {
+// RFT = threads of a ring CTA: six warps walk the segments, all of them load, sort and sum.  512 threads (one CTA per SM) for
+// a single trajectory, where the kernel is a latency chain; 256 threads (two or three CTAs per SM) when a batch fills the GPU.
+template <int RFT>
+__device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B, int n_scans, float leaf, int MAXR) {
   pdl_launch_dependents();   // the next kernel of the stream may become resident (it blocks in pdl_wait())
   const RingFeatArgs& A = B.a[blockIdx.y];   // blockIdx.x = ring, blockIdx.y = trajectory of the batch
   const Pt4* __restrict__ full = A.full;
@@ -481,8 +510,8 @@ __global__ void __launch_bounds__(256) k_ring_features(const __grid_constant__ B
   __shared__ unsigned short s_less[6][20], s_flat[6][4];
   __shared__ int s_nl[6], s_nf[6];
   __shared__ unsigned s_spill[6];
-  __shared__ int s_i[16];
-  __shared__ float s_red[6][8];
+  __shared__ int s_i[RFT / 32];
+  __shared__ float s_red[6][RFT / 32];
 
   const int ring = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g0 = ring_start[ring], nr = ring_start[ring + 1] - g0;
@@ -649,13 +678,12 @@ __global__ void __launch_bounds__(256) k_ring_features(const __grid_constant__ B
     }
     return ((unsigned long long)idx << 12) | (unsigned)i;
   };
-  if (P < 512) P = 512;
+  if (P < 1024) P = 1024;
   __syncthreads();
   if (tid == 0) dbg[4] = clock64();
-  if (P == 512) cta_sort_keys<2>(keys, voxel_key);
-  else if (P == 1024) cta_sort_keys<4>(keys, voxel_key);
-  else if (P == 2048) cta_sort_keys<8>(keys, voxel_key);
-  else cta_sort_keys<16>(keys, voxel_key);
+  if (P == 1024) cta_sort_keys<1024 / RFT, RFT>(keys, voxel_key);
+  else if (P == 2048) cta_sort_keys<2048 / RFT, RFT>(keys, voxel_key);
+  else cta_sort_keys<4096 / RFT, RFT>(keys, voxel_key);
   if (tid == 0) dbg[5] = clock64();
 
   // head flags -> output slots ; each thread owns E consecutive sorted slots
@@ -681,12 +709,19 @@ __global__ void __launch_bounds__(256) k_ring_features(const __grid_constant__ B
   for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) { if (w2 < warp) wbase += s_i[w2]; total += s_i[w2]; }
   int slot = wbase + incl - heads;
   Pt4* o_lf = st_less_flat + (size_t)ring * MAXR;
+  // the heads' sorted positions, compacted: afterwards ONE thread per voxel sums its run (a thread that owned several
+  // single-point voxels and one long run used to serialise them all)
+  int* head_pos = reinterpret_cast<int*>(curv);   // the curvatures are not needed any more ; #voxels <= #points <= MAXR
   for (int k = k0; k < k0 + E && k < P; ++k) {
     unsigned long long key = keys[k];
     if (key == ~0ull) break;
-    unsigned idx = (unsigned)(key >> 12);
-    bool head = overflow || k == 0 || (unsigned)(keys[k - 1] >> 12) != idx;
-    if (!head) continue;
+    const bool head = overflow || k == 0 || (unsigned)(keys[k - 1] >> 12) != (unsigned)(key >> 12);
+    if (head) head_pos[slot++] = k;
+  }
+  __syncthreads();
+  for (int h = tid; h < total; h += blockDim.x) {
+    const int k = head_pos[h];
+    const unsigned idx = (unsigned)(keys[k] >> 12);
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
     int cnt = 0;
     for (int k2 = k; k2 < P; ++k2) {  // float accumulation in sorted order, then divide (pcl::CentroidPoint)
@@ -698,9 +733,16 @@ __global__ void __launch_bounds__(256) k_ring_features(const __grid_constant__ B
     }
     const float nf = (float)cnt;
     Pt4 o; o.x = sx / nf; o.y = sy / nf; o.z = sz / nf; o.i = si / nf;
-    o_lf[slot++] = o;
+    o_lf[h] = o;
   }
   if (tid == 0) { counts[3] = total; dbg[6] = clock64(); }
+}
+
+__global__ void __launch_bounds__(512) k_ring_features(const __grid_constant__ Batch<RingFeatArgs> B, int n_scans, float leaf, int max_ring) {
+  ring_features_body<512>(B, n_scans, leaf, max_ring);
+}
+__global__ void __launch_bounds__(256) k_ring_features_batch(const __grid_constant__ Batch<RingFeatArgs> B, int n_scans, float leaf, int max_ring) {
+  ring_features_body<256>(B, n_scans, leaf, max_ring);
 }
 
 void features_debug_cycles(long long* host64x8) { cudaMemcpyFromSymbol(host64x8, g_dbg_cycles, sizeof(long long) * 64 * 8); }
