@@ -199,6 +199,7 @@ int aloam_create(const aloam_config* cfg_in, aloam_ctx** out) {
   TRY(cudaFuncSetAttribute(k_ring_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_features_smem_bytes(ALOAM_MAX_RING)));
   TRY(cudaFuncSetAttribute(k_ring_features_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_features_smem_bytes(ALOAM_MAX_RING)));
   TRY(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dynamic_smem_bytes()));
+  TRY(cudaFuncSetAttribute(k_lm_solve_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dynamic_smem_bytes()));
   TRY(cudaFuncSetAttribute(k_lm_eval_shard, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dynamic_smem_bytes()));
 #undef TRY
   int rc = aloam_reset_odometry(c);
@@ -305,7 +306,7 @@ void run_register(aloam_ctx* c, int nb, int cur, int last, int sharp_slots, int 
     }
     // within one call the chain association -> LM -> association -> LM is launched with programmatic dependencies
     if (slots > 0) launch_ex(c, KID_ODOM_ASSOC, k_odom_assoc, dim3((slots + 7) / 8, nb), dim3(256), 0, 1, it > 0, aa, op, sharp_slots);
-    launch_lm_batch(c, slots > 0, la, nb, lp, 0, (integrate && last_it) ? 1 : 0);
+    launch_lm_batch(c, slots > 0, la, nb, lp, 0, (integrate && last_it) ? 1 : 0, c->cfg.distortion != 0);
   }
 }
 
@@ -742,7 +743,7 @@ static int run_lm_api(aloam_ctx* c, const double* blocks, int n_blocks, const do
   for (int k = 0; k < 7; ++k) c->h_dbl[k] = x[k];
   CUDA_CHECK_RET(cudaMemcpyAsync(L.d_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
   launch_lm(c, false, (const BlockRec*)L.d_blocks, (const int*)nullptr, n_blocks, L.d_pose, lm_params(c->cfg), L.d_summary, mode,
-            c->d_out28, (double*)nullptr, 0);
+            c->d_out28, (double*)nullptr, 0, true /* blocks from the caller may carry any interpolation ratio */);
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 8, L.d_pose, 56, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 32, c->d_out28, 28 * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, L.d_summary, sizeof(LmSummary), cudaMemcpyDeviceToHost, c->stream));

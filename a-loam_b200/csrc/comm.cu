@@ -54,7 +54,7 @@ void launch_lm_sharded(aloam_ctx* c, const BlockRec* blocks, const int* d_n, dou
     PeerState* ps = static_cast<PeerState*>(c->peer);
     Batch<LmArgs> b = {};
     b.a[0] = LmArgs{blocks, d_n, 0, pose, summary, nullptr, nullptr};
-    launch_lm_batch(c, true, b, 1, lp, 0, 0, &ps->px);
+    launch_lm_batch(c, true, b, 1, lp, 0, 0, true, &ps->px);
     return;
   }
   const int evals = 1 + lp.max_iters;

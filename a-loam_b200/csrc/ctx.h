@@ -166,17 +166,23 @@ void launch_ex(aloam_ctx* c, int kid, K kernel, dim3 grid, dim3 block, size_t sm
 
 // the LM kernel runs as one thread-block cluster per trajectory (distributed-shared-memory reduction, see lm.cu)
 constexpr int kLmCluster = 8;
-inline void launch_lm_batch(aloam_ctx* c, bool pdl, const Batch<LmArgs>& args, int lanes, const LmParams& lp, int mode, int integrate, const PeerX* px = nullptr) {
+// general = false: all blocks have s == 1 and there is no peer exchange (the reference-build odometry, scan-to-map on one GPU)
+inline void launch_lm_batch(aloam_ctx* c, bool pdl, const Batch<LmArgs>& args, int lanes, const LmParams& lp, int mode, int integrate, bool general = false,
+                            const PeerX* px = nullptr) {
+  if (!general && !px) {
+    launch_ex(c, KID_LM_SOLVE, k_lm_solve, dim3(kLmCluster, lanes), dim3(ALOAM_LM_THREADS), lm_dynamic_smem_bytes(), kLmCluster, pdl, args, lp, mode, integrate);
+    return;
+  }
   PeerX none = {};
-  launch_ex(c, KID_LM_SOLVE, k_lm_solve, dim3(kLmCluster, lanes), dim3(ALOAM_LM_THREADS), lm_dynamic_smem_bytes(), kLmCluster, pdl, args, lp, mode, integrate,
+  launch_ex(c, KID_LM_SOLVE, k_lm_solve_x, dim3(kLmCluster, lanes), dim3(ALOAM_LM_THREADS), lm_dynamic_smem_bytes(), kLmCluster, pdl, args, lp, mode, integrate,
             px ? *px : none);
 }
 // single solve: blocks, n (device pointer or host value), pose in / out
 inline void launch_lm(aloam_ctx* c, bool pdl, const BlockRec* blocks, const int* n_ptr, int n_host, double* x7, const LmParams& lp, LmSummary* summary,
-                      int mode, double* out28, double* world7, int integrate) {
+                      int mode, double* out28, double* world7, int integrate, bool general = false) {
   Batch<LmArgs> b = {};
   b.a[0] = LmArgs{blocks, n_ptr, n_host, x7, summary, out28, world7};
-  launch_lm_batch(c, pdl, b, 1, lp, mode, integrate);
+  launch_lm_batch(c, pdl, b, 1, lp, mode, integrate, general);
 }
 
 }  // namespace

@@ -157,7 +157,8 @@ struct PeerX {
   int* err;                                 // set to 1 when a peer did not answer in time
   int rank, world;
 };
-__global__ void k_lm_solve(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate, PeerX px);   // grid (8, lanes), clusters of 8 along x
+__global__ void k_lm_solve(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate);   // every block s == 1, one GPU; grid (8, lanes), clusters of 8 along x
+__global__ void k_lm_solve_x(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate, const __grid_constant__ PeerX px);   // general s and / or peer exchange
 // sharded solve: per-evaluation kernels around an ncclAllReduce (see lm.cu, comm.cu)
 size_t lm_state_bytes();
 size_t lm_dynamic_smem_bytes();   // dynamic shared memory of k_lm_solve / k_lm_eval_shard (opt-in > 48 KB)

@@ -98,10 +98,11 @@ __device__ __noinline__ void start_frame_general(const double* x, const V3& cp, 
   F.m2 = s * (b2 + a2 + a1 * b1 - a2 * b2);
 }
 // Jacobian row for gradient g wrt lp, scaled by sr
+template <bool GENERAL>
 __device__ __forceinline__ void start_row(const StartFrame& F, const V3& g, double sr, double* j) {
   const V3 t = crossd(F.Rp, g);
   V3 h{2.0 * t.x, 2.0 * t.y, 2.0 * t.z};
-  if (F.m1 != 0.0 || F.m2 != 0.0 || F.m0 != 1.0) {
+  if (GENERAL && (F.m1 != 0.0 || F.m2 != 0.0 || F.m0 != 1.0)) {
     const V3 hk = crossd(h, F.k), hkk = crossd(hk, F.k);
     h = V3{F.m0 * h.x + F.m1 * hk.x + F.m2 * hkk.x, F.m0 * h.y + F.m1 * hk.y + F.m2 * hkk.y, F.m0 * h.z + F.m1 * hk.z + F.m2 * hkk.z};
   }
@@ -109,12 +110,15 @@ __device__ __forceinline__ void start_row(const StartFrame& F, const V3& g, doub
   j[3] = F.s * g.x * sr; j[4] = F.s * g.y * sr; j[5] = F.s * g.z * sr;
 }
 
+// GENERAL = false: every block has s == 1 (the reference build: DISTORTION 0 odometry, all scan-to-map blocks); the slerp path
+// is not even compiled in, which keeps the common kernel at its round-1 register budget and code size.
+template <bool GENERAL>
 __device__ __forceinline__ void eval_block(const BlockRec& rb, const double* x, double huber_a, double* acc) {
   // lp = R(q)^s cp + s t   (s == 1 for every block the reference build makes: slerp(1, q) == q)
   const V3 cp{rb.cp[0], rb.cp[1], rb.cp[2]};
   StartFrame F;
-  const double s = rb.type == 2 ? 1.0 : rb.s;
-  if (s == 1.0) {
+  const double s = (!GENERAL || rb.type == 2) ? 1.0 : rb.s;
+  if (!GENERAL || s == 1.0) {
     const V3 u{x[0], x[1], x[2]};
     const double w = x[3];
     V3 uv = crossd(u, cp);
@@ -145,7 +149,7 @@ __device__ __forceinline__ void eval_block(const BlockRec& rb, const double* x, 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       double j[6];
-      start_row(F, ns[k], sr, j);
+      start_row<GENERAL>(F, ns[k], sr, j);
       accumulate_row(acc, j, r[k] * sr);
     }
   } else {
@@ -161,7 +165,7 @@ __device__ __forceinline__ void eval_block(const BlockRec& rb, const double* x, 
     huber_rho(huber_a, r * r, rho0, sr);
     acc[27] += 0.5 * rho0;
     double j[6];
-    start_row(F, n, sr, j);
+    start_row<GENERAL>(F, n, sr, j);
     accumulate_row(acc, j, r * sr);
   }
 }
@@ -453,7 +457,7 @@ __device__ __forceinline__ int first_block_index(unsigned crank, unsigned csize)
 }
 
 constexpr int RS = 30;   // doubles per thread row of the transpose scratch (240 B: 16-byte aligned, bank-conflict free)
-template <typename Cluster>
+template <bool GENERAL, typename Cluster>
 __device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRec* __restrict__ blocks, int n, const BlockRec& rb0,
                                                  const double* xs, double huber_a, double* s_red, double (*s_part)[32],
                                                  double (*s_in)[8][32], double* s_tot, int& pass) {
@@ -470,7 +474,7 @@ __device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRe
     BlockRec rb = rb0;
     for (int b = gtid;;) {
       if (rb.type >= 0) {
-        eval_block(rb, x, huber_a, acc);
+        eval_block<GENERAL>(rb, x, huber_a, acc);
         acc[28] += (rb.type == 0) ? 1.0 : 0.0;
         acc[29] += (rb.type > 0) ? 1.0 : 0.0;
       }
@@ -579,7 +583,8 @@ __device__ __forceinline__ void peer_allreduce(Cluster& cluster, const PeerX& px
   if (warp == 0) { tot[lane] = *reinterpret_cast<const volatile double*>(px.gtot + par * 32 + lane); __syncwarp(); }
 }
 
-__global__ void __launch_bounds__(NT, 1) k_lm_solve(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate, PeerX px) {
+template <bool GENERAL>
+__device__ __forceinline__ void lm_solve_body(const Batch<LmArgs>& B, const LmParams& prm, int mode, int integrate, const PeerX& px) {
   // one cluster (8 CTAs along x) per trajectory of the batch: blockIdx.y selects it
   const LmArgs& A = B.a[blockIdx.y];
   const BlockRec* __restrict__ blocks = A.blocks;
@@ -615,12 +620,12 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const __grid_constant__ Batc
   // one evaluation site (the evaluation body is large; duplicating it costs instruction-cache misses)
   bool first = true;
   long long cyc_eval = 0, cyc_tr = 0;
-  const unsigned long long seq0 = px.world > 1 ? *px.seq : 0ull;
+  const unsigned long long seq0 = (GENERAL && px.world > 1) ? *px.seq : 0ull;
   do {
     const long long c0 = clock64();
     double* tot = s_tot[first ? 0 : 1 - T.acc_buf];
-    cluster_evaluate(cluster, blocks, n, rb0, first ? s_x : T.xc, prm.huber_a, s_red, s_part, s_in, tot, pass);
-    if (px.world > 1) peer_allreduce(cluster, px, seq0 + (unsigned long long)pass, tot);   // pass was advanced: tags start at seq0 + 1
+    cluster_evaluate<GENERAL>(cluster, blocks, n, rb0, first ? s_x : T.xc, prm.huber_a, s_red, s_part, s_in, tot, pass);
+    if (GENERAL && px.world > 1) peer_allreduce(cluster, px, seq0 + (unsigned long long)pass, tot);   // pass was advanced: tags start at seq0 + 1
     const long long c1 = clock64();
     cyc_eval += c1 - c0;
     if (first && mode == 1) {
@@ -637,7 +642,7 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const __grid_constant__ Batc
     cyc_tr += clock64() - c1;
   } while (T.go);
   if (writer) {
-    if (px.world > 1) *px.seq = seq0 + (unsigned long long)pass;
+    if (GENERAL && px.world > 1) *px.seq = seq0 + (unsigned long long)pass;
     tr_finish(T, x7, summary);
     summary->cyc_total = clock64() - clk0;
     summary->cyc_eval = cyc_eval;
@@ -669,6 +674,17 @@ __global__ void __launch_bounds__(NT, 1) k_lm_solve(const __grid_constant__ Batc
   // no trailing cluster barrier: the only remote accesses are the pushes that precede each pass's barrier
 }
 
+// the common solve: every block has s == 1, one GPU
+__global__ void __launch_bounds__(NT, 1) k_lm_solve(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate) {
+  PeerX none; none.world = 0; none.rank = 0; none.seq = nullptr; none.gtot = nullptr; none.err = nullptr;
+  lm_solve_body<false>(B, prm, mode, integrate, none);
+}
+// the general solve: blocks with an interpolation ratio s != 1 (DISTORTION build, blocks handed in through the C ABI) and / or the
+// all-reduce of every evaluation over NVLink peer memory (sharded scan-to-map)
+__global__ void __launch_bounds__(NT, 1) k_lm_solve_x(const __grid_constant__ Batch<LmArgs> B, LmParams prm, int mode, int integrate, const __grid_constant__ PeerX px) {
+  lm_solve_body<true>(B, prm, mode, integrate, px);
+}
+
 size_t lm_dynamic_smem_bytes() { return (size_t)NT * RS * sizeof(double); }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -696,7 +712,7 @@ __global__ void __launch_bounds__(NT, 1) k_lm_eval_shard(const BlockRec* __restr
   int pass = 0;
   if (active) {
     const BlockRec rb0 = load_first_block(blocks, n, cluster.block_rank());
-    cluster_evaluate(cluster, blocks, n, rb0, s_x, huber_a, s_red, s_part, s_in, s_tot, pass);
+    cluster_evaluate<true>(cluster, blocks, n, rb0, s_x, huber_a, s_red, s_part, s_in, s_tot, pass);
     if (cluster.block_rank() == 0 && tid < 32) local32[tid] = tid < RS ? s_tot[tid] : 0.0;
   } else if (cluster.block_rank() == 0 && tid < 32) {
     local32[tid] = 0.0;
