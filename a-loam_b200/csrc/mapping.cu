@@ -80,7 +80,9 @@ __global__ void k_grid_clear(GridTable a, GridTable b) {
   for (int i = gtid; i <= mb; i += gstride) b.slots[i] = empty;
 }
 
-// blockIdx.y selects the cloud (0 = a, 1 = b)
+// blockIdx.y selects the cloud (0 = a, 1 = b).  The lanes of a warp that fall into the same cell form a group (__match_any):
+// maps come out of voxel filters in voxel order, so neighbouring points share cells and ONE lane per group claims the slot and
+// adds the group's size -- about half the atomics of one-per-point.
 __global__ void k_grid_insert(GridTable a, const Pt4* __restrict__ pa, GridTable b, const Pt4* __restrict__ pb, int shard_rank,
                               int shard_count) {
   pdl_launch_dependents();
@@ -89,24 +91,34 @@ __global__ void k_grid_insert(GridTable a, const Pt4* __restrict__ pa, GridTable
   const Pt4* __restrict__ pts = blockIdx.y == 0 ? pa : pb;
   const int n = g.dyn->n;
   const unsigned mask = g.dyn->mask;
+  const unsigned lane = lane_id();
   int owned = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const Pt4 p = pts[i];
-    const int cx = cell_of(p.x, g.inv_cs);
-    const unsigned long long key = cell_key(cx, cell_of(p.y, g.inv_cs), cell_of(p.z, g.inv_cs));
-    unsigned h = hash_key(key) & mask;
-    for (;;) {
-      const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&g.slots[h]), kEmpty, key);
-      if (prev == kEmpty || prev == key) break;
-      h = (h + 1) & mask;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {   // whole warps iterate together
+    const int i = i0 + (int)lane;
+    unsigned long long key = kEmpty;
+    int cx = 0;
+    if (i < n) {
+      const Pt4 p = pts[i];
+      cx = cell_of(p.x, g.inv_cs);
+      key = cell_key(cx, cell_of(p.y, g.inv_cs), cell_of(p.z, g.inv_cs));
     }
-    atomicAdd(reinterpret_cast<int*>(&g.slots[h]) + 2, 1);
-    if (shard_count > 1 && owner_of(cx, shard_count) == shard_rank) ++owned;
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    if (i < n && lane == (unsigned)(__ffs(grp) - 1)) {
+      unsigned h = hash_key(key) & mask;
+      for (;;) {
+        const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&g.slots[h]), kEmpty, key);
+        if (prev == kEmpty || prev == key) break;
+        h = (h + 1) & mask;
+      }
+      atomicAdd(reinterpret_cast<int*>(&g.slots[h]) + 2, __popc(grp));
+    }
+    if (i < n && shard_count > 1 && owner_of(cx, shard_count) == shard_rank) ++owned;
   }
   if (shard_count > 1) {   // points in cells this rank owns (the halo excluded): the global map size is their sum over ranks
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) owned += __shfl_xor_sync(0xffffffffu, owned, d);
-    if ((threadIdx.x & 31) == 0 && owned) atomicAdd(&g.dyn->owned, owned);
+    if (lane == 0 && owned) atomicAdd(&g.dyn->owned, owned);
   }
 }
 
@@ -154,13 +166,26 @@ __global__ void k_grid_fill(GridTable a, const Pt4* __restrict__ pa, GridTable b
   const Pt4* __restrict__ pts = blockIdx.y == 0 ? pa : pb;
   const int n = g.dyn->n;
   const unsigned mask = g.dyn->mask;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const Pt4 p = pts[i];
-    const unsigned long long key = cell_key(cell_of(p.x, g.inv_cs), cell_of(p.y, g.inv_cs), cell_of(p.z, g.inv_cs));
-    unsigned h = hash_key(key) & mask;
-    while (*reinterpret_cast<const volatile unsigned long long*>(&g.slots[h]) != key) h = (h + 1) & mask;   // inserted by k_grid_insert
-    const int pos = atomicAdd(reinterpret_cast<int*>(&g.slots[h]) + 3, 1);
-    g.gpts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  const unsigned lane = lane_id();
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
+    const int i = i0 + (int)lane;
+    unsigned long long key = kEmpty;
+    Pt4 p = {0.f, 0.f, 0.f, 0.f};
+    if (i < n) {
+      p = pts[i];
+      key = cell_key(cell_of(p.x, g.inv_cs), cell_of(p.y, g.inv_cs), cell_of(p.z, g.inv_cs));
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (i < n && (int)lane == leader) {   // one probe and one atomic per group of lanes in the same cell
+      unsigned h = hash_key(key) & mask;
+      while (*reinterpret_cast<const volatile unsigned long long*>(&g.slots[h]) != key) h = (h + 1) & mask;   // inserted by k_grid_insert
+      base = atomicAdd(reinterpret_cast<int*>(&g.slots[h]) + 3, __popc(grp));
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < n) g.gpts[base + __popc(grp & ((1u << lane) - 1u))] = make_float4(p.x, p.y, p.z, __int_as_float(i));
   }
 }
 
@@ -636,11 +661,11 @@ void map_register_device(aloam_ctx* c, const Pt4* d_corner_stack, const Pt4* d_s
                          double* d_pose, bool want_fits) {
   const LmParams lp = lm_params(c->cfg);
   const int kb = std::max(1, std::min((nq_upper + 7) / 8, kGridCtas));
-  const int fb = std::max(1, (nq_upper + 127) / 128);
+  const int fb = std::max(1, (nq_upper + 31) / 32);   // one warp per CTA: a few thousand serial double-precision fits spread over all SMs
   for (int it = 0; it < c->cfg.outer_iters; ++it) {
     launch_ex(c, KID_MAP_KNN5, k_map_knn5, dim3(kb), dim3(256), 0, 1, it > 0, d_corner_stack, d_surf_stack, d_counts3, c->map_corner, c->map_surf,
               (const double*)d_pose, c->d_nbr, c->shard_rank, c->shard_count);
-    launch_ex(c, KID_MAP_FIT, k_map_fit, dim3(fb), dim3(128), 0, 1, true, d_corner_stack, d_surf_stack, d_counts3, (const float4*)c->d_nbr,
+    launch_ex(c, KID_MAP_FIT, k_map_fit, dim3(fb), dim3(32), 0, 1, true, d_corner_stack, d_surf_stack, d_counts3, (const float4*)c->d_nbr,
               c->d_map_blocks, want_fits ? c->d_fits : (double*)nullptr);
     if (c->shard_count <= 1)
       launch_lm(c, true, (const BlockRec*)c->d_map_blocks, d_counts3 + 2, 0, d_pose, lp, c->d_map_summary + (it & 3), 0, (double*)nullptr, (double*)nullptr, 0);
@@ -806,7 +831,7 @@ int aloam_mapping_associate(aloam_ctx* c, aloam_cloud_view corner_stack, aloam_c
   if (nq > 0) {
     LAUNCH(c, KID_MAP_KNN5, k_map_knn5, std::min((nq + 7) / 8, kGridCtas), 256, 0, c->d_stack_corner, c->d_stack_surf, c->d_stack_counts, c->map_corner,
            c->map_surf, c->d_map_pose, c->d_nbr, c->shard_rank, c->shard_count);
-    LAUNCH(c, KID_MAP_FIT, k_map_fit, (nq + 127) / 128, 128, 0, c->d_stack_corner, c->d_stack_surf, c->d_stack_counts, c->d_nbr, c->d_map_blocks, c->d_fits);
+    LAUNCH(c, KID_MAP_FIT, k_map_fit, (nq + 31) / 32, 32, 0, c->d_stack_corner, c->d_stack_surf, c->d_stack_counts, c->d_nbr, c->d_map_blocks, c->d_fits);
     CUDA_CHECK_RET(cudaMemcpyAsync(fits, c->d_fits, (size_t)nq * 14 * 8, cudaMemcpyDeviceToHost, c->stream));
   }
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));

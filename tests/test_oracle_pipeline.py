@@ -121,3 +121,35 @@ def test_transform_helpers(orc):
     qm2, tm2 = np.zeros(4), np.zeros(3)
     L.orc_transform_update(dp(x), dp(qo), dp(to), dp(qm2), dp(tm2))
     assert np.allclose(qm2, qm, atol=1e-12) and np.allclose(tm2, tm, atol=1e-12)   # laserMapping.cpp:142-152 round trip
+
+
+def test_distortion_mode_of_the_oracle(orc, synth, scans):
+    """#define DISTORTION 1 (laserOdometry.cpp:59): per-point ratio s = (intensity - int(intensity)) / SCAN_PERIOD in
+    TransformToStart and the residual blocks; TransformToEnd (:133-148) maps the sweep-start frame to the sweep-end frame"""
+    ns, _, mr = synth.SENSORS["VLP-16"][:3]
+    f0 = orc.Features(scans("VLP-16", 0), ns, mr)
+    f1 = orc.Features(scans("VLP-16", 1), ns, mr)
+    q = np.array([0.003, -0.002, 0.01, 1.0]); q /= np.linalg.norm(q)
+    t = np.array([0.75, 0.02, -0.01])
+    # s == 1 everywhere: TransformToEnd(p) = q^-1 (q p + t - t) = p up to float rounding, intensity -> scan id
+    same = orc.transform_to_end(f1.less_flat, q, t, distortion=False)
+    assert np.abs(same[:, :3] - f1.less_flat[:, :3]).max() < 2e-5
+    assert np.array_equal(same[:, 3], np.floor(f1.less_flat[:, 3]))
+    # with the ratio: a point at the sweep end (s -> 1) stays, a point at the sweep start (s -> 0) moves by about q^-1 (p - t) - p
+    moved = orc.transform_to_end(f1.less_flat, q, t, distortion=True)
+    s = (f1.less_flat[:, 3] - np.floor(f1.less_flat[:, 3])) / 0.1
+    d = np.linalg.norm(moved[:, :3] - f1.less_flat[:, :3], axis=1)
+    late, early = s > 0.95, s < 0.05
+    assert late.any() and early.any() and d[late].max() < 0.08 and d[early].min() > 0.5
+    # the blocks carry the ratio, and the association differs from the DISTORTION 0 one
+    od0, od1 = orc.Odometry(), orc.Odometry(distortion=True)
+    for od in (od0, od1):
+        od.set_last(f0.less_sharp, f0.less_flat)
+    _, _, b0 = od0.associate(f1.sharp, f1.flat, q, t)
+    _, _, b1 = od1.associate(f1.sharp, f1.flat, q, t)
+    assert np.all(b0[:, 10] == 1.0) and b1[:, 10].min() < 0.2 and b1[:, 10].max() <= 1.0
+    # analytic evaluation falls back to autodiff for s != 1 inside the oracle: both flags give the same normal equations
+    x = np.concatenate([q, t])
+    Ja, ga, ca = orc.normal_equations(b1, x, autodiff=True)
+    Jb, gb, cb = orc.normal_equations(b1, x, autodiff=False)
+    assert np.array_equal(Ja, Jb) and ca == cb
