@@ -807,10 +807,13 @@ int aloam_debug_lm_cycles(aloam_ctx* c, long long* out, int outer) {
   for (int it = 0; it < outer && it < 4; ++it) { const LmSummary& s = c->h_summary[it]; out[5 * it] = s.cyc_total; out[5 * it + 1] = s.cyc_eval; out[5 * it + 2] = s.cyc_chol; out[5 * it + 3] = s.cyc_plus; out[5 * it + 4] = s.cyc_grad; }
   return ALOAM_OK;
 }
+// out == NULL arms the time stamps of k_ring_features (they are off by default), otherwise reads them (65 x 8 + 12 values) and disarms
 int aloam_debug_feature_cycles(aloam_ctx* c, long long* out64x8) {
-  if (!c || !out64x8) return ALOAM_ERR_INVALID_ARG;
+  if (!c) return ALOAM_ERR_INVALID_ARG;
   cudaSetDevice(c->cfg.device);
+  if (!out64x8) { features_debug_enable(1); return ALOAM_OK; }
   features_debug_cycles(out64x8);
+  features_debug_enable(0);
   return ALOAM_OK;
 }
 

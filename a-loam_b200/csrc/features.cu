@@ -20,6 +20,12 @@
 
 namespace aloam {
 
+// debug time stamps (SM clock), taken only when a tool arms them with aloam_debug_feature_cycles(ctx, NULL): g_dbg_pick = ring 8:
+// [0..3] one segment walk (entry, after the register loads, after the sharp walk, after the flat walk), [4..5] picks made,
+// [6..7] after the speculative pass / after the re-run loop, [8..19] (start, end) of the six segment walks
+__device__ long long g_dbg_pick[8 + 12];
+__device__ int g_dbg_stamp = 0;
+
 namespace {
 
 constexpr int CT = 256;        // threads per CTA in classify / scatter
@@ -380,6 +386,8 @@ __device__ __forceinline__ void pick_segment(const float* curv, const unsigned c
                                              unsigned short* less, int& n_less, unsigned short* flat, int& n_flat,
                                              unsigned& spill_out) {
   const int lane = threadIdx.x & 31;
+  const bool dbg_me = g_dbg_stamp != 0 && blockIdx.x == 8 && blockIdx.y == 0 && (threadIdx.x >> 5) == 3 && lane == 0;
+  if (dbg_me) g_dbg_pick[0] = clock64();
   float c[NS];
   unsigned valid = 0, pk = 0;   // bit s: slot s is inside the segment / is marked in cloudNeighborPicked
 #pragma unroll
@@ -398,6 +406,7 @@ __device__ __forceinline__ void pick_segment(const float* curv, const unsigned c
     if (hi > ep) spill_out |= ((1u << (hi - ep)) - 1u) & ~((lo > ep + 1) ? ((1u << (lo - ep - 1)) - 1u) : 0u);
   };
   n_less = 0; n_flat = 0;
+  if (dbg_me) g_dbg_pick[1] = clock64();
   // ---- largest curvature first (:291-344): eligible = !picked && c > 0.1 ; ties -> larger index (top of the sorted run)
   // The local scan is written as independent operations (a max tree, then "highest slot equal to the maximum" from a bit
   // mask) instead of a 12-deep dependent compare / select chain: the warp runs alone on its scheduler, so instruction-level
@@ -438,6 +447,7 @@ __device__ __forceinline__ void pick_segment(const float* curv, const unsigned c
     ++n_less;
     mark(win - (r >> 4), win + (r & 15));
   }
+  if (dbg_me) g_dbg_pick[2] = clock64();
   // ---- smallest curvature first (:346-390): eligible = !picked && c < 0.1 ; ties -> smaller index ; 4th pick not marked
   el = 0;
 #pragma unroll
@@ -470,6 +480,7 @@ __device__ __forceinline__ void pick_segment(const float* curv, const unsigned c
     const unsigned char r = fb[win];
     mark(win - (r >> 4), win + (r & 15));
   }
+  if (dbg_me) { g_dbg_pick[3] = clock64(); g_dbg_pick[4] = n_less; g_dbg_pick[5] = n_flat; }
   __syncwarp();
 }
 
@@ -514,6 +525,7 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
   __shared__ float s_red[6][RFT / 32];
 
   const int ring = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool stamp = g_dbg_stamp != 0;
   const int g0 = ring_start[ring], nr = ring_start[ring + 1] - g0;
   int* counts = st_counts + ring * 4;
   if (nr > MAXR) {
@@ -531,7 +543,7 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
   while (P < nr) P <<= 1;
 
   long long* dbg = g_dbg_cycles + (blockIdx.y == 0 ? ring : 64) * 8;   // lane 0 only; the other lanes write a dummy row
-  if (tid == 0) dbg[0] = clock64();
+  if (stamp && tid == 0) dbg[0] = clock64();
   for (int i = tid; i < nr; i += blockDim.x) pts[i] = full[g0 + i];
   for (int i = tid; i < MAXR / 32 + 2; i += blockDim.x) { gap[i] = 0; picked[i] = 0; }
   __syncthreads();
@@ -567,7 +579,7 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     fb[i] = v;
   }
   __syncthreads();
-  if (tid == 0) { dbg[1] = clock64(); dbg[2] = dbg[1]; }
+  if (stamp && tid == 0) { dbg[1] = clock64(); dbg[2] = dbg[1]; }
 
   // greedy picks (:291-390).  std::sort + walk == repeatedly taking the arg-max (arg-min) of the still-eligible
   // points under the (curvature, index) order, so no sort is needed: one warp keeps a segment's curvatures in
@@ -583,10 +595,17 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     else pick_segment<24>(curv, fb, sp, ep, spill_in, s_less[w], nl, s_flat[w], nf, so);
     if (lane == 0) { s_nl[w] = nl; s_nf[w] = nf; s_spill[w] = so; }
   };
-  if (warp < 6) run_segment(warp, 0u);
+  // Warps 1..6 walk the six segments.  NOT warp 0: it carries the thread that writes the debug stamps, and measured on B200 a
+  // segment walked by warp 0 took 30 k cycles against 9-13 k on any other warp (its REDUX go through the divergent-warp path).
+  if (warp >= 1 && warp <= 6) {
+    if (stamp && lane == 0 && blockIdx.x == 8 && blockIdx.y == 0) g_dbg_pick[8 + 2 * (warp - 1)] = clock64();
+    run_segment(warp - 1, 0u);
+    if (stamp && lane == 0 && blockIdx.x == 8 && blockIdx.y == 0) g_dbg_pick[9 + 2 * (warp - 1)] = clock64();
+  }
   __syncthreads();
+  if (stamp && tid == 0 && blockIdx.x == 8 && blockIdx.y == 0) g_dbg_pick[6] = clock64();
   for (int w = 1; w < 6; ++w) {
-    if (warp == w) {
+    if (warp == w + 1) {
       const unsigned in = s_spill[w - 1];
       if (in != 0u) {
         const int sp = s_loc + span * w / 6;
@@ -601,6 +620,7 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     }
     __syncthreads();
   }
+  if (stamp && tid == 0 && blockIdx.x == 8 && blockIdx.y == 0) g_dbg_pick[7] = clock64();
   // labels (:303,309,355) and ring-ordered outputs (ring, segment, pick order) from the per-segment lists
   if (tid < 6 * 24) {
     const int w = tid / 24, i = tid % 24;
@@ -624,7 +644,7 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     }
   }
   __syncthreads();
-  if (tid == 0) dbg[3] = clock64();
+  if (stamp && tid == 0) dbg[3] = clock64();
   if (dbg_label) for (int i = tid; i < nr; i += blockDim.x) dbg_label[g0 + i] = label[i];
 
   // ---- less-flat candidates = positions [s_loc, e_loc-1] with label <= 0 (:392-398), voxel-filtered per ring (:401-407)
@@ -680,11 +700,11 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
   };
   if (P < 1024) P = 1024;
   __syncthreads();
-  if (tid == 0) dbg[4] = clock64();
+  if (stamp && tid == 0) dbg[4] = clock64();
   if (P == 1024) cta_sort_keys<1024 / RFT, RFT>(keys, voxel_key);
   else if (P == 2048) cta_sort_keys<2048 / RFT, RFT>(keys, voxel_key);
   else cta_sort_keys<4096 / RFT, RFT>(keys, voxel_key);
-  if (tid == 0) dbg[5] = clock64();
+  if (stamp && tid == 0) dbg[5] = clock64();
 
   // head flags -> output slots ; each thread owns E consecutive sorted slots
   const int E = P / (int)blockDim.x > 0 ? P / (int)blockDim.x : 1;
@@ -735,7 +755,7 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     Pt4 o; o.x = sx / nf; o.y = sy / nf; o.z = sz / nf; o.i = si / nf;
     o_lf[h] = o;
   }
-  if (tid == 0) { counts[3] = total; dbg[6] = clock64(); }
+  if (tid == 0) { counts[3] = total; if (stamp) dbg[6] = clock64(); }
 }
 
 __global__ void __launch_bounds__(512) k_ring_features(const __grid_constant__ Batch<RingFeatArgs> B, int n_scans, float leaf, int max_ring) {
@@ -745,7 +765,11 @@ __global__ void __launch_bounds__(256) k_ring_features_batch(const __grid_consta
   ring_features_body<256>(B, n_scans, leaf, max_ring);
 }
 
-void features_debug_cycles(long long* host64x8) { cudaMemcpyFromSymbol(host64x8, g_dbg_cycles, sizeof(long long) * 64 * 8); }
+void features_debug_enable(int on) { cudaMemcpyToSymbol(g_dbg_stamp, &on, sizeof(int)); }
+void features_debug_cycles(long long* host64x8) {
+  cudaMemcpyFromSymbol(host64x8, g_dbg_cycles, sizeof(long long) * 64 * 8);
+  cudaMemcpyFromSymbol(host64x8 + 64 * 8, g_dbg_pick, sizeof(long long) * 20);   // the buffer of the caller holds 65 rows
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // ring-ordered concatenation of the staged per-ring outputs ; also ring_start tables of the two "less" clouds

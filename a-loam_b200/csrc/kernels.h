@@ -22,7 +22,8 @@ template <typename T> struct Batch { T a[ALOAM_MAX_BATCH]; };
 
 // ---- features.cu
 size_t ring_features_smem_bytes(int max_ring);
-void features_debug_cycles(long long* host64x8);
+void features_debug_cycles(long long* host64x8);   // 65 rows of 8 + 12: per-ring phase stamps, pick-walk stamps of ring 8
+void features_debug_enable(int on);
 struct ClassifyArgs { const float* raw; int n, stride; int8_t* ring_out; int* hist; ScanScalars* sc; };
 struct RingScanArgs { const float* raw; int stride, nblocks; const int* hist; int* offsets; int* ring_start; int* scan_start; int* scan_end;
                       ScanScalars* sc; ScanScalars* sc_next; int* n_full_out; };
