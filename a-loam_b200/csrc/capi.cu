@@ -196,8 +196,8 @@ int aloam_create(const aloam_config* cfg_in, aloam_ctx** out) {
   TRY(halloc(&c->h_summary, (size_t)4 * c->n_lanes)); TRY(halloc(&c->h_sc, (size_t)3 * c->n_lanes));
   TRY(cudaMemset(c->d_err, 0, 16));
   // function attributes are process-wide: always opt in to the largest ring capacity, whatever this context uses
-  TRY(cudaFuncSetAttribute(k_ring_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_features_smem_bytes(ALOAM_MAX_RING)));
-  TRY(cudaFuncSetAttribute(k_ring_features_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_features_smem_bytes(ALOAM_MAX_RING)));
+  TRY(cudaFuncSetAttribute(k_ring_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_features_smem_bytes(ALOAM_MAX_RING, true)));
+  TRY(cudaFuncSetAttribute(k_ring_features_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_features_smem_bytes(ALOAM_MAX_RING, false)));
   TRY(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dynamic_smem_bytes()));
   TRY(cudaFuncSetAttribute(k_lm_solve_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dynamic_smem_bytes()));
   TRY(cudaFuncSetAttribute(k_lm_eval_shard, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dynamic_smem_bytes()));
@@ -249,8 +249,8 @@ int run_features_b1(aloam_ctx* c, int nb, int buf, int sc_slot) {
     fa.a[l] = RingFeatArgs{L.d_full[buf], L.d_ring_start[buf], L.st_sharp[buf], L.st_less_sharp[buf], L.st_flat[buf], L.st_less_flat[buf], L.st_counts[buf],
                            l == 0 ? c->d_curv : nullptr, l == 0 ? c->d_label : nullptr, L.d_sc + sc_slot};
   }
-  if (nb == 1) LAUNCH(c, KID_RING_FEATURES, k_ring_features, dim3(c->cfg.n_scans, nb), 512, ring_features_smem_bytes(c->max_ring), fa, c->cfg.n_scans, 0.2f, c->max_ring);
-  else LAUNCH(c, KID_RING_FEATURES, k_ring_features_batch, dim3(c->cfg.n_scans, nb), 256, ring_features_smem_bytes(c->max_ring), fa, c->cfg.n_scans, 0.2f, c->max_ring);
+  if (nb == 1) LAUNCH(c, KID_RING_FEATURES, k_ring_features, dim3(c->cfg.n_scans, nb), 512, ring_features_smem_bytes(c->max_ring, true), fa, c->cfg.n_scans, 0.2f, c->max_ring);
+  else LAUNCH(c, KID_RING_FEATURES, k_ring_features_batch, dim3(c->cfg.n_scans, nb), 256, ring_features_smem_bytes(c->max_ring, false), fa, c->cfg.n_scans, 0.2f, c->max_ring);
   CUDA_CHECK_RET(cudaGetLastError());
   return ALOAM_OK;
 }

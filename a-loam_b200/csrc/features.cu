@@ -355,6 +355,50 @@ __device__ __forceinline__ void cta_sort_keys(unsigned long long* keys, KeyOf&& 
   __syncthreads();
 }
 
+// Merge sort of P = NT*E 64-bit keys by the whole CTA: every warp sorts its 32*E keys in registers / shuffles (the bitonic network
+// above on one warp), then log2(NT/32) merge levels over two shared-memory buffers: every thread owns E consecutive outputs of a
+// merged pair, finds where they start in the two runs with a merge-path binary search and merges E keys sequentially.
+// 2048 keys on 512 threads: 28 warp-local stages + 4 levels of (11-step search + 4 picks), against 66 CTA-wide bitonic stages of
+// which 10 go through shared memory with two barriers each.  Returns the buffer that holds the sorted keys.
+template <int E, int NT, typename KeyOf>
+__device__ __forceinline__ unsigned long long* cta_merge_sort(unsigned long long* bufA, unsigned long long* bufB, KeyOf&& key_of) {
+  const int t = threadIdx.x, lane = t & 31;
+  constexpr int P = NT * E, RUN0 = 32 * E;
+  unsigned long long v[E];
+#pragma unroll
+  for (int s2 = 0; s2 < E; ++s2) v[s2] = key_of(t * E + s2);
+  hybrid_bitonic<E, 32>(v, nullptr);   // warp-local: element index inside the warp = lane * E + slot
+#pragma unroll
+  for (int s2 = 0; s2 < E; ++s2) bufA[(t >> 5) * RUN0 + lane * E + s2] = v[s2];
+  __syncthreads();
+  unsigned long long* src = bufA;
+  unsigned long long* dst = bufB;
+#pragma unroll 1
+  for (int L = RUN0; L < P; L <<= 1) {
+    const int o = t * E;                 // first output slot of this thread
+    const int pair0 = o & ~(2 * L - 1);  // start of the pair of runs it falls into
+    const int d = o - pair0;             // diagonal inside the merged pair
+    const unsigned long long* X = src + pair0;
+    const unsigned long long* Y = src + pair0 + L;
+    int lo = max(0, d - L), hi = min(d, L);
+    while (lo < hi) {                    // smallest a with X[a] >= Y[d - 1 - a]  (ties: X first, the keys of real points are unique)
+      const int mid = (lo + hi) >> 1;
+      if (X[mid] <= Y[d - 1 - mid]) lo = mid + 1; else hi = mid;
+    }
+    int a = lo, b = d - lo;
+    unsigned long long xa = a < L ? X[a] : ~0ull, yb = b < L ? Y[b] : ~0ull;
+#pragma unroll
+    for (int s2 = 0; s2 < E; ++s2) {
+      const bool take_x = b >= L || (a < L && xa <= yb);
+      dst[o + s2] = take_x ? xa : yb;
+      if (take_x) { ++a; xa = a < L ? X[a] : ~0ull; } else { ++b; yb = b < L ? Y[b] : ~0ull; }
+    }
+    __syncthreads();
+    unsigned long long* tmp = src; src = dst; dst = tmp;
+  }
+  return src;
+}
+
 // gap bit i = |p[i+1]-p[i]|^2 > 0.05 (float expression compared with the double literal, :324)
 __device__ __forceinline__ unsigned bits5(const unsigned* m, int from) {  // 5 bits starting at bit `from`
   unsigned long long two = (unsigned long long)m[from >> 5] | ((unsigned long long)m[(from >> 5) + 1] << 32);
@@ -491,7 +535,10 @@ __device__ long long g_dbg_cycles[65 * 8];   // per-ring phase time stamps (cloc
 // The smaller the ring capacity the more CTAs are resident per SM (2048: 65 KB -> 3 per SM; 4096: 131 KB -> 1 per SM),
 // which is what a batch of trajectories needs.
 __host__ __device__ inline int sort_width(int maxr) { int p = 1024; while (p < maxr) p <<= 1; return p; }
-size_t ring_features_smem_bytes(int maxr) { return (size_t)maxr * (16 + 4 + 1 + 1) + (size_t)sort_width(maxr) * 8 + 2 * 4 * (maxr / 32 + 2) + 64; }
+// merge = the 512-thread kernel, which sorts by merging and needs a second key buffer (placed after everything else)
+size_t ring_features_smem_bytes(int maxr, bool merge) {
+  return (size_t)maxr * (16 + 4 + 1 + 1) + (size_t)sort_width(maxr) * 8 * (merge ? 2 : 1) + 2 * 4 * (maxr / 32 + 2) + 64;
+}
 
 // RFT = threads of a ring CTA: six warps walk the segments, all of them load, sort and sum.  512 threads (one CTA per SM) for
 // a single trajectory, where the kernel is a latency chain; 256 threads (two or three CTAs per SM) when a batch fills the GPU.
@@ -518,6 +565,7 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
   unsigned* gap = reinterpret_cast<unsigned*>(label + MAXR);
   unsigned* picked = gap + (MAXR / 32 + 2);
   unsigned char* fb = reinterpret_cast<unsigned char*>(picked + (MAXR / 32 + 2));   // [MAXR]
+  unsigned long long* keys2 = reinterpret_cast<unsigned long long*>(smem + (((size_t)(fb + MAXR - smem) + 15) & ~(size_t)15));   // [PW], 512-thread kernel only
   __shared__ unsigned short s_less[6][20], s_flat[6][4];
   __shared__ int s_nl[6], s_nf[6];
   __shared__ unsigned s_spill[6];
@@ -701,9 +749,15 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
   if (P < 1024) P = 1024;
   __syncthreads();
   if (stamp && tid == 0) dbg[4] = clock64();
-  if (P == 1024) cta_sort_keys<1024 / RFT, RFT>(keys, voxel_key);
-  else if (P == 2048) cta_sort_keys<2048 / RFT, RFT>(keys, voxel_key);
-  else cta_sort_keys<4096 / RFT, RFT>(keys, voxel_key);
+  if (RFT == 512) {   // single trajectory: merge sort (two key buffers); the result may be in either buffer
+    if (P == 1024) keys = cta_merge_sort<1024 / RFT, RFT>(keys, keys2, voxel_key);
+    else if (P == 2048) keys = cta_merge_sort<2048 / RFT, RFT>(keys, keys2, voxel_key);
+    else keys = cta_merge_sort<4096 / RFT, RFT>(keys, keys2, voxel_key);
+  } else {            // batches: bitonic network in place (one key buffer: more CTAs per SM)
+    if (P == 1024) cta_sort_keys<1024 / RFT, RFT>(keys, voxel_key);
+    else if (P == 2048) cta_sort_keys<2048 / RFT, RFT>(keys, voxel_key);
+    else cta_sort_keys<4096 / RFT, RFT>(keys, voxel_key);
+  }
   if (stamp && tid == 0) dbg[5] = clock64();
 
   // head flags -> output slots ; each thread owns E consecutive sorted slots

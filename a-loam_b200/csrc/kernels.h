@@ -21,7 +21,7 @@ namespace aloam {
 template <typename T> struct Batch { T a[ALOAM_MAX_BATCH]; };
 
 // ---- features.cu
-size_t ring_features_smem_bytes(int max_ring);
+size_t ring_features_smem_bytes(int max_ring, bool merge);   // merge: the 512-thread kernel (second key buffer)
 void features_debug_cycles(long long* host64x8);   // 65 rows of 8 + 12: per-ring phase stamps, pick-walk stamps of ring 8
 void features_debug_enable(int on);
 struct ClassifyArgs { const float* raw; int n, stride; int8_t* ring_out; int* hist; ScanScalars* sc; };
