@@ -83,7 +83,7 @@ int aloam_destroy(aloam_ctx* c) {
   if (c->h_poses) cudaFreeHost(c->h_poses);
   if (c->h_scan_nfull) cudaFreeHost(c->h_scan_nfull);
   for (Lane& L : c->lanes) free_lane(L);
-  void* dev[] = {c->d_poses, c->d_map_poses, c->d_scan_nfull, c->d_curv, c->d_label, c->d_out28, c->d_packed, c->d_err, c->d_query, c->d_knn_idx, c->d_knn_d};
+  void* dev[] = {c->d_poses, c->d_map_poses, c->d_scan_nfull, c->d_curv, c->d_label, c->d_out28, c->d_api_pose, c->d_packed, c->d_err, c->d_query, c->d_knn_idx, c->d_knn_d};
   for (void* p : dev) if (p) cudaFree(p);
   aloam_map_free_impl(c);
   { void* vp[] = {c->d_vox_keys[0], c->d_vox_keys[1], c->d_vox_vals[0], c->d_vox_vals[1], c->d_vox_hist, c->d_vox_offs, c->d_vox_misc}; for (void* p : vp) if (p) cudaFree(p); }
@@ -114,6 +114,7 @@ int aloam_reset_odometry(aloam_ctx* c) {
     CUDA_CHECK_RET(cudaMemcpyAsync(L.d_world, ident, sizeof(ident), cudaMemcpyHostToDevice, c->stream));
   }
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
+  if (c->s_idx) CUDA_CHECK_RET(cudaStreamSynchronize(c->s_idx));   // an index build of the last synchronous call may still be running
   c->frame = 0; c->cur = 0; c->have_last = false;
   return ALOAM_OK;
 }
@@ -187,7 +188,7 @@ int aloam_create(const aloam_config* cfg_in, aloam_ctx** out) {
     TRY(dalloc(&L.d_blocks, (size_t)2 * kMaxQueries)); TRY(dalloc(&L.d_corr, (size_t)2 * kMaxQueries * 4));
     TRY(dalloc(&L.d_pose, 8)); TRY(dalloc(&L.d_world, 8)); TRY(dalloc(&L.d_summary, 4));
   }
-  TRY(dalloc(&c->d_out28, 32));
+  TRY(dalloc(&c->d_out28, 32)); TRY(dalloc(&c->d_api_pose, 8));
   TRY(dalloc(&c->d_packed, (size_t)2 * kMaxQueries * 11));
   TRY(dalloc(&c->d_err, 4));
   TRY(dalloc(&c->d_query, mp)); TRY(dalloc(&c->d_knn_idx, mp)); TRY(dalloc(&c->d_knn_d, mp));
@@ -290,7 +291,8 @@ void run_grid_build(aloam_ctx* c, int nb, int slot, int n_ls, int n_lf) {
 
 // outer_iters x (association + LM) ; feat[cur] supplies sharp/flat, feat[last] the targets ; pose in lane.d_pose
 // pose_slots (device, lane-major 7 doubles each, may be null): the integrated world pose is also written there by the last solve
-void run_register(aloam_ctx* c, int nb, int cur, int last, int sharp_slots, int flat_slots, bool integrate, bool want_corr, double* pose_slots) {
+void run_register(aloam_ctx* c, int nb, int cur, int last, int sharp_slots, int flat_slots, bool integrate, bool want_corr, double* pose_slots,
+                  double* pose_override = nullptr /* lane 0: solve for this pose instead of the lane's warm start */) {
   OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan, c->cfg.distortion};
   const LmParams lp = lm_params(c->cfg);
   const int slots = sharp_slots + flat_slots;
@@ -301,8 +303,9 @@ void run_register(aloam_ctx* c, int nb, int cur, int last, int sharp_slots, int 
       Lane& L = c->lanes[l];
       const FeatBuf& fc = L.feat[cur];
       const FeatBuf& fl = L.feat[last];
-      aa.a[l] = AssocArgs{fc.sharp, fc.flat, fc.counts, last_corner(fl), last_surf(fl), L.d_pose, L.d_blocks, want_corr ? L.d_corr : nullptr};
-      la.a[l] = LmArgs{L.d_blocks, nullptr, slots, L.d_pose, L.d_summary + (it & 3), (integrate && last_it && pose_slots) ? pose_slots + (size_t)l * 7 : nullptr, L.d_world};
+      double* pose = (l == 0 && pose_override) ? pose_override : L.d_pose;
+      aa.a[l] = AssocArgs{fc.sharp, fc.flat, fc.counts, last_corner(fl), last_surf(fl), pose, L.d_blocks, want_corr ? L.d_corr : nullptr};
+      la.a[l] = LmArgs{L.d_blocks, nullptr, slots, pose, L.d_summary + (it & 3), (integrate && last_it && pose_slots) ? pose_slots + (size_t)l * 7 : nullptr, L.d_world};
     }
     // within one call the chain association -> LM -> association -> LM is launched with programmatic dependencies
     if (slots > 0) launch_ex(c, KID_ODOM_ASSOC, k_odom_assoc, dim3((slots + 7) / 8, nb), dim3(256), 0, 1, it > 0, aa, op, sharp_slots);
@@ -337,10 +340,10 @@ int aloam_extract_features(aloam_ctx* c, aloam_cloud_view raw, aloam_cloud_view*
   CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
   Lane& L = c->lanes[0];
   CUDA_CHECK_RET(cudaMemcpyAsync(L.d_raw[0], raw.data, (size_t)raw.n * raw.stride_floats * 4, cudaMemcpyHostToDevice, c->stream));
-  FeatBuf& f = L.feat[1];
+  FeatBuf& f = L.feat[kApiCur];
   const int slot = c->parity;
   const float* rp = L.d_raw[0];
-  rc = run_features(c, 1, &rp, &raw.n, raw.stride_floats, 1);
+  rc = run_features(c, 1, &rp, &raw.n, raw.stride_floats, kApiCur);
   if (rc) return rc;
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints, f.counts, 16, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_sc, L.d_sc + slot, sizeof(ScanScalars), cudaMemcpyDeviceToHost, c->stream));
@@ -384,7 +387,7 @@ int aloam_odometry_set_last(aloam_ctx* c, aloam_cloud_view corner_last, aloam_cl
   int rc = check_view(corner_last); if (rc) return rc;
   rc = check_view(surf_last); if (rc) return rc;
   CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
-  FeatBuf& f = c->lanes[0].feat[0];
+  FeatBuf& f = c->lanes[0].feat[kApiLast];
   rc = upload_cloud(c, corner_last, f.less_sharp, c->max_points); if (rc) return rc;
   rc = upload_cloud(c, surf_last, f.less_flat, c->max_points); if (rc) return rc;
   c->h_ints[0] = 0; c->h_ints[1] = corner_last.n; c->h_ints[2] = 0; c->h_ints[3] = surf_last.n;
@@ -394,7 +397,7 @@ int aloam_odometry_set_last(aloam_ctx* c, aloam_cloud_view corner_last, aloam_cl
   CUDA_CHECK_RET(cudaMemsetAsync(c->d_err, 0, 4, c->stream));
   if (corner_last.n > 0) LAUNCH(c, KID_RING_OFFSETS, k_ring_offsets, (corner_last.n + 255) / 256, 256, 0, f.less_sharp, corner_last.n, f.rs_ls, c->d_err);
   if (surf_last.n > 0) LAUNCH(c, KID_RING_OFFSETS, k_ring_offsets, (surf_last.n + 255) / 256, 256, 0, f.less_flat, surf_last.n, f.rs_lf, c->d_err);
-  run_grid_build(c, 1, 0, corner_last.n, surf_last.n);
+  run_grid_build(c, 1, kApiLast, corner_last.n, surf_last.n);
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_ints + 8, c->d_err, 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
   CUDA_CHECK_RET(cudaGetLastError());
@@ -419,13 +422,13 @@ int aloam_odometry_register(aloam_ctx* c, aloam_cloud_view sharp, aloam_cloud_vi
   if (!c->have_last) return ALOAM_ERR_STATE;
   CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
   Lane& L = c->lanes[0];
-  int rc = upload_queries(c, sharp, flat, L.feat[1]); if (rc) return rc;
+  int rc = upload_queries(c, sharp, flat, L.feat[kApiCur]); if (rc) return rc;
   for (int k = 0; k < 4; ++k) c->h_dbl[k] = q[k];
   for (int k = 0; k < 3; ++k) c->h_dbl[4 + k] = t[k];
   CUDA_CHECK_RET(cudaEventRecord(c->ev0, c->stream));
-  CUDA_CHECK_RET(cudaMemcpyAsync(L.d_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
-  run_register(c, 1, 1, 0, sharp.n, flat.n, false, false, nullptr);
-  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 8, L.d_pose, 56, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->d_api_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
+  run_register(c, 1, kApiCur, kApiLast, sharp.n, flat.n, false, false, nullptr, c->d_api_pose);
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 8, c->d_api_pose, 56, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, L.d_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaEventRecord(c->ev1, c->stream));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));
@@ -444,16 +447,16 @@ int aloam_odometry_associate(aloam_ctx* c, aloam_cloud_view sharp, aloam_cloud_v
   if (!c->have_last) return ALOAM_ERR_STATE;
   CUDA_CHECK_RET(cudaSetDevice(c->cfg.device));
   Lane& L = c->lanes[0];
-  FeatBuf& cur = L.feat[1];
+  FeatBuf& cur = L.feat[kApiCur];
   int rc = upload_queries(c, sharp, flat, cur); if (rc) return rc;
   for (int k = 0; k < 4; ++k) c->h_dbl[k] = q[k];
   for (int k = 0; k < 3; ++k) c->h_dbl[4 + k] = t[k];
-  CUDA_CHECK_RET(cudaMemcpyAsync(L.d_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->d_api_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
   OdomParams op{c->cfg.dist_sq_thresh, c->cfg.nearby_scan, c->cfg.distortion};
   const int slots = sharp.n + flat.n;
   if (slots > 0) {
     Batch<AssocArgs> aa = {};
-    aa.a[0] = AssocArgs{cur.sharp, cur.flat, cur.counts, last_corner(L.feat[0]), last_surf(L.feat[0]), L.d_pose, L.d_blocks, L.d_corr};
+    aa.a[0] = AssocArgs{cur.sharp, cur.flat, cur.counts, last_corner(L.feat[kApiLast]), last_surf(L.feat[kApiLast]), c->d_api_pose, L.d_blocks, L.d_corr};
     LAUNCH(c, KID_ODOM_ASSOC, k_odom_assoc, dim3((slots + 7) / 8, 1), 256, 0, aa, op, sharp.n);
   }
   std::vector<int> h((size_t)slots * 4 + 4);
@@ -476,12 +479,24 @@ static int scan_to_pose_impl(aloam_ctx* c, const float* d_raw, int n, int stride
   int rc = run_features(c, 1, &d_raw, &n, stride, cur);
   if (rc) return rc;
   int flags = 0;
+  // The search index over this scan's less-sharp / less-flat clouds (what replaces the kd-tree rebuild, laserOdometry.cpp:567-568)
+  // is needed by the NEXT scan only: it is built on the index stream while this scan's association + LM run on the main stream, and
+  // the call returns the pose without waiting for it (the next call, or aloam_scan_stream, waits on ev_idx).
+  {
+    StreamGuard guard(c);
+    CUDA_CHECK_RET(cudaEventRecord(c->ev_feat[cur], c->stream));
+    CUDA_CHECK_RET(cudaStreamWaitEvent(c->s_idx, c->ev_feat[cur], 0));
+    if (!c->prof_on) c->stream = c->s_idx;   // (the per-kernel profiler times everything on one stream)
+    run_grid_build(c, 1, cur, 64 * kMaxLessSharpPerRing, std::min(n, c->max_points));
+    CUDA_CHECK_RET(cudaEventRecord(c->ev_idx[cur], c->stream));
+  }
   if (c->frame == 0) {
     flags |= ALOAM_FLAG_INITIALISED_ONLY;  // laserOdometry.cpp:267-271
   } else {
+    CUDA_CHECK_RET(cudaStreamWaitEvent(c->stream, c->ev_idx[last], 0));   // the previous scan's index (built during the previous call)
     run_register(c, 1, cur, last, kFusedSharpSlots, kFusedFlatSlots, true, false, nullptr);
   }
-  run_grid_build(c, 1, cur, 64 * kMaxLessSharpPerRing, std::min(n, c->max_points));  // index for the next scan (replaces the kd-tree rebuild, laserOdometry.cpp:567-568)
+  CUDA_CHECK_RET(cudaEventRecord(c->ev_odo[cur], c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 16, L.d_world, 56, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, L.d_summary, sizeof(LmSummary) * 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_sc, L.d_sc + slot, sizeof(ScanScalars), cudaMemcpyDeviceToHost, c->stream));
@@ -700,7 +715,7 @@ int aloam_knn(aloam_ctx* c, int which, aloam_cloud_view queries, int k, int* idx
     if (k != 1) return ALOAM_ERR_INVALID_ARG;  // the reference only asks for k = 1 on these trees (laserOdometry.cpp:302,390)
     rc = upload_cloud(c, queries, c->d_query, c->max_points); if (rc) return rc;
     if (queries.n > 0) {
-      const FeatBuf& f0 = c->lanes[0].feat[0];
+      const FeatBuf& f0 = c->lanes[0].feat[kApiLast];
       LastCloud L = which == 0 ? last_corner(f0) : last_surf(f0);
       LAUNCH(c, KID_KNN_LAST, k_knn_last, (queries.n + 7) / 8, 256, 0, L, c->d_query, queries.n, c->d_knn_idx, c->d_knn_d);
       CUDA_CHECK_RET(cudaMemcpyAsync(idx, c->d_knn_idx, (size_t)queries.n * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -741,10 +756,10 @@ static int run_lm_api(aloam_ctx* c, const double* blocks, int n_blocks, const do
     LAUNCH(c, KID_PACK_BLOCKS, k_pack_blocks, (n_blocks + 255) / 256, 256, 0, c->d_packed, n_blocks, L.d_blocks);
   }
   for (int k = 0; k < 7; ++k) c->h_dbl[k] = x[k];
-  CUDA_CHECK_RET(cudaMemcpyAsync(L.d_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
-  launch_lm(c, false, (const BlockRec*)L.d_blocks, (const int*)nullptr, n_blocks, L.d_pose, lm_params(c->cfg), L.d_summary, mode,
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->d_api_pose, c->h_dbl, 56, cudaMemcpyHostToDevice, c->stream));
+  launch_lm(c, false, (const BlockRec*)L.d_blocks, (const int*)nullptr, n_blocks, c->d_api_pose, lm_params(c->cfg), L.d_summary, mode,
             c->d_out28, (double*)nullptr, 0, true /* blocks from the caller may carry any interpolation ratio */);
-  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 8, L.d_pose, 56, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 8, c->d_api_pose, 56, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_dbl + 32, c->d_out28, 28 * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaMemcpyAsync(c->h_summary, L.d_summary, sizeof(LmSummary), cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK_RET(cudaStreamSynchronize(c->stream));

@@ -19,6 +19,7 @@ constexpr int kFusedFlatSlots = 64 * kMaxFlatPerRing;    // 1536
 constexpr int kMaxQueries = ALOAM_MAX_QUERIES;         // API-path capacity for sharp / flat query clouds
 constexpr int kProfSlots = 192;                        // kernel launches timed per profile window (one API call)
 constexpr int kFeatSlots = 4;                          // feature-set ring of the fused / stream paths
+constexpr int kApiLast = kFeatSlots, kApiCur = kFeatSlots + 1;   // feature sets of the per-stage entry points (set_last / extract, register): never the ring's
 constexpr int kMaxStreamScans = 4096;                  // scans x lanes per aloam_scan_stream(_batch) call
 
 struct FeatBuf {
@@ -40,7 +41,7 @@ struct Lane {
   // per-ring staging sets: in the stream call k_compact(k) runs on the index stream while k_ring_features(k+1) fills the other set
   Pt4 *st_sharp[2] = {}, *st_less_sharp[2] = {}, *st_flat[2] = {}, *st_less_flat[2] = {};
   int* st_counts[2] = {};
-  FeatBuf feat[kFeatSlots];                      // ring of feature sets: odometry k reads sets k-1 and k while extraction runs ahead
+  FeatBuf feat[kFeatSlots + 2];                  // [0, kFeatSlots): ring of feature sets (odometry k reads sets k-1 and k while extraction runs ahead) ; kApiLast, kApiCur
   BlockRec* d_blocks = nullptr;
   int* d_corr = nullptr;
   double *d_pose = nullptr, *d_world = nullptr;  // para_q/para_t (laserOdometry.cpp:97-98) and q_w_curr/t_w_curr (:93-94)
@@ -59,6 +60,7 @@ struct aloam_ctx {
   int8_t* d_label = nullptr;
   int* d_scan_nfull = nullptr;     // [kMaxStreamScans] ring-major cloud size of every (scan, lane) of a stream call
   double *d_out28 = nullptr, *d_packed = nullptr;
+  double* d_api_pose = nullptr;    // [8] pose of the per-stage entry points (odometry_register, solve, ...): not the warm start of the fused pipeline
   int* d_err = nullptr;
   Pt4* d_query = nullptr;
   int* d_knn_idx = nullptr;

@@ -186,3 +186,25 @@ def test_replay_of_kitti_files_equals_direct_calls(aloam, synth, scans, tmp_path
     T = io.lidar_pose_to_kitti(got[-1][:4], got[-1][4:])
     q, t = io.kitti_pose_to_lidar(T)
     assert np.abs(t - got[-1][4:]).max() < 1e-12 and rot_angle(q, got[-1][:4]) < 1e-7
+
+
+def test_per_stage_calls_do_not_disturb_the_fused_pipeline(aloam, synth, scans):
+    """aloam_extract_features / aloam_odometry_set_last / aloam_odometry_register / aloam_solve between aloam_scan_to_pose calls
+    of the same context leave the fused pipeline's feature sets, search indices and warm start alone (the per-stage entry
+    points own separate feature sets and a separate pose), also while the index of the previous scan is still being built
+    on the index stream"""
+    raws = [scans("VLP-16", k, n_az=900) for k in range(5)]
+    clean = aloam.Aloam(n_scans=16, max_points=40000)
+    ref = [np.concatenate(clean.scan_to_pose(r)[:2]) for r in raws]
+    clean.close()
+    c = aloam.Aloam(n_scans=16, max_points=40000)
+    rng = np.random.default_rng(5)
+    for k, r in enumerate(raws):
+        q, t, _ = c.scan_to_pose(r)
+        assert np.array_equal(np.concatenate([q, t]), ref[k]), k
+        f = c.extract_features(raws[(k + 2) % 5])                      # a different scan through the per-stage path
+        c.odometry_set_last(f["less_sharp"], f["less_flat"])
+        c.odometry_register(f["sharp"], f["flat"], np.array([0, 0, 0, 1.0]), rng.normal(0, 0.1, 3))
+        blocks = np.array([[2, 1, 2, 3, 0, 0, 1, 0, 0, 0, -2.5]], float)
+        c.solve(blocks, np.array([0, 0, 0, 1.0, 0.3, 0.2, 0.1]))
+    c.close()
