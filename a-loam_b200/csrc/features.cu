@@ -592,8 +592,31 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
 
   long long* dbg = g_dbg_cycles + (blockIdx.y == 0 ? ring : 64) * 8;   // lane 0 only; the other lanes write a dummy row
   if (stamp && tid == 0) dbg[0] = clock64();
-  for (int i = tid; i < nr; i += blockDim.x) pts[i] = full[g0 + i];
+  // The ring (nr x 16 bytes, up to 64 KB, contiguous in the ring-major cloud) is staged into shared memory by ONE TMA bulk copy
+  // (cp.async.bulk, 1-D): a single thread arms an mbarrier with the byte count and issues the copy, the copy engine moves the
+  // tile while the CTA clears its bit arrays, and everybody waits on the barrier's phase.  (Before: every thread looped over
+  // LDG.128 + STS.128 pairs.)
+  __shared__ __align__(8) unsigned long long s_bar;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned bytes = (unsigned)nr * 16u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(pts)),
+                 "l"(full + g0), "r"(bytes), "r"(bar)
+                 : "memory");
+  }
   for (int i = tid; i < MAXR / 32 + 2; i += blockDim.x) { gap[i] = 0; picked[i] = 0; }
+  {
+    unsigned done = 0;
+    while (!done)
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+  }
   __syncthreads();
 
   // curvature (:256-266) for local 5 .. nr-6, left-to-right float sums ; gap bits (whole warps iterate together)
