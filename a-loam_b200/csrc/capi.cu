@@ -250,7 +250,8 @@ int run_features_b1(aloam_ctx* c, int nb, int buf, int sc_slot) {
     fa.a[l] = RingFeatArgs{L.d_full[buf], L.d_ring_start[buf], L.st_sharp[buf], L.st_less_sharp[buf], L.st_flat[buf], L.st_less_flat[buf], L.st_counts[buf],
                            l == 0 ? c->d_curv : nullptr, l == 0 ? c->d_label : nullptr, L.d_sc + sc_slot};
   }
-  if (nb == 1) LAUNCH(c, KID_RING_FEATURES, k_ring_features, dim3(c->cfg.n_scans, nb), 512, ring_features_smem_bytes(c->max_ring, true), fa, c->cfg.n_scans, 0.2f, c->max_ring);
+  // one trajectory: a cluster of two CTAs per ring (picks | voxel sort, see features.cu) ; a batch: one CTA per ring and trajectory
+  if (nb == 1) launch_ex(c, KID_RING_FEATURES, k_ring_features, dim3(2 * c->cfg.n_scans, 1), dim3(512), ring_features_smem_bytes(c->max_ring, true), 2, false, fa, c->cfg.n_scans, 0.2f, c->max_ring);
   else LAUNCH(c, KID_RING_FEATURES, k_ring_features_batch, dim3(c->cfg.n_scans, nb), 256, ring_features_smem_bytes(c->max_ring, false), fa, c->cfg.n_scans, 0.2f, c->max_ring);
   CUDA_CHECK_RET(cudaGetLastError());
   return ALOAM_OK;

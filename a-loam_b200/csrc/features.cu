@@ -428,9 +428,9 @@ __device__ __forceinline__ void set_bits(unsigned* m, int lo, int hi) {  // sing
 template <int NS>
 __device__ __forceinline__ void pick_segment(const float* curv, const unsigned char* fb, int sp, int ep, unsigned spill_in,
                                              unsigned short* less, int& n_less, unsigned short* flat, int& n_flat,
-                                             unsigned& spill_out) {
+                                             unsigned& spill_out, bool dbg_seg) {
   const int lane = threadIdx.x & 31;
-  const bool dbg_me = g_dbg_stamp != 0 && blockIdx.x == 8 && blockIdx.y == 0 && (threadIdx.x >> 5) == 3 && lane == 0;
+  const bool dbg_me = dbg_seg && lane == 0;
   if (dbg_me) g_dbg_pick[0] = clock64();
   float c[NS];
   unsigned valid = 0, pk = 0;   // bit s: slot s is inside the segment / is marked in cloudNeighborPicked
@@ -540,12 +540,31 @@ size_t ring_features_smem_bytes(int maxr, bool merge) {
   return (size_t)maxr * (16 + 4 + 1 + 1) + (size_t)sort_width(maxr) * 8 * (merge ? 2 : 1) + 2 * 4 * (maxr / 32 + 2) + 64;
 }
 
-// RFT = threads of a ring CTA: six warps walk the segments, all of them load, sort and sum.  512 threads (one CTA per SM) for
-// a single trajectory, where the kernel is a latency chain; 256 threads (two or three CTAs per SM) when a batch fills the GPU.
-template <int RFT>
+// ---- thread-block-cluster helpers of the paired kernel (raw PTX: the barrier is used split, arrive now / wait later)
+__device__ __forceinline__ unsigned cluster_cta_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_dsmem_u32(const void* local, unsigned rank) {   // the same shared-memory offset in CTA `rank` of the cluster
+  const unsigned a = (unsigned)__cvta_generic_to_shared(local);
+  unsigned ra, v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+// RFT = threads of a ring CTA: six warps walk the segments, all of them load, sort and sum.
+//   PAIR = false : one CTA does the whole ring (256 threads, two or three CTAs per SM): batches of trajectories, which fill the GPU.
+//   PAIR = true  : a single trajectory, where the kernel is a latency chain on 64 of 148 SMs.  A ring is processed by a CLUSTER
+//                  OF TWO CTAs on two SMs: rank 0 = curvature, greedy picks, labels, the three picked clouds ; rank 1 = the voxel
+//                  sort of the ring, which is made INDEPENDENT of the picks: it sorts every in-range position by its absolute voxel
+//                  coordinates (floor(z/leaf), floor(y/leaf), floor(x/leaf)) -- the same order as PCL's index relative to the
+//                  bounding box of the candidates, because that index is lexicographic in (z, y, x) -- and removes the picked
+//                  positions afterwards, reading rank 0's labels through distributed shared memory.  The two halves overlap;
+//                  the chain is max(picks, sort) + centroids instead of their sum.
+template <int RFT, bool PAIR>
 __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B, int n_scans, float leaf, int MAXR) {
   pdl_launch_dependents();   // the next kernel of the stream may become resident (it blocks in pdl_wait())
-  const RingFeatArgs& A = B.a[blockIdx.y];   // blockIdx.x = ring, blockIdx.y = trajectory of the batch
+  const RingFeatArgs& A = B.a[blockIdx.y];   // blockIdx.x = ring (PAIR: 2 * ring + cluster rank), blockIdx.y = trajectory of the batch
   const Pt4* __restrict__ full = A.full;
   const int* __restrict__ ring_start = A.ring_start;
   Pt4* __restrict__ st_sharp = A.st_sharp;
@@ -572,26 +591,31 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
   __shared__ int s_i[RFT / 32];
   __shared__ float s_red[6][RFT / 32];
 
-  const int ring = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // role 0: the whole ring ; 1: the picks CTA of a pair ; 2: the voxel CTA of a pair
+  const int role = PAIR ? (int)cluster_cta_rank() + 1 : 0;
+  const int ring = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool stamp = g_dbg_stamp != 0;
+  const bool dbg8 = stamp && ring == 8 && blockIdx.y == 0;
   const int g0 = ring_start[ring], nr = ring_start[ring + 1] - g0;
   int* counts = st_counts + ring * 4;
-  if (nr > MAXR) {
-    if (tid == 0) { sc->error = ALOAM_ERR_RING_TOO_LARGE_DEV; counts[0] = counts[1] = counts[2] = counts[3] = 0; }
+  if (nr > MAXR) {   // (both CTAs of a pair leave here, before any cluster barrier)
+    if (tid == 0 && role != 2) { sc->error = ALOAM_ERR_RING_TOO_LARGE_DEV; counts[0] = counts[1] = counts[2] = counts[3] = 0; }
     return;
   }
   // scanStartInd = g0+5, scanEndInd = g0+nr-6 ; skip ring if end - start < 6 (:279)
   const int s_loc = 5, e_loc = nr - 6;
-  for (int i = tid; i < nr; i += blockDim.x) { label[i] = 0; if (dbg_label) dbg_label[g0 + i] = 0; if (dbg_curv) dbg_curv[g0 + i] = 0.f; }
+  if (role != 2)
+    for (int i = tid; i < nr; i += blockDim.x) { label[i] = 0; if (dbg_label) dbg_label[g0 + i] = 0; if (dbg_curv) dbg_curv[g0 + i] = 0.f; }
   if (e_loc - s_loc < 6) {
-    if (tid == 0) counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    if (tid == 0 && role != 2) counts[0] = counts[1] = counts[2] = counts[3] = 0;
     return;
   }
   int P = 32;
   while (P < nr) P <<= 1;
 
   long long* dbg = g_dbg_cycles + (blockIdx.y == 0 ? ring : 64) * 8;   // lane 0 only; the other lanes write a dummy row
-  if (stamp && tid == 0) dbg[0] = clock64();
+  if (stamp && tid == 0) dbg[role == 2 ? 7 : 0] = clock64();
   // The ring (nr x 16 bytes, up to 64 KB, contiguous in the ring-major cloud) is staged into shared memory by ONE TMA bulk copy
   // (cp.async.bulk, 1-D): a single thread arms an mbarrier with the byte count and issues the copy, the copy engine moves the
   // tile while the CTA clears its bit arrays, and everybody waits on the barrier's phase.  (Before: every thread looped over
@@ -619,6 +643,7 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
   }
   __syncthreads();
 
+  if (role != 2) {
   // curvature (:256-266) for local 5 .. nr-6, left-to-right float sums ; gap bits (whole warps iterate together)
   for (int base = warp * 32; base < nr; base += blockDim.x) {
     const int i = base + lane;
@@ -656,25 +681,25 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
   // points under the (curvature, index) order, so no sort is needed: one warp keeps a segment's curvatures in
   // registers (position sp + 32 s + lane in slot s) and performs <= 20 + 4 REDUX selections.
   // The six segments of a ring depend on each other only through the <= 5 marks a segment spills onto the start of
-  // the next one (:319-330).  Warps 0..5 therefore process the six segments CONCURRENTLY assuming an empty spill;
+  // the next one (:319-330).  Six warps therefore process the six segments CONCURRENTLY assuming an empty spill;
   // a segment is re-run (in order) only if a position actually spilled onto it is one of its own picks -- removing a
   // point that never wins a selection cannot change any selection, so otherwise the speculative result is exact.
   auto run_segment = [&](int w, unsigned spill_in) {
     const int sp = s_loc + span * w / 6, ep = s_loc + span * (w + 1) / 6 - 1;
     int nl, nf; unsigned so;
-    if (ep - sp + 1 <= 12 * 32) pick_segment<12>(curv, fb, sp, ep, spill_in, s_less[w], nl, s_flat[w], nf, so);
-    else pick_segment<24>(curv, fb, sp, ep, spill_in, s_less[w], nl, s_flat[w], nf, so);
+    if (ep - sp + 1 <= 12 * 32) pick_segment<12>(curv, fb, sp, ep, spill_in, s_less[w], nl, s_flat[w], nf, so, dbg8 && w == 2);
+    else pick_segment<24>(curv, fb, sp, ep, spill_in, s_less[w], nl, s_flat[w], nf, so, dbg8 && w == 2);
     if (lane == 0) { s_nl[w] = nl; s_nf[w] = nf; s_spill[w] = so; }
   };
   // Warps 1..6 walk the six segments.  NOT warp 0: it carries the thread that writes the debug stamps, and measured on B200 a
   // segment walked by warp 0 took 30 k cycles against 9-13 k on any other warp (its REDUX go through the divergent-warp path).
   if (warp >= 1 && warp <= 6) {
-    if (stamp && lane == 0 && blockIdx.x == 8 && blockIdx.y == 0) g_dbg_pick[8 + 2 * (warp - 1)] = clock64();
+    if (dbg8 && lane == 0) g_dbg_pick[8 + 2 * (warp - 1)] = clock64();
     run_segment(warp - 1, 0u);
-    if (stamp && lane == 0 && blockIdx.x == 8 && blockIdx.y == 0) g_dbg_pick[9 + 2 * (warp - 1)] = clock64();
+    if (dbg8 && lane == 0) g_dbg_pick[9 + 2 * (warp - 1)] = clock64();
   }
   __syncthreads();
-  if (stamp && tid == 0 && blockIdx.x == 8 && blockIdx.y == 0) g_dbg_pick[6] = clock64();
+  if (dbg8 && tid == 0) g_dbg_pick[6] = clock64();
   for (int w = 1; w < 6; ++w) {
     if (warp == w + 1) {
       const unsigned in = s_spill[w - 1];
@@ -691,7 +716,7 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     }
     __syncthreads();
   }
-  if (stamp && tid == 0 && blockIdx.x == 8 && blockIdx.y == 0) g_dbg_pick[7] = clock64();
+  if (dbg8 && tid == 0) g_dbg_pick[7] = clock64();
   // labels (:303,309,355) and ring-ordered outputs (ring, segment, pick order) from the per-segment lists
   if (tid < 6 * 24) {
     const int w = tid / 24, i = tid % 24;
@@ -715,84 +740,152 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     }
   }
   __syncthreads();
+  if (role == 1) cluster_arrive();   // barrier A (release): the labels are final
   if (stamp && tid == 0) dbg[3] = clock64();
   if (dbg_label) for (int i = tid; i < nr; i += blockDim.x) dbg_label[g0 + i] = label[i];
+  if (role == 1) {
+    // A completes when the voxel CTA has sorted ; B when it has copied the labels out of this CTA's shared memory, which
+    // therefore has to stay alive until then
+    __syncwarp();
+    cluster_wait();
+    cluster_arrive();
+    cluster_wait();
+    return;
+  }
+  }   // role != 2
 
   // ---- less-flat candidates = positions [s_loc, e_loc-1] with label <= 0 (:392-398), voxel-filtered per ring (:401-407)
   // pcl::VoxelGrid::applyFilter: bounding box, voxel index, sort by (index, position), float centroid per voxel
-  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  int my_cnt = 0;
-  for (int i = s_loc + tid; i < e_loc; i += blockDim.x) {
-    if (label[i] <= 0) {
-      ++my_cnt;
-      mn[0] = fminf(mn[0], pts[i].x); mn[1] = fminf(mn[1], pts[i].y); mn[2] = fminf(mn[2], pts[i].z);
-      mx[0] = fmaxf(mx[0], pts[i].x); mx[1] = fmaxf(mx[1], pts[i].y); mx[2] = fmaxf(mx[2], pts[i].z);
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], d));
-      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], d));
-    }
-    if (lane == 0) { s_red[a][warp] = mn[a]; s_red[3 + a][warp] = mx[a]; }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    float lo = s_red[a][0], hi = s_red[3 + a][0];
-    for (int w2 = 1; w2 < (int)(blockDim.x >> 5); ++w2) { lo = fminf(lo, s_red[a][w2]); hi = fmaxf(hi, s_red[3 + a][w2]); }
-    mn[a] = lo; mx[a] = hi;
-  }
   const float inv = 1.0f / leaf;  // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
-  long long dxyz[3];
-  int min_b[3], div_b[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    dxyz[a] = (long long)((mx[a] - mn[a]) * inv) + 1;
-    min_b[a] = (int)floorf(mn[a] * inv);
-    div_b[a] = (int)floorf(mx[a] * inv) - min_b[a] + 1;
-  }
-  const bool any_cand = mn[0] <= mx[0];
-  const bool overflow = any_cand && (dxyz[0] * dxyz[1] * dxyz[2] > (long long)INT_MAX);
-  // keys: [voxel idx 32b | local position 12b], non-candidates last ; sorted by the whole CTA
-  // (overflow case: idx = 0 everywhere => position order, i.e. output = input, PCL's early return)
-  auto voxel_key = [&](int i) -> unsigned long long {
-    if (!(i >= s_loc && i < e_loc && label[i] <= 0)) return ~0ull;
-    unsigned idx = 0;
-    if (!overflow) {
-      const int i0 = (int)(floorf(pts[i].x * inv) - (float)min_b[0]);
-      const int i1 = (int)(floorf(pts[i].y * inv) - (float)min_b[1]);
-      const int i2 = (int)(floorf(pts[i].z * inv) - (float)min_b[2]);
-      idx = (unsigned)(i0 + i1 * div_b[0] + i2 * div_b[0] * div_b[1]);
+  // bounding box of the positions [s_loc, e_loc) accepted by `use`, reduced over the CTA (every thread gets the result)
+  auto block_bbox = [&](auto&& use, float* mn, float* mx) {
+    mn[0] = mn[1] = mn[2] = FLT_MAX; mx[0] = mx[1] = mx[2] = -FLT_MAX;
+    for (int i = s_loc + tid; i < e_loc; i += blockDim.x) {
+      if (use(i)) {
+        mn[0] = fminf(mn[0], pts[i].x); mn[1] = fminf(mn[1], pts[i].y); mn[2] = fminf(mn[2], pts[i].z);
+        mx[0] = fmaxf(mx[0], pts[i].x); mx[1] = fmaxf(mx[1], pts[i].y); mx[2] = fmaxf(mx[2], pts[i].z);
+      }
     }
-    return ((unsigned long long)idx << 12) | (unsigned)i;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], d));
+        mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], d));
+      }
+      if (lane == 0) { s_red[a][warp] = mn[a]; s_red[3 + a][warp] = mx[a]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float lo = s_red[a][0], hi = s_red[3 + a][0];
+      for (int w2 = 1; w2 < (int)(blockDim.x >> 5); ++w2) { lo = fminf(lo, s_red[a][w2]); hi = fmaxf(hi, s_red[3 + a][w2]); }
+      mn[a] = lo; mx[a] = hi;
+    }
+    __syncthreads();   // s_red may be reused
+  };
+  auto grid_overflows = [&](const float* mn, const float* mx) {   // PCL: dx * dy * dz > INT_MAX -> the filter returns its input
+    long long d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) d[a] = (long long)((mx[a] - mn[a]) * inv) + 1;
+    return mn[0] <= mx[0] && d[0] * d[1] * d[2] > (long long)INT_MAX;
   };
   if (P < 1024) P = 1024;
-  __syncthreads();
-  if (stamp && tid == 0) dbg[4] = clock64();
-  if (RFT == 512) {   // single trajectory: merge sort (two key buffers); the result may be in either buffer
-    if (P == 1024) keys = cta_merge_sort<1024 / RFT, RFT>(keys, keys2, voxel_key);
-    else if (P == 2048) keys = cta_merge_sort<2048 / RFT, RFT>(keys, keys2, voxel_key);
-    else keys = cta_merge_sort<4096 / RFT, RFT>(keys, keys2, voxel_key);
-  } else {            // batches: bitonic network in place (one key buffer: more CTAs per SM)
-    if (P == 1024) cta_sort_keys<1024 / RFT, RFT>(keys, voxel_key);
-    else if (P == 2048) cta_sort_keys<2048 / RFT, RFT>(keys, voxel_key);
-    else cta_sort_keys<4096 / RFT, RFT>(keys, voxel_key);
-  }
-  if (stamp && tid == 0) dbg[5] = clock64();
+  auto sort_by = [&](auto&& key_of) {
+    if (RFT == 512) {   // merge sort (two key buffers); the result may be in either buffer
+      if (P == 1024) keys = cta_merge_sort<1024 / RFT, RFT>(keys, keys2, key_of);
+      else if (P == 2048) keys = cta_merge_sort<2048 / RFT, RFT>(keys, keys2, key_of);
+      else keys = cta_merge_sort<4096 / RFT, RFT>(keys, keys2, key_of);
+    } else {            // batches: bitonic network in place (one key buffer: more CTAs per SM)
+      if (P == 1024) cta_sort_keys<1024 / RFT, RFT>(keys, key_of);
+      else if (P == 2048) cta_sort_keys<2048 / RFT, RFT>(keys, key_of);
+      else cta_sort_keys<4096 / RFT, RFT>(keys, key_of);
+    }
+  };
 
+  // The voxel CTA of a pair sorts BEFORE the labels exist.  Preconditions (CTA-uniform, from the bounding box of ALL in-range
+  // positions, a superset of the candidates): every voxel coordinate fits 17 bits and the superset's grid does not overflow
+  // (then the candidates' grid does not either).  Otherwise it falls back to the order of operations of the single CTA.
+  bool presorted = false;
+  if (role == 2) {
+    float mn[3], mx[3];
+    block_bbox([&](int) { return true; }, mn, mx);
+    bool fits = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) fits = fits && floorf(mn[a] * inv) > -65536.f && floorf(mx[a] * inv) < 65536.f;
+    presorted = fits && !grid_overflows(mn, mx);
+    if (stamp && tid == 0) dbg[4] = clock64();
+    if (presorted) {
+      sort_by([&](int i) -> unsigned long long {
+        if (!(i >= s_loc && i < e_loc)) return ~0ull;
+        const unsigned long long ix = (unsigned long long)((int)floorf(pts[i].x * inv) + 65536);
+        const unsigned long long iy = (unsigned long long)((int)floorf(pts[i].y * inv) + 65536);
+        const unsigned long long iz = (unsigned long long)((int)floorf(pts[i].z * inv) + 65536);
+        return ((((iz << 17) | iy) << 17 | ix) << 12) | (unsigned)i;   // 51 + 12 bits
+      });
+      if (stamp && tid == 0) dbg[5] = clock64();
+    }
+    // barrier A: rank 0's labels are final ; copy them (4 positions per word) ; barrier B releases rank 0
+    __syncwarp();
+    cluster_arrive();
+    cluster_wait();
+    unsigned* lw = reinterpret_cast<unsigned*>(label);
+    for (int w4 = tid; w4 < (nr + 3) / 4; w4 += blockDim.x) lw[w4] = ld_dsmem_u32(lw + w4, 0u);
+    __syncthreads();
+    cluster_arrive();
+  }
+
+  bool overflow = false;
+  if (!presorted) {
+    float mn[3], mx[3];
+    block_bbox([&](int i) { return label[i] <= 0; }, mn, mx);
+    int min_b[3], div_b[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      min_b[a] = (int)floorf(mn[a] * inv);
+      div_b[a] = (int)floorf(mx[a] * inv) - min_b[a] + 1;
+    }
+    overflow = grid_overflows(mn, mx);
+    if (stamp && tid == 0) dbg[4] = clock64();
+    // keys: [voxel idx 32b | local position 12b], non-candidates last ; sorted by the whole CTA
+    // (overflow case: idx = 0 everywhere => position order, i.e. output = input, PCL's early return)
+    sort_by([&](int i) -> unsigned long long {
+      if (!(i >= s_loc && i < e_loc && label[i] <= 0)) return ~0ull;
+      unsigned idx = 0;
+      if (!overflow) {
+        const int i0 = (int)(floorf(pts[i].x * inv) - (float)min_b[0]);
+        const int i1 = (int)(floorf(pts[i].y * inv) - (float)min_b[1]);
+        const int i2 = (int)(floorf(pts[i].z * inv) - (float)min_b[2]);
+        idx = (unsigned)(i0 + i1 * div_b[0] + i2 * div_b[0] * div_b[1]);
+      }
+      return ((unsigned long long)idx << 12) | (unsigned)i;
+    });
+    if (stamp && tid == 0) dbg[5] = clock64();
+  }
+
+  // A sorted slot is a candidate unless the presorted order still contains the picked positions ; a candidate is the head of its
+  // voxel if no candidate precedes it in the voxel's run (picked positions are few, so the walk back is short).
+  auto is_cand = [&](unsigned long long key) { return !presorted || label[(int)(key & 0xfffu)] <= 0; };
+  auto is_head = [&](int k, unsigned long long key) {
+    if (!is_cand(key)) return false;
+    if (overflow) return true;
+    for (int k2 = k - 1; k2 >= 0; --k2) {
+      const unsigned long long kp = keys[k2];
+      if ((kp >> 12) != (key >> 12)) break;
+      if (is_cand(kp)) return false;
+    }
+    return true;
+  };
   // head flags -> output slots ; each thread owns E consecutive sorted slots
   const int E = P / (int)blockDim.x > 0 ? P / (int)blockDim.x : 1;
   const int k0 = tid * E;
-  int heads = 0;
+  unsigned head_bits = 0;   // E <= 16
   for (int k = k0; k < k0 + E && k < P; ++k) {
-    unsigned long long key = keys[k];
+    const unsigned long long key = keys[k];
     if (key == ~0ull) break;
-    bool head = overflow || k == 0 || (unsigned)(keys[k - 1] >> 12) != (unsigned)(key >> 12);
-    heads += head ? 1 : 0;
+    if (is_head(k, key)) head_bits |= 1u << (k - k0);
   }
+  const int heads = __popc(head_bits);
   // block exclusive scan of `heads`
   int incl = heads;
 #pragma unroll
@@ -809,21 +902,17 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
   // the heads' sorted positions, compacted: afterwards ONE thread per voxel sums its run (a thread that owned several
   // single-point voxels and one long run used to serialise them all)
   int* head_pos = reinterpret_cast<int*>(curv);   // the curvatures are not needed any more ; #voxels <= #points <= MAXR
-  for (int k = k0; k < k0 + E && k < P; ++k) {
-    unsigned long long key = keys[k];
-    if (key == ~0ull) break;
-    const bool head = overflow || k == 0 || (unsigned)(keys[k - 1] >> 12) != (unsigned)(key >> 12);
-    if (head) head_pos[slot++] = k;
-  }
+  for (unsigned hb = head_bits; hb; hb &= hb - 1) head_pos[slot++] = k0 + __ffs(hb) - 1;
   __syncthreads();
   for (int h = tid; h < total; h += blockDim.x) {
     const int k = head_pos[h];
-    const unsigned idx = (unsigned)(keys[k] >> 12);
+    const unsigned long long idx = keys[k] >> 12;
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
     int cnt = 0;
     for (int k2 = k; k2 < P; ++k2) {  // float accumulation in sorted order, then divide (pcl::CentroidPoint)
-      unsigned long long key2 = keys[k2];
-      if (key2 == ~0ull || (!overflow && (unsigned)(key2 >> 12) != idx) || (overflow && k2 > k)) break;
+      const unsigned long long key2 = keys[k2];
+      if (key2 == ~0ull || (!overflow && (key2 >> 12) != idx) || (overflow && k2 > k)) break;
+      if (!is_cand(key2)) continue;
       const Pt4 p = pts[(int)(key2 & 0xfffu)];
       sx += p.x; sy += p.y; sz += p.z; si += p.i;
       ++cnt;
@@ -833,13 +922,15 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     o_lf[h] = o;
   }
   if (tid == 0) { counts[3] = total; if (stamp) dbg[6] = clock64(); }
+  if (role == 2) { __syncwarp(); cluster_wait(); }   // barrier B (rank 0 arrived long ago)
 }
 
+// grid (2 * rings, 1), clusters of two CTAs
 __global__ void __launch_bounds__(512) k_ring_features(const __grid_constant__ Batch<RingFeatArgs> B, int n_scans, float leaf, int max_ring) {
-  ring_features_body<512>(B, n_scans, leaf, max_ring);
+  ring_features_body<512, true>(B, n_scans, leaf, max_ring);
 }
 __global__ void __launch_bounds__(256) k_ring_features_batch(const __grid_constant__ Batch<RingFeatArgs> B, int n_scans, float leaf, int max_ring) {
-  ring_features_body<256>(B, n_scans, leaf, max_ring);
+  ring_features_body<256, false>(B, n_scans, leaf, max_ring);
 }
 
 void features_debug_enable(int on) { cudaMemcpyToSymbol(g_dbg_stamp, &on, sizeof(int)); }

@@ -35,7 +35,7 @@ struct CompactArgs { const Pt4 *st_sharp, *st_less_sharp, *st_flat, *st_less_fla
 __global__ void k_classify(const __grid_constant__ Batch<ClassifyArgs> B, int n_scans, float thres2);          // grid (blocks, lanes)
 __global__ void k_ring_scan(const __grid_constant__ Batch<RingScanArgs> B, int n_scans);                       // grid (lanes)
 __global__ void k_scatter(const __grid_constant__ Batch<ScatterArgs> B);                                       // grid (blocks, lanes)
-__global__ void k_ring_features(const __grid_constant__ Batch<RingFeatArgs> B, int n_scans, float leaf, int max_ring);        // grid (rings, lanes), 512 threads
+__global__ void k_ring_features(const __grid_constant__ Batch<RingFeatArgs> B, int n_scans, float leaf, int max_ring);        // grid (2 * rings, 1), clusters of 2 CTAs x 512 threads
 __global__ void k_ring_features_batch(const __grid_constant__ Batch<RingFeatArgs> B, int n_scans, float leaf, int max_ring);  // same, 256 threads (batches)
 __global__ void k_compact(const __grid_constant__ Batch<CompactArgs> B, int n_scans, int max_ring);           // grid (rings, lanes)
 
