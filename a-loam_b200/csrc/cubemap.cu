@@ -423,8 +423,15 @@ int mapper_step_device(aloam_ctx* c, const Pt4* d_corner_last, const int* d_nc, 
   launch_ex(c, KID_CUBES, k_mapper_begin, dim3(1), dim3(1024), 0, 1, true, S, d_odom7, m->max_sub);
   launch_ex(c, KID_CUBES, k_mapper_gather, dim3(dim3(kMaxValid, 2)), dim3(256), 0, 1, true, (const MapperState*)S, (const Pt4*)m->d_pts[0], (const Pt4*)m->d_pts[1], m->cap[0], m->cap[1],
          m->d_sub[0], m->d_sub[1]);
-  launch_ex(c, KID_MAP_GRID, k_grid_setup, dim3(1), dim3(32), 0, 1, true, c->map_corner.grid, (const int*)&S->n_sub[0], c->map_surf.grid, (const int*)&S->n_sub[1]);
-  map_index_build(c, m->d_sub[0], m->d_sub[1], m->max_sub);
+  if (c->shard_count > 1) {
+    // A rank of a sharded job keeps the WHOLE cube store (the insertions below are replicated: the refined pose is bit-identical
+    // on every rank) but indexes and searches only its x-slabs (+ halo) of the submap; the ranks meet in the all-reduce of the
+    // normal equations inside the solve.  The too-thin test of k_mapper_prep is on the whole submap, the same on every rank.
+    rc = map_shard_index_device(c, m->d_sub[0], &S->n_sub[0], m->d_sub[1], &S->n_sub[1], m->max_sub, &S->err); if (rc) return rc;
+  } else {
+    launch_ex(c, KID_MAP_GRID, k_grid_setup, dim3(1), dim3(32), 0, 1, true, c->map_corner.grid, (const int*)&S->n_sub[0], c->map_surf.grid, (const int*)&S->n_sub[1]);
+    map_index_build(c, m->d_sub[0], m->d_sub[1], m->max_sub);
+  }
   c->have_map = true;
   // ---- stack filters (:541-550): one segmented pass for both clouds
   launch_ex(c, KID_VOXEL, k_seg_two, dim3(1), dim3(32), 0, 1, true, m->d_segs, m->d_nseg, d_corner_last, d_nc, c->cfg.line_res, c->d_stack_corner, &S->stack_counts[0], d_surf_last, d_ns,

@@ -186,7 +186,10 @@ __device__ __forceinline__ bool in_shard(float x, float inv_cs, int rank, int wo
   const int cx = cell_of(x, inv_cs);
   return owner_of(cx, world) == rank || owner_of(cx - 1, world) == rank || owner_of(cx + 1, world) == rank;
 }
-__global__ void __launch_bounds__(256) k_shard_count(const float* __restrict__ pts, int stride, int n, float inv_cs, int rank, int world, int* __restrict__ block_cnt) {
+// (n_ptr != nullptr: the number of points lives on the device -- the submap gathered by the mapper -- and n is only the launch bound)
+__global__ void __launch_bounds__(256) k_shard_count(const float* __restrict__ pts, int stride, int n, const int* __restrict__ n_ptr, float inv_cs, int rank, int world,
+                                                     int* __restrict__ block_cnt) {
+  if (n_ptr) n = min(n, *n_ptr);
   const int i = blockIdx.x * 256 + threadIdx.x;
   const bool keep = i < n && in_shard(pts[(size_t)i * stride], inv_cs, rank, world);
   const int c = __syncthreads_count(keep);
@@ -216,9 +219,10 @@ __global__ void __launch_bounds__(1024) k_shard_scan(int* __restrict__ block_cnt
   }
   if (t == 0) *base_total = s_carry;
 }
-__global__ void __launch_bounds__(256) k_shard_scatter(const float* __restrict__ pts, int stride, int n, float inv_cs, int rank, int world,
+__global__ void __launch_bounds__(256) k_shard_scatter(const float* __restrict__ pts, int stride, int n, const int* __restrict__ n_ptr, float inv_cs, int rank, int world,
                                                        const int* __restrict__ block_off, Pt4* __restrict__ out, int cap, int* __restrict__ err) {
   __shared__ int s_w[8];
+  if (n_ptr) n = min(n, *n_ptr);
   const int i = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   Pt4 p = {0.f, 0.f, 0.f, 0.f};
   bool keep = false;
@@ -664,6 +668,30 @@ void map_register_device(aloam_ctx* c, const Pt4* d_corner_stack, const Pt4* d_s
   }
 }
 
+// The mapper of a rank of a sharded job (cubemap.cu): the gathered submap (whole, device-resident, sizes on the device) is cut
+// into this rank's x-slabs + halo and indexed, all in stream order -- nothing returns to the host.  An overflow of the shard
+// buffer sets bit 0 of *err_word.
+int map_shard_index_device(aloam_ctx* c, const Pt4* sub_corner, const int* n_corner, const Pt4* sub_surf, const int* n_surf, int n_upper, int* err_word) {
+  const Pt4* subs[2] = {sub_corner, sub_surf};
+  const int* ns[2] = {n_corner, n_surf};
+  int* d_cnt = c->d_stack_counts;    // [0], [1]: points kept per cloud (the mapper keeps its stack counts in its own state)
+  int* d_blocks = reinterpret_cast<int*>(c->d_nbr);
+  const int nb = std::max(1, (n_upper + 255) / 256);
+  if ((size_t)nb * 4 > (size_t)2 * c->max_points * 5 * sizeof(float4)) return ALOAM_ERR_CAPACITY;
+  CUDA_CHECK_RET(cudaMemsetAsync(d_cnt, 0, 8, c->stream));
+  const float inv_cs = c->map_corner.grid.inv_cs;
+  for (int t = 0; t < 2; ++t) {
+    LAUNCH(c, KID_MAP_GRID, k_shard_count, nb, 256, 0, reinterpret_cast<const float*>(subs[t]), 4, n_upper, ns[t], inv_cs, c->shard_rank, c->shard_count, d_blocks);
+    LAUNCH(c, KID_MAP_GRID, k_shard_scan, 1, 1024, 0, d_blocks, nb, d_cnt + t);
+    LAUNCH(c, KID_MAP_GRID, k_shard_scatter, nb, 256, 0, reinterpret_cast<const float*>(subs[t]), 4, n_upper, ns[t], inv_cs, c->shard_rank, c->shard_count, (const int*)d_blocks,
+           c->d_map_pts[t], c->max_map, err_word);
+  }
+  LAUNCH(c, KID_MAP_GRID, k_grid_setup, 1, 32, 0, c->map_corner.grid, (const int*)d_cnt, c->map_surf.grid, (const int*)(d_cnt + 1));
+  map_index_build(c, c->d_map_pts[0], c->d_map_pts[1], c->max_map);
+  CUDA_CHECK_RET(cudaGetLastError());
+  return ALOAM_OK;
+}
+
 extern "C" {
 
 void aloam_map_free_impl(aloam_ctx* c) {
@@ -746,9 +774,9 @@ int aloam_map_upload_sharded(aloam_ctx* c, aloam_cloud_view corner_map, aloam_cl
       }
       const int nb = (m + 255) / 256;
       if ((size_t)nb * 4 > (size_t)2 * c->max_points * 5 * sizeof(float4)) return ALOAM_ERR_CAPACITY;
-      LAUNCH(c, KID_MAP_GRID, k_shard_count, nb, 256, 0, src, stride, m, inv_cs, c->shard_rank, c->shard_count, d_blocks);
+      LAUNCH(c, KID_MAP_GRID, k_shard_count, nb, 256, 0, src, stride, m, (const int*)nullptr, inv_cs, c->shard_rank, c->shard_count, d_blocks);
       LAUNCH(c, KID_MAP_GRID, k_shard_scan, 1, 1024, 0, d_blocks, nb, d_cnt + t);
-      LAUNCH(c, KID_MAP_GRID, k_shard_scatter, nb, 256, 0, src, stride, m, inv_cs, c->shard_rank, c->shard_count, (const int*)d_blocks, c->d_map_pts[t], c->max_map, d_cnt + 2);
+      LAUNCH(c, KID_MAP_GRID, k_shard_scatter, nb, 256, 0, src, stride, m, (const int*)nullptr, inv_cs, c->shard_rank, c->shard_count, (const int*)d_blocks, c->d_map_pts[t], c->max_map, d_cnt + 2);
     }
   }
   LAUNCH(c, KID_MAP_GRID, k_grid_setup, 1, 32, 0, c->map_corner.grid, (const int*)d_cnt, c->map_surf.grid, (const int*)(d_cnt + 1));

@@ -149,7 +149,10 @@ int aloam_scan_stream_batch(aloam_ctx* ctx, const aloam_cloud_view* raws, int n_
  * per scan, on its own stream, overlapping the odometry of the following scans) -- what the reference ships over
  * /laser_cloud_corner_last, /laser_cloud_surf_last and /laser_odom_to_init (laserOdometry.cpp:570-591 ->
  * laserMapping.cpp:278-288, 142-152).  odom_poses / map_poses: n_scans x 7 doubles (q xyzw, t): laser_odom_to_init and
- * aft_mapped_to_init.  Identical to calling aloam_scan_to_pose + aloam_mapper_step per scan.  Needs cfg.max_map_points > 0. */
+ * aft_mapped_to_init.  Identical to calling aloam_scan_to_pose + aloam_mapper_step per scan.  Needs cfg.max_map_points > 0.
+ * After aloam_comm_init (every rank fed the same scans) the scan-to-map stage is sharded: each rank keeps the whole cube store,
+ * indexes and searches only its x-slabs of the gathered submap, and the ranks meet in the all-reduce of the normal equations;
+ * all ranks return the same poses (equal to a single-GPU run to rounding of the summation order). */
 int aloam_scan_stream_mapped(aloam_ctx* ctx, const aloam_cloud_view* raws, int n_scans, int device_resident, double* odom_poses,
                              double* map_poses, aloam_stats* stats_last);
 int aloam_reset_odometry(aloam_ctx* ctx); /* forget pose, warm start and "last" clouds (all trajectories) */

@@ -69,6 +69,28 @@ def main():
           % (rank, world, int(shard.shard_mask(cmap, rank, world).sum()), int(shard.shard_mask(smap, rank, world).sum()), len(cmap), len(smap),
              counts.tolist(), st_ref["n_corner_corr"], st_ref["n_plane_corr"], dt, dq, st_sh["lm_iters"], st_ref["lm_iters"]), flush=True)
     ok = dt < 1e-9 and dq < 1e-12 and st_sh["lm_iters"] == st_ref["lm_iters"] and counts.tolist() == [st_ref["n_corner_corr"], st_ref["n_plane_corr"]] and split_ok
+    # ---- the whole mapping loop on a rank of a sharded job: cube store replicated, submap index + 5-NN + normal equations sharded
+    # (aloam_scan_stream_mapped = odometry -> aloam_mapper_step per scan on the device) against a context without a communicator
+    raws = [synth.scan("HDL-64", k) for k in range(5)]
+    single = pkg.Aloam(n_scans=64, device=local, max_points=200000, max_map_points=600000)
+    o_ref, m_ref = single.scan_stream_mapped([r.ctypes.data for r in raws], [r.shape[0] for r in raws], False)
+    ms_ref = single.mapper_state()
+    single.close()
+    ctx.reset_odometry()
+    ctx.mapper_reset()
+    o_sh, m_sh = ctx.scan_stream_mapped([r.ctypes.data for r in raws], [r.shape[0] for r in raws], False)
+    ms_sh = ctx.mapper_state()
+    loop_dt = float(np.abs(m_sh[:, 4:] - m_ref[:, 4:]).max())
+    loop_dq = float(np.abs(np.abs(np.sum(m_sh[:, :4] * m_ref[:, :4], axis=1)) - 1.0).max())
+    moved = float(np.abs(m_ref[:, 4:] - o_ref[:, 4:]).max())   # the refinement did something
+    loop_ok = (np.array_equal(o_sh, o_ref) and loop_dt < 1e-9 and loop_dq < 1e-12 and ms_sh["centre"] == ms_ref["centre"] and ms_sh["valid"] == ms_ref["valid"]
+               and abs(ms_sh["total_corner"] - ms_ref["total_corner"]) <= 5 and abs(ms_sh["total_surf"] - ms_ref["total_surf"]) <= 20 and moved > 0)
+    print("rank %d/%d: mapping loop over %d scans, sharded vs single GPU: |dt| %.3e, 1-|dq| %.3e, cube store %d+%d vs %d+%d pts, refinement moved the pose by %.3e m"
+          % (rank, world, len(raws), loop_dt, loop_dq, ms_sh["total_corner"], ms_sh["total_surf"], ms_ref["total_corner"], ms_ref["total_surf"], moved), flush=True)
+    ok = ok and loop_ok
+    ml = torch.tensor(m_sh.reshape(-1), device="cuda"); mlo = ml.clone(); mhi = ml.clone()
+    dist.all_reduce(mlo, op=dist.ReduceOp.MIN); dist.all_reduce(mhi, op=dist.ReduceOp.MAX)
+    ok = ok and bool(torch.equal(mlo, mhi))   # every rank refined to the identical poses
     # all ranks must hold the identical pose
     xs = torch.tensor(x_sh, device="cuda"); lo = xs.clone(); hi = xs.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
