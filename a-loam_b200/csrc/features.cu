@@ -544,12 +544,11 @@ size_t ring_features_smem_bytes(int maxr, bool merge) {
 __device__ __forceinline__ unsigned cluster_cta_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ unsigned ld_dsmem_u32(const void* local, unsigned rank) {   // the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void st_dsmem_s8(void* local, unsigned rank, int v) {   // the same shared-memory offset in CTA `rank` of the cluster
   const unsigned a = (unsigned)__cvta_generic_to_shared(local);
-  unsigned ra, v;
+  unsigned ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(ra) : "memory");
-  return v;
+  asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
 }
 
 // RFT = threads of a ring CTA: six warps walk the segments, all of them load, sort and sum.
@@ -559,7 +558,7 @@ __device__ __forceinline__ unsigned ld_dsmem_u32(const void* local, unsigned ran
 //                  sort of the ring, which is made INDEPENDENT of the picks: it sorts every in-range position by its absolute voxel
 //                  coordinates (floor(z/leaf), floor(y/leaf), floor(x/leaf)) -- the same order as PCL's index relative to the
 //                  bounding box of the candidates, because that index is lexicographic in (z, y, x) -- and removes the picked
-//                  positions afterwards, reading rank 0's labels through distributed shared memory.  The two halves overlap;
+//                  positions afterwards, using rank 0's labels, which rank 0 pushes into rank 1's shared memory (DSMEM stores).  The two halves overlap;
 //                  the chain is max(picks, sort) + centroids instead of their sum.
 template <int RFT, bool PAIR>
 __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B, int n_scans, float leaf, int MAXR) {
@@ -587,7 +586,7 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
   unsigned long long* keys2 = reinterpret_cast<unsigned long long*>(smem + (((size_t)(fb + MAXR - smem) + 15) & ~(size_t)15));   // [PW], 512-thread kernel only
   __shared__ unsigned short s_less[6][20], s_flat[6][4];
   __shared__ int s_nl[6], s_nf[6];
-  __shared__ unsigned s_spill[6];
+  __shared__ unsigned s_spill[6], s_in[6];
   __shared__ int s_i[RFT / 32];
   __shared__ float s_red[6][RFT / 32];
 
@@ -605,8 +604,10 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
   }
   // scanStartInd = g0+5, scanEndInd = g0+nr-6 ; skip ring if end - start < 6 (:279)
   const int s_loc = 5, e_loc = nr - 6;
-  if (role != 2)
-    for (int i = tid; i < nr; i += blockDim.x) { label[i] = 0; if (dbg_label) dbg_label[g0 + i] = 0; if (dbg_curv) dbg_curv[g0 + i] = 0.f; }
+  for (int i = tid; i < nr; i += blockDim.x) {
+    label[i] = 0;
+    if (role != 2) { if (dbg_label) dbg_label[g0 + i] = 0; if (dbg_curv) dbg_curv[g0 + i] = 0.f; }
+  }
   if (e_loc - s_loc < 6) {
     if (tid == 0 && role != 2) counts[0] = counts[1] = counts[2] = counts[3] = 0;
     return;
@@ -642,6 +643,9 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
       asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
   }
   __syncthreads();
+  // pair, barrier Z: the voxel CTA's label array is zeroed -- the picks CTA will PUSH the few non-zero labels into it
+  if (role != 0) cluster_arrive();
+  if (role == 2) cluster_wait();
 
   if (role != 2) {
   // curvature (:256-266) for local 5 .. nr-6, left-to-right float sums ; gap bits (whole warps iterate together)
@@ -698,26 +702,42 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     run_segment(warp - 1, 0u);
     if (dbg8 && lane == 0) g_dbg_pick[9 + 2 * (warp - 1)] = clock64();
   }
-  __syncthreads();
+  if (tid < 6) s_in[tid] = 0u;   // the incoming spill every segment was walked with
   if (dbg8 && tid == 0) g_dbg_pick[6] = clock64();
-  for (int w = 1; w < 6; ++w) {
-    if (warp == w + 1) {
-      const unsigned in = s_spill[w - 1];
-      if (in != 0u) {
+  // Fixed-point rounds instead of a sequential sweep over the boundaries: every segment compares the spill its predecessor
+  // CURRENTLY reports (S) with the one it was walked with (A) and walks again, all such segments in parallel, if the difference
+  // can matter: a mark it assumed is not there (A & ~S), or a new mark sits on one of its own picks.  Otherwise its result is
+  // also the result for S.  When a round changes nothing every segment is consistent with its predecessor, and segment 0
+  // (no predecessor) is exact, so by induction all are; the lowest inconsistent segment becomes final in every round, hence
+  // at most five rounds -- typically one, where the sequential sweep paid one walk per conflict.
+  for (;;) {
+    __syncthreads();
+    bool need = false;
+    unsigned S = 0u;
+    if (warp >= 2 && warp <= 6) {
+      const int w = warp - 1;
+      S = s_spill[w - 1];
+      const unsigned Ain = s_in[w];
+      if (S != Ain) {
         const int sp = s_loc + span * w / 6;
         const int nl = s_nl[w], nf = s_nf[w];
-        bool hit = false;
-        if (lane < nl) { const int k = (int)s_less[w][lane] - sp; hit = k < 5 && ((in >> k) & 1u); }
-        if (lane >= 24 && lane - 24 < nf) { const int k = (int)s_flat[w][lane - 24] - sp; hit = hit || (k < 5 && ((in >> k) & 1u)); }
-        const bool rerun = __any_sync(0xffffffffu, hit);
-        __syncwarp();   // the reads of s_less / s_flat above are ordered before the re-run's writes (votes do not order memory)
-        if (rerun) run_segment(w, in);
+        const unsigned fresh = S & ~Ain;
+        bool hit = (Ain & ~S) != 0u;
+        if (lane < nl) { const int k = (int)s_less[w][lane] - sp; hit = hit || (k < 5 && ((fresh >> k) & 1u)); }
+        if (lane >= 24 && lane - 24 < nf) { const int k = (int)s_flat[w][lane - 24] - sp; hit = hit || (k < 5 && ((fresh >> k) & 1u)); }
+        need = __any_sync(0xffffffffu, hit);
       }
     }
-    __syncthreads();
+    if (!__syncthreads_or(need ? 1 : 0)) break;   // (also orders this round's reads of s_spill / s_less before the walks' writes)
+    if (warp >= 2 && warp <= 6) {
+      const int w = warp - 1;
+      if (need) run_segment(w, S);
+      if (lane == 0) s_in[w] = S;   // walked with S, or its result is the result for S as well
+    }
   }
   if (dbg8 && tid == 0) g_dbg_pick[7] = clock64();
   // labels (:303,309,355) and ring-ordered outputs (ring, segment, pick order) from the per-segment lists
+  if (role == 1) { __syncwarp(); cluster_wait(); }   // barrier Z (arrived at the start): the voxel CTA has zeroed its labels
   if (tid < 6 * 24) {
     const int w = tid / 24, i = tid % 24;
     int o_sh = 0, o_ls = 0, o_fl = 0;
@@ -725,12 +745,14 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     if (i < s_nl[w]) {
       const int p = s_less[w][i];
       label[p] = i < 2 ? 2 : 1;
+      if (role == 1) st_dsmem_s8(label + p, 1u, i < 2 ? 2 : 1);
       if (i < 2) st_sharp[ring * 12 + o_sh + i] = pts[p];
       st_less_sharp[ring * 120 + o_ls + i] = pts[p];
     }
     if (i >= 20 && i - 20 < s_nf[w]) {
       const int p = s_flat[w][i - 20];
       label[p] = -1;
+      if (role == 1) st_dsmem_s8(label + p, 1u, -1);
       st_flat[ring * 24 + o_fl + (i - 20)] = pts[p];
     }
     if (tid == 0) {
@@ -740,15 +762,11 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     }
   }
   __syncthreads();
-  if (role == 1) cluster_arrive();   // barrier A (release): the labels are final
+  if (role == 1) cluster_arrive();   // barrier A (release): the labels are final and pushed
   if (stamp && tid == 0) dbg[3] = clock64();
   if (dbg_label) for (int i = tid; i < nr; i += blockDim.x) dbg_label[g0 + i] = label[i];
-  if (role == 1) {
-    // A completes when the voxel CTA has sorted ; B when it has copied the labels out of this CTA's shared memory, which
-    // therefore has to stay alive until then
+  if (role == 1) {   // nothing of this CTA is read remotely: it leaves as soon as the barrier phase is complete
     __syncwarp();
-    cluster_wait();
-    cluster_arrive();
     cluster_wait();
     return;
   }
@@ -825,14 +843,10 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
       });
       if (stamp && tid == 0) dbg[5] = clock64();
     }
-    // barrier A: rank 0's labels are final ; copy them (4 positions per word) ; barrier B releases rank 0
+    // barrier A (acquire): rank 0's labels are final and sit in this CTA's label array
     __syncwarp();
     cluster_arrive();
     cluster_wait();
-    unsigned* lw = reinterpret_cast<unsigned*>(label);
-    for (int w4 = tid; w4 < (nr + 3) / 4; w4 += blockDim.x) lw[w4] = ld_dsmem_u32(lw + w4, 0u);
-    __syncthreads();
-    cluster_arrive();
   }
 
   bool overflow = false;
@@ -922,7 +936,6 @@ __device__ __forceinline__ void ring_features_body(const Batch<RingFeatArgs>& B,
     o_lf[h] = o;
   }
   if (tid == 0) { counts[3] = total; if (stamp) dbg[6] = clock64(); }
-  if (role == 2) { __syncwarp(); cluster_wait(); }   // barrier B (rank 0 arrived long ago)
 }
 
 // grid (2 * rings, 1), clusters of two CTAs
