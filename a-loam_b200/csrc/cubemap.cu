@@ -72,6 +72,8 @@ struct Mapper {
   SegBuffers buf;
   double* d_pose_io = nullptr;              // [14] host API: odometry pose in, refined pose out
   int max_sub = 0;
+  cudaStream_t s_aux = nullptr;             // the stack filters run here, beside the submap gather + index build
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 // ---- Eigen-order quaternion helpers (operation order of Eigen::Quaternion: the pose hand-off is compared bit for bit)
@@ -262,11 +264,15 @@ __global__ void k_mapper_update(MapperState* S, double* __restrict__ out7) {
 }
 
 // pointAssociateToMap (:154-163) in double, stored as float, then the cube of the stored point (:741-758)
-__global__ void k_cube_ids(const Pt4* __restrict__ stack, const int* __restrict__ n_ptr, const MapperState* __restrict__ S, Pt4* __restrict__ world,
-                           int* __restrict__ cube) {
+// blockIdx.y = cloud (0 corner stack, 1 surf stack); the scratch of cloud 1 starts `scratch_stride` elements in
+__global__ void k_cube_ids(const Pt4* __restrict__ stack0, const Pt4* __restrict__ stack1, const MapperState* __restrict__ S, Pt4* __restrict__ world,
+                           int* __restrict__ cube, int scratch_stride) {
   pdl_launch_dependents();
   pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
-  const int n = *n_ptr;
+  const int which = blockIdx.y;
+  const Pt4* __restrict__ stack = which ? stack1 : stack0;
+  world += (size_t)which * scratch_stride; cube += (size_t)which * scratch_stride;
+  const int n = S->stack_counts[which];
   const double ux = S->x[0], uy = S->x[1], uz = S->x[2], w = S->x[3], tx = S->x[4], ty = S->x[5], tz = S->x[6];
   const int c0 = S->cen[0], c1 = S->cen[1], c2 = S->cen[2];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -286,17 +292,22 @@ __global__ void k_cube_ids(const Pt4* __restrict__ stack, const int* __restrict_
   }
 }
 
-// stable append of the stack points to their cubes (push_back order = stack order, :759-767).  ONE CTA: the stack is walked in
+// stable append of the stack points to their cubes (push_back order = stack order, :759-767).  ONE CTA per cloud (blockIdx.x: the
+// corner and the surf store are independent, the two appends run side by side): the stack is walked in
 // chunks of 1024; inside a chunk the warps take turns, the lanes of one cube form a group (__match_any) whose leader
 // advances the cube's running end in shared memory -- and takes a slab from the free list when the cube had none.
-__global__ void __launch_bounds__(1024) k_cube_insert(const Pt4* __restrict__ world, const int* __restrict__ cube, const int* __restrict__ n_ptr,
-                                                      MapperState* S, int ty, Pt4* __restrict__ pts, int cap) {
+__global__ void __launch_bounds__(1024) k_cube_insert(const Pt4* __restrict__ world, const int* __restrict__ cube, int scratch_stride, MapperState* S,
+                                                      Pt4* __restrict__ pts0, int cap0, Pt4* __restrict__ pts1, int cap1) {
   pdl_launch_dependents();
   pdl_wait();   // may have been launched with a programmatic dependency on the previous kernel of the stream
+  const int ty = blockIdx.x;
+  world += (size_t)ty * scratch_stride; cube += (size_t)ty * scratch_stride;
+  Pt4* __restrict__ pts = ty ? pts1 : pts0;
+  const int cap = ty ? cap1 : cap0;
   __shared__ int s_end[NCUBE];    // running end of every cube
   __shared__ int s_slab[NCUBE];   // cube -> slab (the warps' turns must not wait on global memory)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = *n_ptr;
+  const int n = S->stack_counts[ty];
   int* slab_of = S->slab_of[ty];
   int* cnt = S->cnt[ty];
   for (int c = tid; c < NCUBE; c += blockDim.x) { const int s = slab_of[c]; s_slab[c] = s; s_end[c] = s < 0 ? 0 : cnt[s]; }
@@ -365,8 +376,8 @@ int ensure_mapper(aloam_ctx* c) {
     ok = ok && cudaMalloc((void**)&m->d_sub[t], (size_t)m->max_sub * sizeof(Pt4)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&m->d_in[t], (size_t)c->max_points * sizeof(Pt4)) == cudaSuccess;
   }
-  ok = ok && cudaMalloc((void**)&m->d_world, (size_t)c->max_points * sizeof(Pt4)) == cudaSuccess;
-  ok = ok && cudaMalloc((void**)&m->d_cube, (size_t)c->max_points * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&m->d_world, (size_t)2 * c->max_points * sizeof(Pt4)) == cudaSuccess;   // both stacks side by side
+  ok = ok && cudaMalloc((void**)&m->d_cube, (size_t)2 * c->max_points * sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&m->d_state, sizeof(MapperState)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&m->h_state, sizeof(MapperState)) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&m->d_segs, ALOAM_MAX_SEGS * sizeof(SegDesc)) == cudaSuccess;
@@ -376,6 +387,8 @@ int ensure_mapper(aloam_ctx* c) {
   ok = ok && cudaMalloc((void**)&m->d_bbox, ALOAM_MAX_SEGS * 6 * sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&m->d_total, 16) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&m->d_pose_io, 16 * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&m->s_aux, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) == cudaSuccess;
   // the re-filter sorts every point of the valid cubes (<= the submap capacity per type), the stack filter two scan clouds
   ok = ok && vox_seg_alloc(m->buf, std::max((size_t)2 * m->max_sub, (size_t)2 * c->max_points)) == ALOAM_OK;
   if (!ok) {   // publish nothing half-built
@@ -400,6 +413,9 @@ extern "C" void aloam_mapper_free_impl(aloam_ctx* c) {
   Mapper* m = static_cast<Mapper*>(c->mapper);
   if (!m) return;
   for (int t = 0; t < 2; ++t) { if (m->d_pts[t]) cudaFree(m->d_pts[t]); if (m->d_sub[t]) cudaFree(m->d_sub[t]); if (m->d_in[t]) cudaFree(m->d_in[t]); }
+  if (m->s_aux) { cudaStreamSynchronize(m->s_aux); cudaStreamDestroy(m->s_aux); }
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
   void* ps[] = {m->d_world, m->d_cube, m->d_state, m->d_segs, m->d_nseg, m->d_off, m->d_rank0, m->d_bbox, m->d_total, m->d_pose_io};
   for (void* p : ps) if (p) cudaFree(p);
   if (m->h_state) cudaFreeHost(m->h_state);
@@ -420,6 +436,21 @@ int mapper_step_device(aloam_ctx* c, const Pt4* d_corner_last, const int* d_nc, 
     aloam_cloud_view none{nullptr, 0, 4};
     rc = aloam_map_upload_impl(c, none, none); if (rc) return rc;
   }
+  // ---- stack filters (:541-550): one segmented pass for both clouds.  They read only the scan's clouds, the gather + index
+  // build below only the cube store: two independent chains, the filters forked onto an auxiliary stream and joined before the
+  // registration.
+  {
+    cudaStream_t main_stream = c->stream;
+    CUDA_CHECK_RET(cudaEventRecord(m->ev_fork, main_stream));
+    CUDA_CHECK_RET(cudaStreamWaitEvent(m->s_aux, m->ev_fork, 0));
+    c->stream = m->s_aux;
+    launch_ex(c, KID_VOXEL, k_seg_two, dim3(1), dim3(32), 0, 1, false, m->d_segs, m->d_nseg, d_corner_last, d_nc, c->cfg.line_res, c->d_stack_corner, &S->stack_counts[0], d_surf_last, d_ns,
+              c->cfg.plane_res, c->d_stack_surf, &S->stack_counts[1]);
+    vox_seg_filter(c, make_filter(m, 31), m->buf, 2, n_upper_c + n_upper_s, std::max(n_upper_c, n_upper_s));
+    const cudaError_t e = cudaEventRecord(m->ev_join, m->s_aux);
+    c->stream = main_stream;
+    CUDA_CHECK_RET(e);
+  }
   launch_ex(c, KID_CUBES, k_mapper_begin, dim3(1), dim3(1024), 0, 1, true, S, d_odom7, m->max_sub);
   launch_ex(c, KID_CUBES, k_mapper_gather, dim3(dim3(kMaxValid, 2)), dim3(256), 0, 1, true, (const MapperState*)S, (const Pt4*)m->d_pts[0], (const Pt4*)m->d_pts[1], m->cap[0], m->cap[1],
          m->d_sub[0], m->d_sub[1]);
@@ -433,22 +464,17 @@ int mapper_step_device(aloam_ctx* c, const Pt4* d_corner_last, const int* d_nc, 
     map_index_build(c, m->d_sub[0], m->d_sub[1], m->max_sub);
   }
   c->have_map = true;
-  // ---- stack filters (:541-550): one segmented pass for both clouds
-  launch_ex(c, KID_VOXEL, k_seg_two, dim3(1), dim3(32), 0, 1, true, m->d_segs, m->d_nseg, d_corner_last, d_nc, c->cfg.line_res, c->d_stack_corner, &S->stack_counts[0], d_surf_last, d_ns,
-         c->cfg.plane_res, c->d_stack_surf, &S->stack_counts[1]);
-  vox_seg_filter(c, make_filter(m, 31), m->buf, 2, n_upper_c + n_upper_s, std::max(n_upper_c, n_upper_s));
+  CUDA_CHECK_RET(cudaStreamWaitEvent(c->stream, m->ev_join, 0));   // join: the filtered stacks are ready
   launch_ex(c, KID_CUBES, k_mapper_prep, dim3(1), dim3(32), 0, 1, true, S);
   // ---- optimisation (:554-733)
   const int nq_upper = std::min(n_upper_c + n_upper_s, 2 * c->max_points);
   map_register_device(c, c->d_stack_corner, c->d_stack_surf, S->stack_counts, nq_upper, S->x, false);
   launch_ex(c, KID_CUBES, k_mapper_update, dim3(1), dim3(32), 0, 1, true, S, d_out7);
   // ---- insertion (:736-767)
-  const Pt4* stacks[2] = {c->d_stack_corner, c->d_stack_surf};
-  const int ups[2] = {n_upper_c, n_upper_s};
-  for (int t = 0; t < 2; ++t) {
-    launch_ex(c, KID_CUBES, k_cube_ids, dim3(std::max(1, std::min((ups[t] + 255) / 256, 148 * 4))), dim3(256), 0, 1, true, stacks[t], (const int*)&S->stack_counts[t], (const MapperState*)S, m->d_world, m->d_cube);
-    launch_ex(c, KID_CUBES, k_cube_insert, dim3(1), dim3(1024), 0, 1, true, (const Pt4*)m->d_world, (const int*)m->d_cube, (const int*)&S->stack_counts[t], S, t, m->d_pts[t], m->cap[t]);
-  }
+  const int up = std::max(n_upper_c, n_upper_s);
+  launch_ex(c, KID_CUBES, k_cube_ids, dim3(std::max(1, std::min((up + 255) / 256, 148 * 2)), 2), dim3(256), 0, 1, true, (const Pt4*)c->d_stack_corner, (const Pt4*)c->d_stack_surf,
+            (const MapperState*)S, m->d_world, m->d_cube, c->max_points);
+  launch_ex(c, KID_CUBES, k_cube_insert, dim3(2), dim3(1024), 0, 1, true, (const Pt4*)m->d_world, (const int*)m->d_cube, c->max_points, S, m->d_pts[0], m->cap[0], m->d_pts[1], m->cap[1]);
   // ---- per-cube re-filter of the valid cubes (:770-801): one segmented pass over <= 150 cubes, in place
   launch_ex(c, KID_CUBES, k_seg_cubes, dim3(1), dim3(256), 0, 1, true, S, m->d_segs, m->d_nseg, m->d_pts[0], m->d_pts[1], m->cap[0], m->cap[1], c->cfg.line_res, c->cfg.plane_res);
   // index bits of a 50 m cube at the finer leaf: (50 / leaf + 3)^3 voxels at most (PCL itself gives up beyond 2^31)

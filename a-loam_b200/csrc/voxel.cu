@@ -7,6 +7,7 @@
 // the voxel index, 8 bits per pass, as many passes as the index range needs), which is the CANONICAL order of the oracle.
 #include <climits>
 #include <cfloat>
+#include <cooperative_groups.h>
 #include "ctx.h"
 
 namespace aloam {
@@ -136,6 +137,87 @@ __global__ void __launch_bounds__(VT) k_radix_scatter(const unsigned* __restrict
     const int dst = s_cnt[it * (VT / 32) + w][dig[it]] + rank[it];
     keys_out[dst] = keys_in[i];
     vals_out[dst] = vals_in[i];
+  }
+}
+
+// All passes of the LSD radix sort in ONE cooperative launch (the segmented filters of the mapper sort a few 10^4 keys: twelve
+// launches of a few microseconds each were launch latency, not work).  Tiles of VCH keys go round-robin over the CTAs; per pass:
+// tile histograms -> grid barrier -> every CTA derives the offsets of its own tiles from the histogram table (thread = digit:
+// digit totals over all tiles, block-wide exclusive scan, plus the running sum over the tiles before its own) and scatters ->
+// grid barrier.  Same stable order as k_radix_hist / k_radix_scan / k_radix_scatter; the result is in buffer (passes & 1).
+__global__ void __launch_bounds__(VT) k_radix_sort_all(unsigned* __restrict__ k0, int* __restrict__ v0, unsigned* __restrict__ k1, int* __restrict__ v1,
+                                                       const int* __restrict__ n_ptr, int bits, int* __restrict__ hist) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ int s_h[256];
+  __shared__ int s_w[VT / 32];
+  __shared__ int s_cnt[VIT * (VT / 32)][256];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int n = *n_ptr;
+  const int tiles = (n + VCH - 1) / VCH;
+  int cur = 0;
+  for (int shift = 0; shift < bits; shift += 8) {   // `bits` is a launch parameter: every CTA passes the same barriers
+    const unsigned* __restrict__ kin = cur ? k1 : k0;
+    const int* __restrict__ vin = cur ? v1 : v0;
+    unsigned* __restrict__ kout = cur ? k0 : k1;
+    int* __restrict__ vout = cur ? v0 : v1;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      s_h[tid] = 0;
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < VIT; ++it) {
+        const int i = t * VCH + it * VT + tid;
+        if (i < n) atomicAdd(&s_h[(kin[i] >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      hist[t * 256 + tid] = s_h[tid];
+      __syncthreads();
+    }
+    grid.sync();
+    // thread = digit: start of the digit in the output = exclusive scan of the digit totals
+    int tot = 0, pre = 0, pre_upto = 0;   // pre = sum of hist[t'][digit] over the tiles t' < pre_upto
+    for (int t = 0; t < tiles; ++t) tot += hist[t * 256 + tid];
+    int incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    int wb = 0;
+    for (int k = 0; k < w; ++k) wb += s_w[k];
+    const int start = wb + incl - tot;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (; pre_upto < t; ++pre_upto) pre += hist[pre_upto * 256 + tid];
+      for (int k = tid; k < VIT * (VT / 32) * 256; k += VT) (&s_cnt[0][0])[k] = 0;
+      __syncthreads();
+      int dig[VIT], rank[VIT];
+#pragma unroll
+      for (int it = 0; it < VIT; ++it) {
+        const int i = t * VCH + it * VT + tid;
+        const int d = i < n ? (int)((kin[i] >> shift) & 255u) : -1;
+        dig[it] = d;
+        const unsigned grp = __match_any_sync(0xffffffffu, d);
+        rank[it] = __popc(grp & ((1u << lane) - 1u));
+        if (d >= 0 && rank[it] == 0) s_cnt[it * (VT / 32) + w][d] = __popc(grp);
+      }
+      __syncthreads();
+      {
+        int run = start + pre;
+#pragma unroll
+        for (int k = 0; k < VIT * (VT / 32); ++k) { const int c = s_cnt[k][tid]; s_cnt[k][tid] = run; run += c; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < VIT; ++it) {
+        if (dig[it] < 0) continue;
+        const int i = t * VCH + it * VT + tid;
+        const int dst = s_cnt[it * (VT / 32) + w][dig[it]] + rank[it];
+        kout[dst] = kin[i];
+        vout[dst] = vin[i];
+      }
+      __syncthreads();
+    }
+    grid.sync();
+    cur ^= 1;
   }
 }
 
@@ -469,13 +551,25 @@ void vox_seg_filter(aloam_ctx* c, const SegFilter& f_in, SegBuffers& b, int S_up
     launch_ex(c, KID_VOXEL, k_seg_prep, dim3(1), dim3(256), 0, 1, true, f);
     launch_ex(c, KID_VOXEL, k_seg_bbox, dim3(dim3(chunks, f.seg_cap)), dim3(256), 0, 1, true, f);
     launch_ex(c, KID_VOXEL, k_seg_keys, dim3(dim3(chunks, f.seg_cap)), dim3(256), 0, 1, true, f, b.keys[0], b.vals[0]);
-    int cur = 0;
-    for (int shift = 0; shift < bits; shift += 8) {
-      launch_ex(c, KID_VOXEL, k_radix_hist, dim3(nblk), dim3(VT), 0, 1, true, b.keys[cur], f.total, shift, b.hist);
-      launch_ex(c, KID_VOXEL, k_radix_scan, dim3(1), dim3(1024), 0, 1, true, b.hist, f.total, b.offs);
-      launch_ex(c, KID_VOXEL, k_radix_scatter, dim3(nblk), dim3(VT), 0, 1, true, b.keys[cur], b.vals[cur], f.total, shift, b.offs, b.keys[cur ^ 1], b.vals[cur ^ 1]);
-      cur ^= 1;
+    // the radix passes: one cooperative launch (all CTAs co-resident, at most one per SM)
+    static int coop_cap = 0;
+    if (!coop_cap) {
+      int per_sm = 0, sms = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_radix_sort_all, VT, 0);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device);
+      coop_cap = std::max(1, std::min(sms, per_sm * sms));
     }
+    {
+      prof_begin(c, KID_VOXEL);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(std::min(nblk, coop_cap)); cfg.blockDim = dim3(VT); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, k_radix_sort_all, b.keys[0], b.vals[0], b.keys[1], b.vals[1], (const int*)f.total, bits, b.hist);
+      prof_end(c);
+    }
+    const int cur = ((bits + 7) / 8) & 1;
     launch_ex(c, KID_VOXEL, k_vox_heads, dim3(nblk), dim3(VT), 0, 1, true, b.keys[cur], f.total, b.block_heads);
     launch_ex(c, KID_VOXEL, k_vox_blockscan, dim3(1), dim3(1024), 0, 1, true, b.block_heads, f.total, b.heads_total);
     launch_ex(c, KID_VOXEL, k_seg_rank0, dim3(f.seg_cap + 1), dim3(32), 0, 1, true, f, b.keys[cur], b.block_heads);
