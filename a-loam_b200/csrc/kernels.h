@@ -139,7 +139,7 @@ struct LmSummary {
   int n_edge, n_plane;      // residual blocks by kind
   double initial_cost, final_cost;
   int trace_rows; int pad;
-  long long cyc_total, cyc_eval, cyc_chol, cyc_plus, cyc_grad;   // SM clock cycles (thread 0 of CTA 0): whole solve / evaluation passes / step solve / Plus / gradient norm
+  long long cyc_total, cyc_eval, cyc_chol, cyc_plus, cyc_grad;   // SM clock cycles (thread 0 of CTA 0): whole solve / evaluation passes / trust-region steps / residual blocks of the thread / cluster barriers
   double trace[ALOAM_LM_MAX_TRACE][8];
 };
 // mode 0: full trust-region solve, x updated in place ; mode 1: one evaluation, out28 = [JtJ upper 21, g 6, cost]

@@ -246,7 +246,7 @@ struct TrState {
 
 // max-norm of Plus(x, -g) - x.  The translation part is |g_t| exactly; the quaternion part (sin / cos / sqrt in double)
 // is only evaluated when it can change the `<= tol` decision, i.e. when the translation part is already <= tol.
-__device__ double gradient_max(const double* x, const double* g, double tol) {
+__device__ __forceinline__ double gradient_max(const double* x, const double* g, double tol) {
   const double mt = fmax(fmax(fabs(g[3]), fabs(g[4])), fabs(g[5]));
   if (mt > tol) return mt;
   double ng[6], xp[7];
@@ -299,11 +299,14 @@ __device__ __forceinline__ bool chol_solve6(const double (&Hs)[6][6], const doub
   return ok;
 }
 
-__device__ __forceinline__ void tr_trace(TrState& T, LmSummary* summary, bool writer, double c, double cc, double gm, double sn,
+// `trace` = where the rows go: a shared-memory staging array in the cluster kernel (flushed once by tr_finish: a store through the
+// generic `summary` pointer in the middle of the step would force the compiler to re-read everything it holds from shared memory),
+// summary->trace itself in the sharded path
+__device__ __forceinline__ void tr_trace(TrState& T, double (*trace)[8], bool writer, double c, double cc, double gm, double sn,
                                          double rd, double rad, int valid, int succ) {
   if (T.trace_rows < ALOAM_LM_MAX_TRACE) {
     if (writer) {
-      double* o = summary->trace[T.trace_rows];
+      double* o = trace[T.trace_rows];
       o[0] = c; o[1] = cc; o[2] = gm; o[3] = sn; o[4] = rd; o[5] = rad; o[6] = valid; o[7] = succ;
     }
     ++T.trace_rows;
@@ -311,7 +314,7 @@ __device__ __forceinline__ void tr_trace(TrState& T, LmSummary* summary, bool wr
 }
 
 // produce the next candidate (-> T.xc, T.go = 1) or stop (T.go = 0).  A = packed totals of the accepted point.
-__device__ void tr_next_candidate(TrState& T, const double* A, const LmParams& prm, LmSummary* summary, bool writer) {
+__device__ __forceinline__ void tr_next_candidate(TrState& T, const double* A, const LmParams& prm, double (*trace)[8], bool writer) {
   double sc[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) sc[j] = T.scale[j];
@@ -348,9 +351,9 @@ __device__ void tr_next_candidate(TrState& T, const double* A, const LmParams& p
     }
     T.mcc = mcc;
     if (!(ok && mcc > 0.0)) {  // invalid step
-      if (++T.num_invalid >= prm.max_invalid) { tr_trace(T, summary, writer, T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0); T.termination = 5; T.go = 0; return; }
+      if (++T.num_invalid >= prm.max_invalid) { tr_trace(T, trace, writer, T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0); T.termination = 5; T.go = 0; return; }
       T.radius *= 0.5;
-      tr_trace(T, summary, writer, T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0);
+      tr_trace(T, trace, writer, T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0);
       continue;
     }
     T.num_invalid = 0;
@@ -364,16 +367,21 @@ __device__ void tr_next_candidate(TrState& T, const double* A, const LmParams& p
 }
 
 // iteration 0: totals of the evaluation at x ; tot[28], tot[29] = number of edge / plane blocks
-__device__ void tr_start(TrState& T, const double* x, const double* tot, const LmParams& prm, LmSummary* summary, bool writer) {
+// Returns true when the caller has to produce the first candidate (tr_next_candidate on the same totals): the big step routine
+// has ONE call site per kernel, shared with tr_after_eval.
+__device__ __forceinline__ bool tr_start(TrState& T, const double* x, const double* tot, const LmParams& prm, LmSummary* summary, bool summary_writer,
+                                         double (*trace)[8], bool writer) {
   const int ne = (int)(tot[28] + 0.5), np = (int)(tot[29] + 0.5);
 #pragma unroll
   for (int k = 0; k < 7; ++k) { T.x[k] = x[k]; T.xc[k] = x[k]; }
   T.cost = tot[27];
   T.radius = prm.initial_radius; T.decrease_factor = 2.0; T.mcc = 0; T.gmax = 0;
   T.reuse_diag = 0; T.last_successful = 0; T.iteration = 0; T.num_invalid = 0; T.num_successful = 0; T.num_evals = 1;
-  T.termination = 0; T.trace_rows = 0; T.n_res = ne + np; T.go = 0; T.acc_buf = 0;
-  if (writer) { summary->initial_cost = T.cost; summary->n_edge = ne; summary->n_plane = np; }
-  if (ne + np == 0) { T.termination = 4; return; }  // Ceres: nothing to optimise, parameters untouched
+  T.termination = 0; T.trace_rows = 0; T.n_res = ne + np; T.go = 0; T.acc_buf = 0; T.x_norm = 0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) { T.scale[j] = 0; T.diag[j] = 0; }
+  if (summary_writer) { summary->initial_cost = T.cost; summary->n_edge = ne; summary->n_plane = np; }
+  if (ne + np == 0) { T.termination = 4; return false; }  // Ceres: nothing to optimise, parameters untouched
 #pragma unroll
   for (int j = 0; j < 6; ++j) T.scale[j] = 1.0 / (1.0 + sqrt(tot[pk(j, j)]));
   T.gmax = gradient_max(T.x, tot + 21, prm.gradient_tolerance);
@@ -381,56 +389,77 @@ __device__ void tr_start(TrState& T, const double* x, const double* tot, const L
 #pragma unroll
   for (int k = 0; k < 7; ++k) xn += T.x[k] * T.x[k];
   T.x_norm = sqrt(xn);
-  tr_trace(T, summary, writer, T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0);
-  if (T.gmax <= prm.gradient_tolerance) { T.termination = 1; return; }
-  tr_next_candidate(T, tot, prm, summary, writer);
+  tr_trace(T, trace, writer, T.cost, 0, T.gmax, 0, 0, T.radius, 0, 0);
+  if (T.gmax <= prm.gradient_tolerance) { T.termination = 1; return false; }
+  return true;
 }
 
 // after the evaluation of candidate T.xc (totals `tot`; `A` = totals of the currently accepted point): tolerance tests,
-// accept / reject, next candidate.  Returns true when the candidate was accepted (its totals are the accepted ones now).
-__device__ bool tr_after_eval(TrState& T, const double* tot, const double* A, const LmParams& prm, LmSummary* summary, bool writer) {
+// accept / reject.  Returns 0 when the solve is over, 1 when the candidate was rejected, 2 when it was accepted (its totals are the
+// accepted ones now); for 1 and 2 the caller produces the next candidate.
+__device__ __forceinline__ int tr_after_eval(TrState& T, const double* tot, const LmParams& prm, double (*trace)[8], bool writer) {
   ++T.num_evals;
   const double cand_cost = tot[27];
-  double sn = 0;
+  // Every long-latency operation of the step (two square roots, three divisions) is issued up front, before the branches that
+  // decide which of them are used: they are independent of each other except radius_acc <- rho, so one thread overlaps their
+  // latencies instead of paying them one after the other.  Each value is exactly the one the branch would have computed.
+  double sn2 = 0, xn2 = 0;
 #pragma unroll
-  for (int k = 0; k < 7; ++k) sn += (T.x[k] - T.xc[k]) * (T.x[k] - T.xc[k]);
-  sn = sqrt(sn);
+  for (int k = 0; k < 7; ++k) { sn2 += (T.x[k] - T.xc[k]) * (T.x[k] - T.xc[k]); xn2 += T.xc[k] * T.xc[k]; }
+  const double sn = sqrt(sn2);
+  const double xn_cand = sqrt(xn2);                          // |xc|: the new x_norm if the step is accepted
   const double cost_change = T.cost - cand_cost;
+  const double rho = cost_change / T.mcc;                    // mcc > 0 for every candidate that was evaluated
+  const double radius_rej = T.radius / T.decrease_factor;
+  const double tq = 2.0 * rho - 1.0;
+  const double radius_acc = fmin(prm.max_radius, T.radius / fmax(1.0 / 3.0, 1.0 - tq * tq * tq));
   if (sn <= prm.parameter_tolerance * (T.x_norm + prm.parameter_tolerance)) {
-    tr_trace(T, summary, writer, T.cost, 0, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 2; T.go = 0; return false;
+    tr_trace(T, trace, writer, T.cost, 0, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 2; T.go = 0; return 0;
   }
   if (fabs(cost_change) <= prm.function_tolerance * T.cost) {
-    tr_trace(T, summary, writer, T.cost, cost_change, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 3; T.go = 0; return false;
+    tr_trace(T, trace, writer, T.cost, cost_change, T.gmax, sn, 0, T.radius, 1, 0); T.termination = 3; T.go = 0; return 0;
   }
-  const double rho = cost_change / T.mcc;
   const bool accept = rho > prm.min_relative_decrease;
   if (accept) {
-    double xn = 0;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) { T.x[k] = T.xc[k]; xn += T.xc[k] * T.xc[k]; }
-    T.x_norm = sqrt(xn);
+    for (int k = 0; k < 7; ++k) T.x[k] = T.xc[k];
+    T.x_norm = xn_cand;
     T.cost = cand_cost;
     T.gmax = gradient_max(T.x, tot + 21, prm.gradient_tolerance);
     T.last_successful = 1;
     ++T.num_successful;
-    const double tq = 2.0 * rho - 1.0;
-    T.radius = fmin(prm.max_radius, T.radius / fmax(1.0 / 3.0, 1.0 - tq * tq * tq));
+    T.radius = radius_acc;
     T.decrease_factor = 2.0;
     T.reuse_diag = 0;
-    tr_trace(T, summary, writer, T.cost, cost_change, T.gmax, sn, rho, T.radius, 1, 1);
+    tr_trace(T, trace, writer, T.cost, cost_change, T.gmax, sn, rho, T.radius, 1, 1);
   } else {
-    T.radius = T.radius / T.decrease_factor;
+    T.radius = radius_rej;
     T.decrease_factor *= 2.0;
     T.reuse_diag = 1;
-    tr_trace(T, summary, writer, T.cost, cost_change, T.gmax, sn, rho, T.radius, 1, 0);
+    tr_trace(T, trace, writer, T.cost, cost_change, T.gmax, sn, rho, T.radius, 1, 0);
   }
-  tr_next_candidate(T, accept ? tot : A, prm, summary, writer);
-  return accept;
+  return accept ? 2 : 1;
 }
 
-__device__ void tr_finish(const TrState& T, double* x7, LmSummary* summary) {
+// the part of the state the step works on, between its home (shared / global memory) and a local copy that lives in registers
+// for the duration of a step (`acc`, the sharded path's totals, stays where it is)
+__device__ __forceinline__ void tr_copy(TrState& d, const TrState& s) {
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { d.x[k] = s.x[k]; d.xc[k] = s.xc[k]; }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { d.scale[k] = s.scale[k]; d.diag[k] = s.diag[k]; }
+  d.cost = s.cost; d.radius = s.radius; d.decrease_factor = s.decrease_factor; d.mcc = s.mcc; d.gmax = s.gmax; d.x_norm = s.x_norm;
+  d.reuse_diag = s.reuse_diag; d.last_successful = s.last_successful; d.iteration = s.iteration; d.num_invalid = s.num_invalid;
+  d.num_successful = s.num_successful; d.num_evals = s.num_evals; d.termination = s.termination; d.trace_rows = s.trace_rows;
+  d.go = s.go; d.acc_buf = s.acc_buf; d.n_res = s.n_res;
+}
+
+__device__ void tr_finish(const TrState& T, double* x7, LmSummary* summary, const double (*staged_trace)[8] = nullptr) {
 #pragma unroll
   for (int k = 0; k < 7; ++k) x7[k] = T.x[k];
+  if (staged_trace)
+    for (int r = 0; r < T.trace_rows && r < ALOAM_LM_MAX_TRACE; ++r)
+      for (int k = 0; k < 8; ++k) summary->trace[r][k] = staged_trace[r][k];
   summary->termination = T.termination;
   summary->num_iterations = T.iteration;
   summary->num_successful = T.num_successful;
@@ -460,8 +489,9 @@ constexpr int RS = 30;   // doubles per thread row of the transpose scratch (240
 template <bool GENERAL, typename Cluster>
 __device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRec* __restrict__ blocks, int n, const BlockRec& rb0,
                                                  const double* xs, double huber_a, double* s_red, double (*s_part)[32],
-                                                 double (*s_in)[8][32], double* s_tot, int& pass) {
+                                                 double (*s_in)[8][32], double* s_tot, int& pass, long long& cyc_blocks, long long& cyc_barrier) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long t_a = clock64();
   const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
   const int gtid = first_block_index(crank, csize), gstride = (int)csize * NT;
   double x[7];
@@ -483,6 +513,7 @@ __device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRe
       rb = blocks[b];
     }
   }
+  cyc_blocks += clock64() - t_a;
   double2* row = reinterpret_cast<double2*>(s_red + (size_t)tid * RS);
 #pragma unroll
   for (int k = 0; k < RS / 2; ++k) row[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
@@ -507,7 +538,9 @@ __device__ __forceinline__ void cluster_evaluate(Cluster& cluster, const BlockRe
     double* slot = &s_in[pass & 1][crank][lane];
     for (unsigned r = 0; r < csize; ++r) *cluster.map_shared_rank(slot, r) = v;
   }
+  const long long t_c = clock64();
   cluster.sync();   // release / acquire: every CTA's pushes of this pass are visible
+  cyc_barrier += clock64() - t_c;
   if (warp == 0) {
     // rank order, fixed tree => identical totals in every CTA (the cluster size is 8 in every launch; ranks that do
     // not exist would read zeros written at kernel start)
@@ -601,6 +634,7 @@ __device__ __forceinline__ void lm_solve_body(const Batch<LmArgs>& B, const LmPa
   __shared__ double s_tot[2][32];   // totals of the accepted point (T.acc_buf) and of the candidate being evaluated
   __shared__ double s_x[7];
   __shared__ TrState T;
+  __shared__ double s_trace[ALOAM_LM_MAX_TRACE][8];   // trace rows of this solve, flushed by tr_finish
   const int tid = threadIdx.x;
   pdl_launch_dependents();
   // Every CTA of the cluster must have started before its shared memory is written remotely (the first push happens
@@ -619,12 +653,12 @@ __device__ __forceinline__ void lm_solve_body(const Batch<LmArgs>& B, const LmPa
   __syncthreads();
   // one evaluation site (the evaluation body is large; duplicating it costs instruction-cache misses)
   bool first = true;
-  long long cyc_eval = 0, cyc_tr = 0;
+  long long cyc_eval = 0, cyc_tr = 0, cyc_blocks = 0, cyc_barrier = 0;
   const unsigned long long seq0 = (GENERAL && px.world > 1) ? *px.seq : 0ull;
   do {
     const long long c0 = clock64();
     double* tot = s_tot[first ? 0 : 1 - T.acc_buf];
-    cluster_evaluate<GENERAL>(cluster, blocks, n, rb0, first ? s_x : T.xc, prm.huber_a, s_red, s_part, s_in, tot, pass);
+    cluster_evaluate<GENERAL>(cluster, blocks, n, rb0, first ? s_x : T.xc, prm.huber_a, s_red, s_part, s_in, tot, pass, cyc_blocks, cyc_barrier);
     if (GENERAL && px.world > 1) peer_allreduce(cluster, px, seq0 + (unsigned long long)pass, tot);   // pass was advanced: tags start at seq0 + 1
     const long long c1 = clock64();
     cyc_eval += c1 - c0;
@@ -632,10 +666,20 @@ __device__ __forceinline__ void lm_solve_body(const Batch<LmArgs>& B, const LmPa
       if (cluster.block_rank() == 0 && tid < 28) out28[tid] = tot[tid];
       return;   // all remote stores into this CTA preceded the cluster barrier inside cluster_evaluate
     }
-    // thread 0 of EVERY CTA takes the same decision from the same totals (no broadcast needed)
+    // thread 0 of EVERY CTA takes the same decision from the same totals (no broadcast needed).  The step works on a LOCAL copy
+    // of the state (registers) and of nothing else in shared memory but the two totals vectors: measured, the step was 46 % of the
+    // solve (3.6 k cycles per pass) when every field access went to shared memory behind possibly-aliasing stores.
     if (tid == 0) {
-      if (first) tr_start(T, s_x, tot, prm, summary, writer);
-      else if (tr_after_eval(T, tot, s_tot[T.acc_buf], prm, summary, writer)) T.acc_buf ^= 1;
+      TrState t;
+      int next = 0;   // 0: nothing to produce, 1: next candidate from the accepted totals, 2: from the totals just evaluated
+      if (first) next = tr_start(t, s_x, tot, prm, summary, writer, s_trace, true) ? 2 : 0;
+      else {
+        tr_copy(t, T);
+        next = tr_after_eval(t, tot, prm, s_trace, true);
+        if (next == 2) t.acc_buf ^= 1;
+      }
+      if (next) tr_next_candidate(t, next == 2 ? tot : s_tot[t.acc_buf], prm, s_trace, true);
+      tr_copy(T, t);
     }
     first = false;
     __syncthreads();
@@ -643,11 +687,12 @@ __device__ __forceinline__ void lm_solve_body(const Batch<LmArgs>& B, const LmPa
   } while (T.go);
   if (writer) {
     if (GENERAL && px.world > 1) *px.seq = seq0 + (unsigned long long)pass;
-    tr_finish(T, x7, summary);
+    tr_finish(T, x7, summary, s_trace);
     summary->cyc_total = clock64() - clk0;
     summary->cyc_eval = cyc_eval;
     summary->cyc_chol = cyc_tr;
-    summary->cyc_plus = pass;
+    summary->cyc_plus = cyc_blocks;    // residual blocks of this thread (the reductions are cyc_eval - cyc_plus - cyc_grad)
+    summary->cyc_grad = cyc_barrier;   // cluster barriers
     if (integrate && world7) {
       // laserOdometry.cpp:504-505  t_w += q_w * t_last_curr ; q_w = q_w * q_last_curr
       const V3 u{world7[0], world7[1], world7[2]};
@@ -712,7 +757,8 @@ __global__ void __launch_bounds__(NT, 1) k_lm_eval_shard(const BlockRec* __restr
   int pass = 0;
   if (active) {
     const BlockRec rb0 = load_first_block(blocks, n, cluster.block_rank());
-    cluster_evaluate<true>(cluster, blocks, n, rb0, s_x, huber_a, s_red, s_part, s_in, s_tot, pass);
+    long long cyc_unused0 = 0, cyc_unused1 = 0;
+    cluster_evaluate<true>(cluster, blocks, n, rb0, s_x, huber_a, s_red, s_part, s_in, s_tot, pass, cyc_unused0, cyc_unused1);
     if (cluster.block_rank() == 0 && tid < 32) local32[tid] = tid < RS ? s_tot[tid] : 0.0;
   } else if (cluster.block_rank() == 0 && tid < 32) {
     local32[tid] = 0.0;
@@ -724,8 +770,14 @@ __global__ void k_lm_tr_shard(void* state, const double* __restrict__ tot32, dou
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   TrState& T = *reinterpret_cast<TrState*>(state);
   bool keep = false;
-  if (first) { tr_start(T, x7, tot32, prm, summary, true); keep = true; }
-  else if (T.go) keep = tr_after_eval(T, tot32, T.acc, prm, summary, true);
+  if (first) {
+    if (tr_start(T, x7, tot32, prm, summary, true, summary->trace, true)) tr_next_candidate(T, tot32, prm, summary->trace, true);
+    keep = true;
+  } else if (T.go) {
+    const int next = tr_after_eval(T, tot32, prm, summary->trace, true);
+    keep = next == 2;
+    if (next) tr_next_candidate(T, keep ? tot32 : T.acc, prm, summary->trace, true);
+  }
   if (keep) { for (int k = 0; k < 28; ++k) T.acc[k] = tot32[k]; }
   if (last || !T.go) {
     if (last && T.go) { T.go = 0; }   // cannot happen: the schedule covers max_iters evaluations
