@@ -6,6 +6,9 @@
 // (middle-split on the widest bbox dimension, branch-and-bound on per-dimension box distances).
 // Deviation, declared: FLANN resolves exact-distance ties by traversal order; here ties are resolved by the
 // smaller original index so that the result is a function of the input only (SURVEY.md 8a "KD").
+// PINNED (the one part of the oracle that is): tests/test_oracle_vs_flann.py compares this file with a real FLANN
+// build -- the copy OpenCV vendors, cv2.flann_Index with KDTREE_SINGLE / leaf_max_size 15 -- on random clouds and on
+// the searches of both registration stages: identical neighbour lists (tie rows as sets), bit-identical distances.
 #include <algorithm>
 #include <cmath>
 #include "oracle.h"

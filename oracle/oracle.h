@@ -5,6 +5,9 @@
 // Eigen unpinned).  This directory is a dependency-free CPU restatement of the hot path, following the
 // reference line by line where the code is in-tree and the libraries' published algorithms where not.
 //
+// One exception to "unpinned": the k-NN search (kdtree.cc) is checked against a real FLANN build, the copy OpenCV
+// vendors (tests/test_oracle_vs_flann.py).  Ceres, PCL's VoxelGrid and Eigen remain restated from their published algorithms.
+//
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
 #pragma once
 #include <cstdint>
