@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <deque>
 #include <functional>
+#include <iostream>
 #include <map>
 #include <memory>
 #include <string>
@@ -67,7 +68,9 @@ class NodeHandle {
   explicit NodeHandle(const std::string&) {}
   template <typename M> Publisher advertise(const std::string& topic, int) { return Publisher(topic); }
   template <typename M> Subscriber subscribe(const std::string& topic, int, void (*cb)(const std::shared_ptr<M const>&)) {
-    shim::Bus::get().subscribers[topic].push_back([cb](const std::shared_ptr<const void>& p) { cb(std::static_pointer_cast<const M>(p)); });
+    auto& subs = shim::Bus::get().subscribers[topic];
+    subs.clear();   // one subscriber per topic and process: a driver may enter the node's main() more than once
+    subs.push_back([cb](const std::shared_ptr<const void>& p) { cb(std::static_pointer_cast<const M>(p)); });
     return Subscriber();
   }
   template <typename T> bool param(const std::string& name, T& var, const T& def) const { return lookup(name, var, def); }

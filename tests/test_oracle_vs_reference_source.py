@@ -182,3 +182,72 @@ def test_canonical_tie_order_changes_nothing_on_these_scans(orc, synth):
     want = orc.Features(raw, ns, mr, mode=orc.SORT_CANONICAL)
     for name in ("full", "sharp", "less_sharp", "flat", "less_flat"):
         assert np.array_equal(got[name].view(np.uint32), getattr(want, name).view(np.uint32)), name
+
+
+# ------------------------------------------------------------------------------------------------ laserOdometry.cpp
+class RefOdometry:
+    def __init__(self, lib):
+        self.lib = lib
+        fp = C.POINTER(C.c_float); dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
+        lib.ref_odom_init.argtypes = [C.c_int]
+        lib.ref_odom_process.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_double]
+        lib.ref_odom_state.argtypes = [dp, dp, dp, dp, ip]
+        lib.ref_odom_published_pose.argtypes = [dp, dp]; lib.ref_odom_published_pose.restype = C.c_long
+        lib.ref_odom_cloud.argtypes = [C.c_char_p, fp, C.c_int]
+        lib.ref_odom_transform_to_start.argtypes = [fp, fp]
+        lib.ref_odom_init(1)
+
+    def process(self, f, stamp):
+        a = [np.ascontiguousarray(x, np.float32) for x in (f.sharp, f.less_sharp, f.flat, f.less_flat, f.full)]
+        args = []
+        for x in a:
+            args += [x.ctypes.data_as(C.POINTER(C.c_float)), x.shape[0]]
+        self.lib.ref_odom_process(*args, float(stamp))
+        q = np.zeros(4); t = np.zeros(3); qw = np.zeros(4); tw = np.zeros(3); cnt = np.zeros(2, np.int32)
+        dp = C.POINTER(C.c_double)
+        self.lib.ref_odom_state(q.ctypes.data_as(dp), t.ctypes.data_as(dp), qw.ctypes.data_as(dp), tw.ctypes.data_as(dp), cnt.ctypes.data_as(C.POINTER(C.c_int)))
+        pq = np.zeros(4); pt = np.zeros(3)
+        n_pub = self.lib.ref_odom_published_pose(pq.ctypes.data_as(dp), pt.ctypes.data_as(dp))
+        return {"q": q, "t": t, "qw": qw, "tw": tw, "counts": cnt, "pub_q": pq, "pub_t": pt, "n_pub": n_pub}
+
+    def cloud(self, topic):
+        n = self.lib.ref_odom_cloud(topic.encode(), None, 0)
+        a = np.zeros((max(n, 0), 4), np.float32)
+        if n > 0:
+            self.lib.ref_odom_cloud(topic.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), n)
+        return a
+
+
+def _private_copy(name, tag):
+    _ref_lib(name)
+    import shutil, tempfile
+    path = os.path.join(tempfile.mkdtemp(prefix="ref_"), name.replace(".so", "_%s.so" % tag))
+    shutil.copy(os.path.join(REF_DIR, name), path)
+    return C.CDLL(path)
+
+
+@pytest.mark.parametrize("sensor,n_az,scans", [("VLP-16", 900, 6), ("HDL-64", None, 4)])
+def test_laser_odometry_source_equals_oracle_odometry(orc, synth, sensor, n_az, scans):
+    """the reference's laserOdometry.cpp (its own TransformToStart, correspondence search, block construction, pose
+    integration and cloud swap; ceres::Solve = oracle/lm.cc behind the stand-in) run scan after scan gives bit-identical
+    q_last_curr / t_last_curr, world pose and correspondence counts to oracle/odometry.cc, and republishes the clouds unchanged"""
+    ns, _, mr = synth.SENSORS[sensor][:3]
+    ref = RefOdometry(_private_copy("libref_odometry.so", "%s_%d" % (sensor, scans)))
+    od = orc.Odometry()
+    q = np.array([0, 0, 0, 1.0]); t = np.zeros(3); qw = q.copy(); tw = t.copy()
+    moved = 0.0
+    for k in range(scans):
+        raw = synth.scan(sensor, k, n_az=n_az) if n_az else synth.scan(sensor, k)
+        f = orc.Features(raw, ns, mr, mode=orc.SORT_LITERAL)
+        got = ref.process(f, stamp=0.1 * (k + 1))
+        if k > 0:
+            q, t, info = od.register(f.sharp, f.flat, q, t)
+            qw, tw = orc.integrate_pose(qw, tw, q, t)
+            assert got["counts"].tolist() == [info["corner_corr"], info["plane_corr"]], (k, got["counts"], info)
+            moved = max(moved, float(np.abs(t).max()))
+        od.set_last(f.less_sharp, f.less_flat)
+        assert np.array_equal(got["q"], q) and np.array_equal(got["t"], t), (k, got["q"] - q, got["t"] - t)
+        assert np.array_equal(got["qw"], qw) and np.array_equal(got["tw"], tw), k
+        assert got["n_pub"] == k + 1 and np.array_equal(got["pub_q"], qw) and np.array_equal(got["pub_t"], tw)
+        assert np.array_equal(ref.cloud("/laser_cloud_corner_last"), f.less_sharp) and np.array_equal(ref.cloud("/laser_cloud_surf_last"), f.less_flat)
+    assert moved > 0.05     # the trajectory moves: the comparison is not between two identities
