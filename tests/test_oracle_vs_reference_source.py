@@ -251,3 +251,117 @@ def test_laser_odometry_source_equals_oracle_odometry(orc, synth, sensor, n_az, 
         assert got["n_pub"] == k + 1 and np.array_equal(got["pub_q"], qw) and np.array_equal(got["pub_t"], tw)
         assert np.array_equal(ref.cloud("/laser_cloud_corner_last"), f.less_sharp) and np.array_equal(ref.cloud("/laser_cloud_surf_last"), f.less_flat)
     assert moved > 0.05     # the trajectory moves: the comparison is not between two identities
+
+
+# ------------------------------------------------------------------------------------------------ laserMapping.cpp
+NCUBE = 21 * 21 * 11
+
+
+class RefMapping:
+    def __init__(self, lib, line_res, plane_res, sort_mode):
+        self.lib = lib
+        fp = C.POINTER(C.c_float); dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
+        lib.ref_map_init.argtypes = [C.c_double, C.c_double, C.c_int]
+        lib.ref_map_process.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, dp, dp, C.c_double]
+        lib.ref_map_state.argtypes = [dp, dp, dp, ip, ip, ip]
+        lib.ref_map_cube.argtypes = [C.c_int, C.c_int, fp, C.c_int]
+        lib.ref_map_cube_sizes.argtypes = [C.c_int, ip]
+        lib.ref_map_published_pose.argtypes = [dp, dp]; lib.ref_map_published_pose.restype = C.c_long
+        lib.ref_map_init(line_res, plane_res, sort_mode)
+
+    def process(self, corner_last, surf_last, full, q, t, stamp):
+        a = [np.ascontiguousarray(x, np.float32) for x in (corner_last, surf_last, full)]
+        q = np.ascontiguousarray(q, np.float64); t = np.ascontiguousarray(t, np.float64)
+        dp = C.POINTER(C.c_double); fp = C.POINTER(C.c_float)
+        self.lib.ref_map_process(a[0].ctypes.data_as(fp), a[0].shape[0], a[1].ctypes.data_as(fp), a[1].shape[0], a[2].ctypes.data_as(fp), a[2].shape[0],
+                                 q.ctypes.data_as(dp), t.ctypes.data_as(dp), float(stamp))
+        pose = np.zeros(7); qm = np.zeros(4); tm = np.zeros(3); cen = np.zeros(3, np.int32); fr = np.zeros(1, np.int32); nv = np.zeros(1, np.int32)
+        ip = C.POINTER(C.c_int)
+        self.lib.ref_map_state(pose.ctypes.data_as(dp), qm.ctypes.data_as(dp), tm.ctypes.data_as(dp), cen.ctypes.data_as(ip), fr.ctypes.data_as(ip), nv.ctypes.data_as(ip))
+        pq = np.zeros(4); pt = np.zeros(3)
+        n_pub = self.lib.ref_map_published_pose(pq.ctypes.data_as(dp), pt.ctypes.data_as(dp))
+        return {"pose": pose, "q_wmap_wodom": qm, "t_wmap_wodom": tm, "centre": tuple(int(v) for v in cen), "frames": int(fr[0]),
+                "pub": np.concatenate([pq, pt]), "n_pub": n_pub}
+
+    def sizes(self, which):
+        s = np.zeros(NCUBE, np.int32)
+        self.lib.ref_map_cube_sizes(which, s.ctypes.data_as(C.POINTER(C.c_int)))
+        return s
+
+    def cube(self, which, index, n):
+        a = np.zeros((n, 4), np.float32)
+        if n:
+            self.lib.ref_map_cube(which, index, a.ctypes.data_as(C.POINTER(C.c_float)), n)
+        return a
+
+
+def _compare_cube_stores(ref, cm, tag):
+    """all 2 x 4851 cubes: sizes, and the contents of every non-empty cube, bit for bit"""
+    nonempty = 0
+    for which in (0, 1):
+        sizes = ref.sizes(which)
+        for idx in range(NCUBE):
+            want = cm.cube(which, idx) if sizes[idx] or idx % 97 == 0 else None
+            if want is None:
+                continue
+            assert want.shape[0] == sizes[idx], (tag, which, idx, want.shape[0], sizes[idx])
+            if sizes[idx]:
+                nonempty += 1
+                assert np.array_equal(ref.cube(which, idx, int(sizes[idx])).view(np.uint32), want.view(np.uint32)), (tag, which, idx)
+    return nonempty
+
+
+def test_laser_mapping_source_ring_buffer_scrolls_like_the_oracle(orc):
+    """thin clouds (no optimisation: the pose is the odometry pose) along a path that scrolls the 21 x 21 x 11 ring buffer in all
+    six directions: centre indices, T_wmap_wodom and EVERY cube of the reference's laserCloudCornerArray / laserCloudSurfArray
+    (laserMapping.cpp:309-505 shift loops, :736-801 insertion + per-cube VoxelGrid) equal oracle/cubemap.cc bit for bit"""
+    rng = np.random.default_rng(11)
+    ref = RefMapping(_private_copy("libref_mapping.so", "scroll"), 0.4, 0.8, orc.SORT_CANONICAL)
+    cm = orc.CubeMap()
+    ident = np.array([0, 0, 0, 1.0])
+    path = [(0, 0, 0), (60, -35, 12), (130, -80, 30), (260, -170, 75), (420, -290, 140), (300, -100, 60), (-90, 40, -30),
+            (-400, 380, -160), (-700, 600, -260), (-640, 610, -250)]
+    for k, t in enumerate(path):
+        t = np.array(t, float)
+        corner = (rng.normal(size=(6, 4)) * [8, 8, 2, 0]).astype(np.float32)
+        surf = (rng.normal(size=(300, 4)) * [30, 30, 3, 0]).astype(np.float32)
+        pose, info = cm.step(corner, surf, ident, t, 0.4, 0.8, sort_mode=orc.SORT_CANONICAL)
+        got = ref.process(corner, surf, surf, ident, t, stamp=0.1 * (k + 1))
+        so = cm.state()
+        assert got["frames"] == k + 1 and got["n_pub"] == k + 1
+        assert np.array_equal(got["pose"], pose) and np.array_equal(got["pub"], pose) and not info["optimised"]
+        assert got["centre"] == so["centre"], (k, got["centre"], so["centre"])
+        assert np.array_equal(got["q_wmap_wodom"], so["q_wmap_wodom"]) and np.array_equal(got["t_wmap_wodom"], so["t_wmap_wodom"])
+        assert _compare_cube_stores(ref, cm, k) >= 2
+
+
+@pytest.mark.parametrize("mode", ["canonical", "literal"])
+def test_laser_mapping_source_equals_oracle_mapping_loop(orc, synth, mode):
+    """the whole alaserMapping frame of the reference's own source (pose hand-off, shift, submap gather, stack filters, 5-NN,
+    line / plane fits, two ceres::Solve passes, transformUpdate, insertion, per-cube re-filter) over a VLP-16 trajectory equals
+    oracle/cubemap.cc + mapping.cc bit for bit: refined pose, T_wmap_wodom, and every cube"""
+    sm = orc.SORT_CANONICAL if mode == "canonical" else orc.SORT_LITERAL
+    ns, _, mr = synth.SENSORS["VLP-16"][:3]
+    ref = RefMapping(_private_copy("libref_mapping.so", "loop_" + mode), 0.2, 0.4, sm)     # the VLP-16 launch file's resolutions
+    cm = orc.CubeMap()
+    od = orc.Odometry()
+    q = np.array([0, 0, 0, 1.0]); t = np.zeros(3); qw = q.copy(); tw = t.copy()
+    optimised = 0
+    refined = 0.0
+    for k in range(6):
+        f = orc.Features(synth.scan("VLP-16", k, n_az=900), ns, mr, mode=sm)
+        if k > 0:
+            q, t, _ = od.register(f.sharp, f.flat, q, t)
+            qw, tw = orc.integrate_pose(qw, tw, q, t)
+        od.set_last(f.less_sharp, f.less_flat)
+        pose, info = cm.step(f.less_sharp, f.less_flat, qw, tw, 0.2, 0.4, sort_mode=sm)
+        got = ref.process(f.less_sharp, f.less_flat, f.full, qw, tw, stamp=0.1 * (k + 1))
+        so = cm.state()
+        optimised += int(info["optimised"])
+        refined = max(refined, float(np.abs(pose[4:] - tw).max()))
+        assert np.array_equal(got["pose"], pose), (k, got["pose"] - pose)
+        assert np.array_equal(got["pub"], pose) and got["n_pub"] == k + 1
+        assert got["centre"] == so["centre"]
+        assert np.array_equal(got["q_wmap_wodom"], so["q_wmap_wodom"]) and np.array_equal(got["t_wmap_wodom"], so["t_wmap_wodom"])
+        assert _compare_cube_stores(ref, cm, k) >= 2
+    assert optimised >= 4 and refined > 0      # the optimisation ran and moved the pose: not a comparison of two hand-offs
