@@ -1,4 +1,4 @@
-// ORACLE (test infrastructure, NOT product code) -- see oracle.h.  PARITY UNPINNED.
+// ORACLE (test infrastructure, NOT product code) -- see oracle.h.  Pinned to the reference's laserMapping.cpp source by tests/test_oracle_vs_reference_source.py.
 //
 // The map cube store of alaserMapping and the per-frame loop around it (laserMapping.cpp:74-108 state, :142-163
 // pose hand-off, :309-529 centre cube / shift / gather, :541-550 stack filters, :554-734 optimisation through

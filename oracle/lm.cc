@@ -5,7 +5,7 @@
 //   TrustRegionMinimizer + LevenbergMarquardtStrategy + DENSE_QR, max_num_iterations = 4, all other options default.
 // Ceres is NOT in /root/reference (un-vendored; 1.12.0 pinned only by docker/Dockerfile:3): the control flow below
 // follows Ceres' published trust_region_minimizer.cc / levenberg_marquardt_strategy.cc / residual_block.cc /
-// corrector.cc / loss_function.cc / local_parameterization.cc (SURVEY.md 8a "R7 spec").  PARITY UNPINNED.
+// corrector.cc / loss_function.cc / local_parameterization.cc (SURVEY.md 8a "R7 spec").  The functors are pinned to the reference's lidarFactor.hpp source; the minimiser is a restatement of Ceres that cannot be checked here.
 #include <algorithm>
 #include <cmath>
 #include <cstring>

@@ -1,12 +1,16 @@
-// ORACLE (test infrastructure, NOT product code).  PARITY UNPINNED: the reference
+// ORACLE (test infrastructure, NOT product code).  PARITY: in-tree code pinned to the reference's own source text
+// (oracle/_ref + tests/test_oracle_vs_reference_source.py), k-NN pinned to a real FLANN, Ceres / VoxelGrid / Eigen restated.  The reference
 // (HKUST-Aerial-Robotics/A-LOAM @ e51f88c) ships no tests, golden vectors or fixtures, it cannot be
 // compiled here (needs ROS + PCL + FLANN + Eigen + Ceres, none present, no network), and part of the
 // arithmetic lives in un-vendored third-party code (Ceres 1.12.0, PCL 1.8.0 -- docker/Dockerfile:3-4;
 // Eigen unpinned).  This directory is a dependency-free CPU restatement of the hot path, following the
 // reference line by line where the code is in-tree and the libraries' published algorithms where not.
 //
-// One exception to "unpinned": the k-NN search (kdtree.cc) is checked against a real FLANN build, the copy OpenCV
-// vendors (tests/test_oracle_vs_flann.py).  Ceres, PCL's VoxelGrid and Eigen remain restated from their published algorithms.
+// What IS pinned: (1) every in-tree stage -- oracle/_ref compiles the reference's own lidarFactor.hpp, scanRegistration.cpp,
+// laserOdometry.cpp and laserMapping.cpp unmodified against stand-in headers (oracle/ref_shim) and
+// tests/test_oracle_vs_reference_source.py finds features.cc / odometry.cc / mapping.cc / cubemap.cc bit-identical to them;
+// (2) the k-NN search (kdtree.cc) against a real FLANN build, the copy OpenCV vendors (tests/test_oracle_vs_flann.py).
+// Ceres' minimiser, PCL's VoxelGrid and Eigen's decompositions remain restated from their published algorithms.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
 #pragma once

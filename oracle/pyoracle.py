@@ -2,7 +2,7 @@
 
 ORACLE = test infrastructure.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 ``--impl reference`` legs may import this module; the product path (a-loam_b200) never does.
-PARITY UNPINNED (see oracle/oracle.h).
+Parity status: see oracle/oracle.h (in-tree code pinned to the reference's source, k-NN to a real FLANN; Ceres / VoxelGrid / Eigen restated).
 """
 import ctypes as C
 import os

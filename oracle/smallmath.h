@@ -1,4 +1,4 @@
-// ORACLE (test infrastructure, NOT product code) -- parity unpinned: the reference ships no tests or
+// ORACLE (test infrastructure, NOT product code) -- third-party semantics, restated (not checkable here): the reference ships no tests or
 // golden vectors and Ceres/PCL/Eigen are absent here, so these are restatements from the published
 // semantics of those libraries.
 //
