@@ -172,16 +172,18 @@ def test_scan_registration_source_with_nan_and_close_points(orc, synth):
         assert np.array_equal(got[name].view(np.uint32), getattr(want, name).view(np.uint32)), name
 
 
-def test_canonical_tie_order_changes_nothing_on_these_scans(orc, synth):
+@pytest.mark.parametrize("sensor,n_az,scans", [("VLP-16", 900, 6), ("HDL-32", None, 3), ("HDL-64", None, 4)])
+def test_canonical_tie_order_changes_nothing_on_these_scans(orc, synth, sensor, n_az, scans):
     """the CUDA path defines ties by index (CANONICAL); on the synthetic scans the literal std::sort order of the reference
     source gives the same features, so GPU == oracle(CANONICAL) == reference source"""
-    ns, _, mr = synth.SENSORS["HDL-64"][:3]
+    ns, _, mr = synth.SENSORS[sensor][:3]
     ref = ref_registration(ns, mr)
-    raw = synth.scan("HDL-64", 3)
-    got = ref.run(raw, orc.SORT_CANONICAL)          # the reference's own std::sort for the picks, canonical ties in VoxelGrid
-    want = orc.Features(raw, ns, mr, mode=orc.SORT_CANONICAL)
-    for name in ("full", "sharp", "less_sharp", "flat", "less_flat"):
-        assert np.array_equal(got[name].view(np.uint32), getattr(want, name).view(np.uint32)), name
+    for k in range(scans):
+        raw = synth.scan(sensor, k, n_az=n_az) if n_az else synth.scan(sensor, k)
+        got = ref.run(raw, orc.SORT_CANONICAL)          # the reference's own std::sort for the picks, canonical ties in VoxelGrid
+        want = orc.Features(raw, ns, mr, mode=orc.SORT_CANONICAL)
+        for name in ("full", "sharp", "less_sharp", "flat", "less_flat"):
+            assert np.array_equal(got[name].view(np.uint32), getattr(want, name).view(np.uint32)), (sensor, k, name)
 
 
 # ------------------------------------------------------------------------------------------------ laserOdometry.cpp
