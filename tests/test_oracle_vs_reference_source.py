@@ -5,30 +5,17 @@ The third-party semantics behind the stand-ins (VoxelGrid, kd-tree, Eigen's oper
 shared by both sides of the comparison.  The libraries are built into oracle/_ref/ by `make -C oracle ref` where
 /root/reference exists; elsewhere the prebuilt files are used, or the tests skip."""
 import ctypes as C
-import os
-import subprocess
 
 import numpy as np
 import pytest
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_DIR = os.path.join(ROOT, "oracle", "_ref")
-
-
-def _ref_lib(name):
-    if os.path.isdir("/root/reference/src"):
-        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "_ref/" + name], capture_output=True, text=True)
-        assert r.returncode == 0, r.stdout + r.stderr
-    path = os.path.join(REF_DIR, name)
-    if not os.path.exists(path):
-        pytest.skip("oracle/_ref/%s is not built and /root/reference is not present" % name)
-    return C.CDLL(path)
+from refsource import NCUBE, RefMapping, RefOdometry, private_copy, ref_lib, ref_registration
 
 
 # ------------------------------------------------------------------------------------------------ lidarFactor.hpp
 @pytest.fixture(scope="module")
 def ref_factor():
-    lib = _ref_lib("libref_factor.so")
+    lib = ref_lib("libref_factor.so")
     dp = C.POINTER(C.c_double)
     lib.ref_factor_eval.argtypes = [C.c_int, dp, C.c_double, dp, dp, dp, dp, dp]
     lib.ref_factor_eval.restype = C.c_int
@@ -77,64 +64,13 @@ def test_the_three_cost_functions_of_lidarFactor_hpp(orc, ref_factor, seed):
 
 
 # ------------------------------------------------------------------------------------------------ scanRegistration.cpp
-TOPICS = {"full": "/velodyne_cloud_2", "sharp": "/laser_cloud_sharp", "less_sharp": "/laser_cloud_less_sharp",
-          "flat": "/laser_cloud_flat", "less_flat": "/laser_cloud_less_flat"}
-
-
-class RefRegistration:
-    """the reference's scanRegistration node, one process-wide instance per N_SCANS (its state is file-scope globals)"""
-
-    def __init__(self, lib, n_scans, min_range):
-        self.lib = lib
-        fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int)
-        lib.ref_reg_init.argtypes = [C.c_int, C.c_double]
-        lib.ref_reg_process.argtypes = [fp, C.c_int, C.c_int, C.c_double]
-        lib.ref_reg_cloud.argtypes = [C.c_char_p, fp, C.c_int]
-        lib.ref_reg_arrays.argtypes = [fp, ip, ip, C.c_int]
-        lib.ref_reg_voxel_sort_mode.argtypes = [C.c_int]
-        lib.ref_reg_published.argtypes = [C.c_char_p]; lib.ref_reg_published.restype = C.c_long
-        lib.ref_reg_init(n_scans, float(min_range))
-
-    def run(self, raw, sort_mode):
-        raw = np.ascontiguousarray(raw, np.float32)
-        self.lib.ref_reg_voxel_sort_mode(sort_mode)
-        before = self.lib.ref_reg_published(b"/laser_cloud_less_flat")
-        self.lib.ref_reg_process(raw.ctypes.data_as(C.POINTER(C.c_float)), raw.shape[0], raw.shape[1], 0.0)
-        assert self.lib.ref_reg_published(b"/laser_cloud_less_flat") == before + 1, "the reference's handler did not publish"
-        out = {}
-        for k, topic in TOPICS.items():
-            n = self.lib.ref_reg_cloud(topic.encode(), None, 0)
-            a = np.zeros((n, 4), np.float32)
-            self.lib.ref_reg_cloud(topic.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), n)
-            out[k] = a
-        n = out["full"].shape[0]
-        out["curvature"] = np.zeros(n, np.float32); out["label"] = np.zeros(n, np.int32); out["picked"] = np.zeros(n, np.int32)
-        self.lib.ref_reg_arrays(out["curvature"].ctypes.data_as(C.POINTER(C.c_float)), out["label"].ctypes.data_as(C.POINTER(C.c_int)),
-                                out["picked"].ctypes.data_as(C.POINTER(C.c_int)), n)
-        return out
-
-
-_REG = {}
-
-
-def ref_registration(n_scans, min_range):
-    """one copy of the library per scan-line count: N_SCANS and the publishers are set once, in the reference's main()"""
-    key = (n_scans, float(min_range))
-    if key not in _REG:
-        _ref_lib("libref_registration.so")
-        import shutil, tempfile
-        d = tempfile.mkdtemp(prefix="ref_reg_")
-        path = os.path.join(d, "libref_registration_%d.so" % n_scans)
-        shutil.copy(os.path.join(REF_DIR, "libref_registration.so"), path)    # a private copy = private globals
-        _REG[key] = RefRegistration(C.CDLL(path), n_scans, min_range)
-    return _REG[key]
 
 
 def test_which_libm_overloads_the_reference_source_sees():
     """scanRegistration.cpp:166 calls atan / sqrt unqualified on floats: with headers that never pull <math.h>'s std overloads
     into the global namespace (GCC 5 of the reference's docker image; this build) they are the C double functions, which is
     what oracle/features.cc and the CUDA kernel restate"""
-    lib = _ref_lib("libref_registration.so")
+    lib = ref_lib("libref_registration.so")
     assert lib.ref_reg_atan_result_bytes() == 8 and lib.ref_reg_sqrt_result_bytes() == 8
 
 
@@ -172,7 +108,7 @@ def test_scan_registration_source_with_nan_and_close_points(orc, synth):
         assert np.array_equal(got[name].view(np.uint32), getattr(want, name).view(np.uint32)), name
 
 
-@pytest.mark.parametrize("sensor,n_az,scans", [("VLP-16", 900, 6), ("HDL-32", None, 3), ("HDL-64", None, 4)])
+@pytest.mark.parametrize("sensor,n_az,scans", [("VLP-16", 900, 6), ("VLP-16", None, 4), ("HDL-32", None, 4), ("HDL-64", None, 4)])
 def test_canonical_tie_order_changes_nothing_on_these_scans(orc, synth, sensor, n_az, scans):
     """the CUDA path defines ties by index (CANONICAL); on the synthetic scans the literal std::sort order of the reference
     source gives the same features, so GPU == oracle(CANONICAL) == reference source"""
@@ -187,54 +123,13 @@ def test_canonical_tie_order_changes_nothing_on_these_scans(orc, synth, sensor, 
 
 
 # ------------------------------------------------------------------------------------------------ laserOdometry.cpp
-class RefOdometry:
-    def __init__(self, lib):
-        self.lib = lib
-        fp = C.POINTER(C.c_float); dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
-        lib.ref_odom_init.argtypes = [C.c_int]
-        lib.ref_odom_process.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_double]
-        lib.ref_odom_state.argtypes = [dp, dp, dp, dp, ip]
-        lib.ref_odom_published_pose.argtypes = [dp, dp]; lib.ref_odom_published_pose.restype = C.c_long
-        lib.ref_odom_cloud.argtypes = [C.c_char_p, fp, C.c_int]
-        lib.ref_odom_transform_to_start.argtypes = [fp, fp]
-        lib.ref_odom_init(1)
-
-    def process(self, f, stamp):
-        a = [np.ascontiguousarray(x, np.float32) for x in (f.sharp, f.less_sharp, f.flat, f.less_flat, f.full)]
-        args = []
-        for x in a:
-            args += [x.ctypes.data_as(C.POINTER(C.c_float)), x.shape[0]]
-        self.lib.ref_odom_process(*args, float(stamp))
-        q = np.zeros(4); t = np.zeros(3); qw = np.zeros(4); tw = np.zeros(3); cnt = np.zeros(2, np.int32)
-        dp = C.POINTER(C.c_double)
-        self.lib.ref_odom_state(q.ctypes.data_as(dp), t.ctypes.data_as(dp), qw.ctypes.data_as(dp), tw.ctypes.data_as(dp), cnt.ctypes.data_as(C.POINTER(C.c_int)))
-        pq = np.zeros(4); pt = np.zeros(3)
-        n_pub = self.lib.ref_odom_published_pose(pq.ctypes.data_as(dp), pt.ctypes.data_as(dp))
-        return {"q": q, "t": t, "qw": qw, "tw": tw, "counts": cnt, "pub_q": pq, "pub_t": pt, "n_pub": n_pub}
-
-    def cloud(self, topic):
-        n = self.lib.ref_odom_cloud(topic.encode(), None, 0)
-        a = np.zeros((max(n, 0), 4), np.float32)
-        if n > 0:
-            self.lib.ref_odom_cloud(topic.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), n)
-        return a
-
-
-def _private_copy(name, tag):
-    _ref_lib(name)
-    import shutil, tempfile
-    path = os.path.join(tempfile.mkdtemp(prefix="ref_"), name.replace(".so", "_%s.so" % tag))
-    shutil.copy(os.path.join(REF_DIR, name), path)
-    return C.CDLL(path)
-
-
 @pytest.mark.parametrize("sensor,n_az,scans", [("VLP-16", 900, 6), ("HDL-64", None, 4)])
 def test_laser_odometry_source_equals_oracle_odometry(orc, synth, sensor, n_az, scans):
     """the reference's laserOdometry.cpp (its own TransformToStart, correspondence search, block construction, pose
     integration and cloud swap; ceres::Solve = oracle/lm.cc behind the stand-in) run scan after scan gives bit-identical
     q_last_curr / t_last_curr, world pose and correspondence counts to oracle/odometry.cc, and republishes the clouds unchanged"""
     ns, _, mr = synth.SENSORS[sensor][:3]
-    ref = RefOdometry(_private_copy("libref_odometry.so", "%s_%d" % (sensor, scans)))
+    ref = RefOdometry(private_copy("libref_odometry.so", "%s_%d" % (sensor, scans)))
     od = orc.Odometry()
     q = np.array([0, 0, 0, 1.0]); t = np.zeros(3); qw = q.copy(); tw = t.copy()
     moved = 0.0
@@ -256,45 +151,6 @@ def test_laser_odometry_source_equals_oracle_odometry(orc, synth, sensor, n_az, 
 
 
 # ------------------------------------------------------------------------------------------------ laserMapping.cpp
-NCUBE = 21 * 21 * 11
-
-
-class RefMapping:
-    def __init__(self, lib, line_res, plane_res, sort_mode):
-        self.lib = lib
-        fp = C.POINTER(C.c_float); dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
-        lib.ref_map_init.argtypes = [C.c_double, C.c_double, C.c_int]
-        lib.ref_map_process.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, dp, dp, C.c_double]
-        lib.ref_map_state.argtypes = [dp, dp, dp, ip, ip, ip]
-        lib.ref_map_cube.argtypes = [C.c_int, C.c_int, fp, C.c_int]
-        lib.ref_map_cube_sizes.argtypes = [C.c_int, ip]
-        lib.ref_map_published_pose.argtypes = [dp, dp]; lib.ref_map_published_pose.restype = C.c_long
-        lib.ref_map_init(line_res, plane_res, sort_mode)
-
-    def process(self, corner_last, surf_last, full, q, t, stamp):
-        a = [np.ascontiguousarray(x, np.float32) for x in (corner_last, surf_last, full)]
-        q = np.ascontiguousarray(q, np.float64); t = np.ascontiguousarray(t, np.float64)
-        dp = C.POINTER(C.c_double); fp = C.POINTER(C.c_float)
-        self.lib.ref_map_process(a[0].ctypes.data_as(fp), a[0].shape[0], a[1].ctypes.data_as(fp), a[1].shape[0], a[2].ctypes.data_as(fp), a[2].shape[0],
-                                 q.ctypes.data_as(dp), t.ctypes.data_as(dp), float(stamp))
-        pose = np.zeros(7); qm = np.zeros(4); tm = np.zeros(3); cen = np.zeros(3, np.int32); fr = np.zeros(1, np.int32); nv = np.zeros(1, np.int32)
-        ip = C.POINTER(C.c_int)
-        self.lib.ref_map_state(pose.ctypes.data_as(dp), qm.ctypes.data_as(dp), tm.ctypes.data_as(dp), cen.ctypes.data_as(ip), fr.ctypes.data_as(ip), nv.ctypes.data_as(ip))
-        pq = np.zeros(4); pt = np.zeros(3)
-        n_pub = self.lib.ref_map_published_pose(pq.ctypes.data_as(dp), pt.ctypes.data_as(dp))
-        return {"pose": pose, "q_wmap_wodom": qm, "t_wmap_wodom": tm, "centre": tuple(int(v) for v in cen), "frames": int(fr[0]),
-                "pub": np.concatenate([pq, pt]), "n_pub": n_pub}
-
-    def sizes(self, which):
-        s = np.zeros(NCUBE, np.int32)
-        self.lib.ref_map_cube_sizes(which, s.ctypes.data_as(C.POINTER(C.c_int)))
-        return s
-
-    def cube(self, which, index, n):
-        a = np.zeros((n, 4), np.float32)
-        if n:
-            self.lib.ref_map_cube(which, index, a.ctypes.data_as(C.POINTER(C.c_float)), n)
-        return a
 
 
 def _compare_cube_stores(ref, cm, tag):
@@ -318,7 +174,7 @@ def test_laser_mapping_source_ring_buffer_scrolls_like_the_oracle(orc):
     six directions: centre indices, T_wmap_wodom and EVERY cube of the reference's laserCloudCornerArray / laserCloudSurfArray
     (laserMapping.cpp:309-505 shift loops, :736-801 insertion + per-cube VoxelGrid) equal oracle/cubemap.cc bit for bit"""
     rng = np.random.default_rng(11)
-    ref = RefMapping(_private_copy("libref_mapping.so", "scroll"), 0.4, 0.8, orc.SORT_CANONICAL)
+    ref = RefMapping(private_copy("libref_mapping.so", "scroll"), 0.4, 0.8, orc.SORT_CANONICAL)
     cm = orc.CubeMap()
     ident = np.array([0, 0, 0, 1.0])
     path = [(0, 0, 0), (60, -35, 12), (130, -80, 30), (260, -170, 75), (420, -290, 140), (300, -100, 60), (-90, 40, -30),
@@ -344,7 +200,7 @@ def test_laser_mapping_source_equals_oracle_mapping_loop(orc, synth, mode):
     oracle/cubemap.cc + mapping.cc bit for bit: refined pose, T_wmap_wodom, and every cube"""
     sm = orc.SORT_CANONICAL if mode == "canonical" else orc.SORT_LITERAL
     ns, _, mr = synth.SENSORS["VLP-16"][:3]
-    ref = RefMapping(_private_copy("libref_mapping.so", "loop_" + mode), 0.2, 0.4, sm)     # the VLP-16 launch file's resolutions
+    ref = RefMapping(private_copy("libref_mapping.so", "loop_" + mode), 0.2, 0.4, sm)     # the VLP-16 launch file's resolutions
     cm = orc.CubeMap()
     od = orc.Odometry()
     q = np.array([0, 0, 0, 1.0]); t = np.zeros(3); qw = q.copy(); tw = t.copy()
