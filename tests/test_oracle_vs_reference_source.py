@@ -223,3 +223,35 @@ def test_laser_mapping_source_equals_oracle_mapping_loop(orc, synth, mode):
         assert np.array_equal(got["q_wmap_wodom"], so["q_wmap_wodom"]) and np.array_equal(got["t_wmap_wodom"], so["t_wmap_wodom"])
         assert _compare_cube_stores(ref, cm, k) >= 2
     assert optimised >= 4 and refined > 0      # the optimisation ran and moved the pose: not a comparison of two hand-offs
+
+
+# ------------------------------------------------------------------------------------------------ the three nodes chained
+def test_the_three_reference_nodes_chained_equal_the_oracle_chain(orc, synth):
+    """raw scans through the reference's scanRegistration -> laserOdometry -> laserMapping sources, each node fed with what the
+    previous one PUBLISHED (the topics of the real pipeline), against the oracle's extract -> register -> integrate -> mapping step:
+    /laser_odom_to_init and /aft_mapped_to_init equal the oracle's poses bit for bit on every frame"""
+    import types
+    ns, _, mr = synth.SENSORS["VLP-16"][:3]
+    reg = ref_registration(ns, mr)
+    odo = RefOdometry(private_copy("libref_odometry.so", "chain"))
+    mp = RefMapping(private_copy("libref_mapping.so", "chain"), 0.2, 0.4, orc.SORT_LITERAL)
+    cm = orc.CubeMap(); od = orc.Odometry()
+    q = np.array([0, 0, 0, 1.0]); t = np.zeros(3); qw = q.copy(); tw = t.copy()
+    drift = 0.0
+    for k in range(6):
+        raw = synth.scan("VLP-16", k, n_az=900)
+        stamp = 0.1 * (k + 1)
+        r = reg.run(raw, orc.SORT_LITERAL)
+        o = odo.process(types.SimpleNamespace(**{n: r[n] for n in ("sharp", "less_sharp", "flat", "less_flat", "full")}), stamp)
+        m = mp.process(odo.cloud("/laser_cloud_corner_last"), odo.cloud("/laser_cloud_surf_last"), odo.cloud("/velodyne_cloud_3"),
+                       o["pub_q"], o["pub_t"], stamp)
+        f = orc.Features(raw, ns, mr, mode=orc.SORT_LITERAL)
+        if k > 0:
+            q, t, _ = od.register(f.sharp, f.flat, q, t)
+            qw, tw = orc.integrate_pose(qw, tw, q, t)
+        od.set_last(f.less_sharp, f.less_flat)
+        pose, info = cm.step(f.less_sharp, f.less_flat, qw, tw, 0.2, 0.4, sort_mode=orc.SORT_LITERAL)
+        assert np.array_equal(np.concatenate([o["pub_q"], o["pub_t"]]), np.concatenate([qw, tw])), k
+        assert np.array_equal(m["pub"], pose), (k, m["pub"] - pose)
+        drift = max(drift, float(np.abs(pose[4:] - tw).max()))
+    assert drift > 0
